@@ -1,0 +1,148 @@
+/*
+ * pn2_abi.h -- C ABI of libpn2_b200.so, the B200 (sm_100a) implementation of the
+ * PointNet++ set-abstraction / feature-propagation geometry path and the
+ * multi-view 2D->3D feature lifting of
+ * ChengnanYu/Multi-modal-Learning-on-3D-Point-Clouds.
+ *
+ * Conventions (mirroring the reference's launcher seam, utils/src/*_gpu.h):
+ *   - every pointer is a DEVICE pointer into memory the caller owns; outputs
+ *     are caller-allocated; nothing is retained between calls;
+ *   - tensors are dense, row-major, fp32 / int32 exactly as the reference's;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *     stream); every call only enqueues work on it and returns;
+ *   - the return value is a pn2_status.  Unlike the reference (which prints
+ *     and calls exit(-1), e.g. utils/src/sampling_gpu.cu:39-43) a failure is
+ *     reported to the caller; pn2_last_error() gives the message.
+ *
+ * Each entry point names the reference interface it replaces.
+ */
+#ifndef PN2_ABI_H
+#define PN2_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN2_ABI_VERSION 1
+
+typedef enum pn2_status {
+    PN2_OK = 0,
+    PN2_ERR_INVALID_ARGUMENT = 1, /* bad dims / null pointer / misaligned pointer */
+    PN2_ERR_UNSUPPORTED = 2,      /* shape outside what the kernels implement */
+    PN2_ERR_CUDA = 3              /* a CUDA runtime call or launch failed */
+} pn2_status;
+
+/* Message for the last non-OK status returned on the calling thread ("" if none). */
+const char *pn2_last_error(void);
+int pn2_abi_version(void);
+/* Number of kernel launches this library has enqueued since load (all threads). */
+uint64_t pn2_launch_count(void);
+
+/* ---- the nine operators of the reference's `pointnet2_cuda` module -------------------- */
+
+/* furthest_point_sampling_wrapper (utils/src/pointnet2_api.cpp:19, utils/src/sampling.cpp:36-46,
+ * launcher utils/src/sampling_gpu.cu:211-253).  xyz (B,N,3) -> idx (B,M) int32, idx[:,0]=0.
+ * `temp` is the reference's (B,N) scratch argument; it is neither read nor written here
+ * (running minima live in registers) and may be NULL. */
+int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, void *stream);
+
+/* furthest_point_sampling + gather_operation of the picked coordinates in one launch
+ * (model/pointnet_util.py:34-35: FPS, gather, and two layout copies).  new_xyz (B,M,3). */
+int pn2_fps_gather(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, float *new_xyz, void *stream);
+
+/* gather_points_wrapper (pointnet2_api.cpp:16, sampling.cpp:11-20, sampling_gpu.cu:26-44).
+ * points (B,C,N), idx (B,M) -> out (B,C,M) */
+int pn2_gather_points(int b, int c, int n, int npoints, const float *points, const int32_t *idx, float *out, void *stream);
+
+/* gather_points_grad_wrapper (pointnet2_api.cpp:17, sampling.cpp:23-33, sampling_gpu.cu:65-83).
+ * grad_out (B,C,M), idx (B,M) -> grad_points (B,C,N) += ; caller pre-zeroes grad_points. */
+int pn2_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int32_t *idx, float *grad_points, void *stream);
+
+/* ball_query_wrapper (pointnet2_api.cpp:11, ball_query.cpp:14-25, ball_query_gpu.cu:48-62).
+ * new_xyz (B,M,3), xyz (B,N,3) -> idx (B,M,nsample).  The whole of idx is written
+ * (rows with an empty ball become zeros, as the reference's pre-zeroed buffer gives). */
+int pn2_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int32_t *idx, void *stream);
+
+/* group_points_wrapper (pointnet2_api.cpp:13, group_points.cpp:25-36, group_points_gpu.cu:69-83).
+ * points (B,C,N), idx (B,npoints,nsample) -> out (B,C,npoints,nsample) */
+int pn2_group_points(int b, int c, int n, int npoints, int nsample, const float *points, const int32_t *idx, float *out, void *stream);
+
+/* group_points_grad_wrapper (pointnet2_api.cpp:14, group_points.cpp:11-22, group_points_gpu.cu:28-44) */
+int pn2_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out, const int32_t *idx, float *grad_points, void *stream);
+
+/* three_nn_wrapper (pointnet2_api.cpp:21, interpolate.cpp:14-23, interpolate_gpu.cu:55-74).
+ * unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3) SQUARED distances, idx (B,n,3) */
+int pn2_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int32_t *idx, void *stream);
+
+/* three_interpolate_wrapper (pointnet2_api.cpp:22, interpolate.cpp:26-39, interpolate_gpu.cu:99-117).
+ * points (B,C,m), idx/weight (B,n,3) -> out (B,C,n) */
+int pn2_three_interpolate(int b, int c, int m, int n, const float *points, const int32_t *idx, const float *weight, float *out, void *stream);
+
+/* three_interpolate_grad_wrapper (pointnet2_api.cpp:23, interpolate.cpp:41-54, interpolate_gpu.cu:144-161).
+ * grad_out (B,C,n) -> grad_points (B,C,m) += ; caller pre-zeroes grad_points. */
+int pn2_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int32_t *idx, const float *weight, float *grad_points, void *stream);
+
+/* ---- multi-view lifting (utils/projection.py:166-256, model/pointnet2multiview.py:27-43,80-102) ---- */
+
+#define PN2_REDUCE_MAX 0   /* F.max_pool1d over views, model/pointnet2multiview.py:39 */
+#define PN2_REDUCE_FIRST 1 /* first view, later views fill all-zero columns, :93-98 */
+
+/* One launch for a whole batch of B clouds x V views: frustum test, projection, nearest-pixel
+ * (round-half-even) lookup, bounds + depth test, feature fetch and view reduction.
+ *   points (B,N,3); feats (B,V,C,H,W); depth (B,V,H,W); w2c (B,V,4,4) = inverse(camera_to_world);
+ *   corner2, corner4 (B,V,3) and normals (B,V,6,3) from compute_frustum_corners/normals
+ *   (utils/projection.py:25-95); intr[4] = {fx, fy, cx, cy} (host pointer).
+ *   out (B,C,N) fp32; pix (B,V,N) int32 = lifted pixel index v*W+u or -1 (may be NULL);
+ *   count (B,V) int32 = number of lifted points per view (may be NULL; must be pre-zeroed). */
+int pn2_lift_views(int b, int n, int v, int c, int h, int w, const float *points, const float *feats, const float *depth,
+                   const float *w2c, const float *corner2, const float *corner4, const float *normals, const float *intr,
+                   float depth_min, float depth_max, float accuracy, int reduce, float *out, int32_t *pix,
+                   int32_t *count, void *stream);
+
+/* ---- fused set-abstraction / feature-propagation blocks (model/pointnet_util.py:70-221) ---- */
+
+#define PN2_MAX_LAYERS 6
+
+/* A stack of 1x1-conv layers with eval-mode BatchNorm folded in:
+ *   y = act(W x + bias),  W (cout, cin) row-major fp32 (device), bias (cout) fp32 (device). */
+typedef struct pn2_mlp {
+    int num_layers;
+    int cin[PN2_MAX_LAYERS];
+    int cout[PN2_MAX_LAYERS];
+    int relu[PN2_MAX_LAYERS];
+    const float *weight[PN2_MAX_LAYERS];
+    const float *bias[PN2_MAX_LAYERS];
+} pn2_mlp;
+
+#define PN2_ORDER_XYZ_FIRST 0  /* SSG concat, model/pointnet_util.py:41 */
+#define PN2_ORDER_FEAT_FIRST 1 /* MSG concat, model/pointnet_util.py:157 */
+
+/* Grouping + shared MLP + max over nsample of one SA scale (model/pointnet_util.py:101-109,
+ * 152-166), channel-last activations:
+ *   xyz (B,N,3); feat (B,N,D) or NULL (D=0); new_xyz (B,M,3); idx (B,M,K) from pn2_ball_query;
+ *   out: element (b, p, ch) at out[(b*M + p)*out_stride + out_offset + ch], ch < cout[last]. */
+int pn2_sa_mlp_max(int b, int n, int m, int k, int d, const float *xyz, const float *feat, const float *new_xyz,
+                   const int32_t *idx, int order, const pn2_mlp *mlp, float *out, int out_stride, int out_offset,
+                   void *stream);
+
+/* Interpolation + skip concat + shared MLP of one FP block (model/pointnet_util.py:200-220),
+ * channel-last activations:
+ *   feat1 (B,n,D1) or NULL; feat2 (B,m,D2); idx/weight (B,n,3) (ignored when m == 1: the single
+ *   coarse feature row is repeated, model/pointnet_util.py:202-203); out (B,n,cout[last]). */
+int pn2_fp_mlp(int b, int n, int m, int d1, int d2, const float *feat1, const float *feat2, const int32_t *idx,
+               const float *weight, const pn2_mlp *mlp, float *out, void *stream);
+
+/* three_nn followed by the reference's weight computation (model/pointnet_util.py:205-208):
+ * dist = sqrt(dist2); clamp 1e-10; w = 1/dist; w /= sum.  -> idx (B,n,3), weight (B,n,3) */
+int pn2_three_nn_weights(int b, int n, int m, const float *unknown, const float *known, int32_t *idx, float *weight, void *stream);
+
+/* Layout helpers between the reference's channel-first tensors and channel-last activations:
+ * in (B,R,Cc) -> out (B,Cc,R) */
+int pn2_transpose(int b, int r, int c, const float *in, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PN2_ABI_H */

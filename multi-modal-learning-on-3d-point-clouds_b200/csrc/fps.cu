@@ -1,0 +1,275 @@
+// fps.cu -- furthest point sampling for sm_100a.
+//
+// Replaces furthest_point_sampling_kernel / _launcher of the reference
+// (utils/src/sampling_gpu.cu:93-253).  Result contract: idx[0] = 0, and round j
+// picks the point maximising temp[k] = min over previous picks of D(k, pick) under the total order
+//     (temp desc, bitrev_{log2 bs}(k mod bs) asc, k asc),   bs = largest pow2 <= min(N, 1024),
+// which is what the reference's per-thread strict-max scan + tree reduction produce.
+//
+// Design (not the reference's): the cloud lives ON CHIP for the whole kernel.  Each thread owns
+// P points (coordinates and running minimum in registers), so a round touches no global or L2
+// memory at all.  The arg-max is a single 64-bit key  (float bits of temp | ~tie key)  reduced with
+// two CREDUX.MAX per warp, one shared-memory hop and ONE block barrier per round (slots are
+// double-buffered by round parity); the reference spends 10 barriers and 20*N bytes of L2 traffic
+// per round.  Clouds larger than one CTA's registers are split over a thread-block cluster whose
+// CTAs exchange their local winners through distributed shared memory (fps_cluster_kernel).
+#include "common.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int QB = 22;  // low bits of the tie key hold q = k / bs; high bits hold bitrev(k mod bs)
+constexpr uint32_t QMASK = (1u << QB) - 1u;
+
+__device__ __forceinline__ void warp_argmax(uint32_t &hi, uint32_t &lo) {
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t l2 = (hi == mh) ? lo : 0u;
+    lo = __reduce_max_sync(0xffffffffu, l2);
+    hi = mh;
+}
+
+template <int T>
+struct Log2 {
+    static constexpr int value = 1 + Log2<T / 2>::value;
+};
+template <>
+struct Log2<1> {
+    static constexpr int value = 0;
+};
+
+// One CTA per cloud, T == the reference block size for this N, N <= T*P.
+// Thread t owns points k = t + i*T (i < P): all share r = k mod bs = t, so the tie key of point i is
+// (bitrev(t) << QB) | i and "first strict maximum in ascending i" is the correct in-thread order.
+template <int T, int P>
+__global__ void __launch_bounds__(T, 1)
+fps_reg_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__restrict__ idx_all,
+               float *__restrict__ new_xyz_all) {
+    constexpr int NW = T / 32;
+    constexpr int LG = Log2<T>::value;
+    extern __shared__ float smem[];
+    float *sx = smem, *sy = smem + T * P, *sz = smem + 2 * T * P;
+    __shared__ unsigned long long slot[2][32];
+
+    const float *xyz = xyz_all + (size_t)blockIdx.x * n * 3;
+    int32_t *idx = idx_all + (size_t)blockIdx.x * m;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+    float x[P], y[P], z[P], tm[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int k = t + i * T;
+        const bool ok = k < n;
+        x[i] = ok ? xyz[3 * k + 0] : 0.f;
+        y[i] = ok ? xyz[3 * k + 1] : 0.f;
+        z[i] = ok ? xyz[3 * k + 2] : 0.f;
+        // padding points carry temp = 0: they can only tie when every real temp is 0, and then
+        // point 0 (tie key 0) wins anyway.  Real points start at 1e10 (model/pointnet2_utils.py:26).
+        tm[i] = ok ? 1e10f : 0.f;
+        sx[k] = x[i];
+        sy[k] = y[i];
+        sz[k] = z[i];
+    }
+    const uint32_t rank = __brev((uint32_t)t) >> (32 - LG);
+    const uint32_t inv_base = 0xFFFFFFFFu - (rank << QB);
+    float *new_xyz = new_xyz_all ? new_xyz_all + (size_t)blockIdx.x * m * 3 : nullptr;
+    if (t == 0) idx[0] = 0;
+    __syncthreads();
+    float x1 = sx[0], y1 = sy[0], z1 = sz[0];
+    if (t == 0 && new_xyz) {
+        new_xyz[0] = x1; new_xyz[1] = y1; new_xyz[2] = z1;
+    }
+
+    for (int j = 1; j < m; ++j) {
+        tm[0] = fminf(dist_ref(x[0], y[0], z[0], x1, y1, z1), tm[0]);
+        float best = tm[0];
+        int besti = 0;
+#pragma unroll
+        for (int i = 1; i < P; ++i) {
+            tm[i] = fminf(dist_ref(x[i], y[i], z[i], x1, y1, z1), tm[i]);
+            if (tm[i] > best) {
+                best = tm[i];
+                besti = i;
+            }
+        }
+        uint32_t hi = __float_as_uint(best), lo = inv_base - (uint32_t)besti;
+        warp_argmax(hi, lo);
+        if (NW > 1) {
+            if (lane == 0) slot[j & 1][warp] = ((unsigned long long)hi << 32) | lo;
+            __syncthreads();
+            const unsigned long long v = lane < NW ? slot[j & 1][lane] : 0ull;
+            hi = (uint32_t)(v >> 32);
+            lo = (uint32_t)v;
+            warp_argmax(hi, lo);
+        }
+        const uint32_t tie = 0xFFFFFFFFu - lo;
+        const int k = (int)(tie & QMASK) * T + (int)(__brev(tie >> QB) >> (32 - LG));
+        x1 = sx[k];
+        y1 = sy[k];
+        z1 = sz[k];
+        if (t == 0) {
+            idx[j] = k;
+            if (new_xyz) {
+                new_xyz[3 * j] = x1; new_xyz[3 * j + 1] = y1; new_xyz[3 * j + 2] = z1;
+            }
+        }
+    }
+}
+
+// Any N >= 1024 with the running minima in global memory (`temp`, caller scratch as in the
+// reference).  Used only when the cloud exceeds what the on-chip kernels hold.
+__global__ void __launch_bounds__(1024, 1)
+fps_global_kernel(int n, int m, const float *__restrict__ xyz_all, float *__restrict__ temp_all,
+                  int32_t *__restrict__ idx_all, float *__restrict__ new_xyz_all) {
+    constexpr int T = 1024, LG = 10;
+    __shared__ unsigned long long slot[2][32];
+    const float *xyz = xyz_all + (size_t)blockIdx.x * n * 3;
+    float *temp = temp_all + (size_t)blockIdx.x * n;
+    int32_t *idx = idx_all + (size_t)blockIdx.x * m;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int k = t; k < n; k += T) temp[k] = 1e10f;
+    const uint32_t rank = __brev((uint32_t)t) >> (32 - LG);
+    const uint32_t inv_base = 0xFFFFFFFFu - (rank << QB);
+    float *new_xyz = new_xyz_all ? new_xyz_all + (size_t)blockIdx.x * m * 3 : nullptr;
+    float x1 = xyz[0], y1 = xyz[1], z1 = xyz[2];
+    if (t == 0) {
+        idx[0] = 0;
+        if (new_xyz) {
+            new_xyz[0] = x1; new_xyz[1] = y1; new_xyz[2] = z1;
+        }
+    }
+    for (int j = 1; j < m; ++j) {
+        float best = -1.f;
+        int bestq = 0;
+        for (int k = t, q = 0; k < n; k += T, ++q) {
+            const float d = dist_ref(xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2], x1, y1, z1);
+            const float d2 = fminf(d, temp[k]);
+            temp[k] = d2;
+            if (d2 > best) {
+                best = d2;
+                bestq = q;
+            }
+        }
+        uint32_t hi = __float_as_uint(best), lo = inv_base - (uint32_t)bestq;
+        warp_argmax(hi, lo);
+        if (lane == 0) slot[j & 1][warp] = ((unsigned long long)hi << 32) | lo;
+        __syncthreads();
+        const unsigned long long v = slot[j & 1][lane];
+        hi = (uint32_t)(v >> 32);
+        lo = (uint32_t)v;
+        warp_argmax(hi, lo);
+        const uint32_t tie = 0xFFFFFFFFu - lo;
+        const int k = (int)(tie & QMASK) * T + (int)(__brev(tie >> QB) >> (32 - LG));
+        x1 = xyz[3 * k];
+        y1 = xyz[3 * k + 1];
+        z1 = xyz[3 * k + 2];
+        if (t == 0) {
+            idx[j] = k;
+            if (new_xyz) {
+                new_xyz[3 * j] = x1; new_xyz[3 * j + 1] = y1; new_xyz[3 * j + 2] = z1;
+            }
+        }
+    }
+}
+
+// N < 32: one thread per cloud walks the total order directly.
+__global__ void fps_tiny_kernel(int b, int n, int m, int bs, int lg, const float *__restrict__ xyz_all,
+                                int32_t *__restrict__ idx_all, float *__restrict__ new_xyz_all) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b) return;
+    const float *xyz = xyz_all + (size_t)c * n * 3;
+    int32_t *idx = idx_all + (size_t)c * m;
+    float tm[32];
+    for (int k = 0; k < n; ++k) tm[k] = 1e10f;
+    float *new_xyz = new_xyz_all ? new_xyz_all + (size_t)c * m * 3 : nullptr;
+    int old = 0;
+    idx[0] = 0;
+    for (int j = 1; j <= m; ++j) {
+        const float x1 = xyz[3 * old], y1 = xyz[3 * old + 1], z1 = xyz[3 * old + 2];
+        if (new_xyz) {
+            new_xyz[3 * (j - 1)] = x1; new_xyz[3 * (j - 1) + 1] = y1; new_xyz[3 * (j - 1) + 2] = z1;
+        }
+        if (j == m) break;
+        float best = -1.f;
+        uint32_t best_rank = 0;
+        int besti = 0;
+        for (int k = 0; k < n; ++k) {
+            const float d2 = fminf(dist_ref(xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2], x1, y1, z1), tm[k]);
+            tm[k] = d2;
+            const uint32_t rk = lg ? (__brev((uint32_t)(k & (bs - 1))) >> (32 - lg)) : 0u;
+            if (d2 > best || (d2 == best && rk < best_rank)) {
+                best = d2;
+                best_rank = rk;
+                besti = k;
+            }
+        }
+        old = besti;
+        idx[j] = old;
+    }
+}
+
+template <int T, int P>
+int launch_reg(int b, int n, int m, const float *xyz, int32_t *idx, float *new_xyz, cudaStream_t s) {
+    const size_t smem = (size_t)3 * T * P * sizeof(float);
+    if (smem > 48 * 1024)
+        PN2_CUDA(cudaFuncSetAttribute(fps_reg_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fps_reg_kernel<T, P><<<b, T, smem, s>>>(n, m, xyz, idx, new_xyz);
+    PN2_LAUNCH_OK("fps_reg_kernel");
+    return PN2_OK;
+}
+
+template <int T>
+int launch_reg_small(int b, int n, int m, const float *xyz, int32_t *idx, float *new_xyz, cudaStream_t s) {
+    return n <= T ? launch_reg<T, 1>(b, n, m, xyz, idx, new_xyz, s) : launch_reg<T, 2>(b, n, m, xyz, idx, new_xyz, s);
+}
+
+}  // namespace
+}  // namespace pn2
+
+namespace pn2 {
+namespace {
+int fps_impl(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, float *new_xyz, void *stream) {
+    PN2_REQUIRE(b >= 0 && n >= 1, "fps: need b >= 0 and n >= 1 (got b=%d n=%d)", b, n);
+    if (b == 0 || m <= 0) return PN2_OK;  // the reference kernel returns at once for m <= 0 (sampling_gpu.cu:101)
+    PN2_REQUIRE(xyz && idx, "fps: null pointer");
+    PN2_REQUIRE((long long)n < (1ll << 31) / 3, "fps: n too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int T = ref_block_size(n);
+    if (T < 32) {
+        int lg = 0;
+        while ((1 << lg) < T) ++lg;
+        fps_tiny_kernel<<<ceil_div(b, 64), 64, 0, s>>>(b, n, m, T, lg, xyz, idx, new_xyz);
+        PN2_LAUNCH_OK("fps_tiny_kernel");
+        return PN2_OK;
+    }
+    switch (T) {
+        case 32: return launch_reg_small<32>(b, n, m, xyz, idx, new_xyz, s);
+        case 64: return launch_reg_small<64>(b, n, m, xyz, idx, new_xyz, s);
+        case 128: return launch_reg_small<128>(b, n, m, xyz, idx, new_xyz, s);
+        case 256: return launch_reg_small<256>(b, n, m, xyz, idx, new_xyz, s);
+        case 512: return launch_reg_small<512>(b, n, m, xyz, idx, new_xyz, s);
+        default: break;
+    }
+    if (n <= 1024) return launch_reg<1024, 1>(b, n, m, xyz, idx, new_xyz, s);
+    if (n <= 2048) return launch_reg<1024, 2>(b, n, m, xyz, idx, new_xyz, s);
+    if (n <= 4096) return launch_reg<1024, 4>(b, n, m, xyz, idx, new_xyz, s);
+    if (n <= 8192) return launch_reg<1024, 8>(b, n, m, xyz, idx, new_xyz, s);
+    if (!temp)
+        return set_error(PN2_ERR_INVALID_ARGUMENT, "fps: n=%d exceeds the on-chip kernels; pass the (B,N) temp scratch", n);
+    PN2_REQUIRE(n < (long long)(QMASK) * 1024ll, "fps: n too large for the tie key");
+    fps_global_kernel<<<b, 1024, 0, s>>>(n, m, xyz, temp, idx, new_xyz);
+    PN2_LAUNCH_OK("fps_global_kernel");
+    return PN2_OK;
+}
+}  // namespace
+}  // namespace pn2
+
+extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int32_t *idx,
+                                           void *stream) {
+    return pn2::fps_impl(b, n, m, xyz, temp, idx, nullptr, stream);
+}
+
+extern "C" int pn2_fps_gather(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, float *new_xyz,
+                              void *stream) {
+    if (m > 0 && b > 0 && !new_xyz) return pn2::set_error(PN2_ERR_INVALID_ARGUMENT, "fps_gather: null new_xyz");
+    return pn2::fps_impl(b, n, m, xyz, temp, idx, new_xyz, stream);
+}

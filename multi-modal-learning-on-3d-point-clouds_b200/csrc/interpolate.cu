@@ -1,0 +1,225 @@
+// interpolate.cu -- three nearest neighbours and inverse-distance interpolation.
+// Replaces utils/src/interpolate_gpu.cu:9-161 (three_nn, three_interpolate, three_interpolate_grad).
+//
+// three_nn contract: per unknown point, scanning known k = 0..m-1 ascending, a
+// strict-'<' insertion into (best1 <= best2 <= best3); squared distances in the reference's fp32
+// contraction order; +inf / index 0 when m < 3.  One thread per unknown point keeps that scan
+// order; the known set is staged once per CTA in shared memory as float4 so every test is one
+// broadcast LDS.128 instead of three dependent global loads per thread.
+//
+// three_interpolate: a thread owns one output point for a chunk of channels; idx and weight are
+// read once (the reference re-reads them for every channel) and the stores of a warp are coalesced.
+#include "common.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int NN_THREADS = 256;
+constexpr int NN_TILE = 2048;  // known points per tile: 32 KB of float4
+
+struct Top3 {
+    float d1, d2, d3;
+    int i1, i2, i3;
+};
+
+__device__ __forceinline__ void top3_insert(Top3 &t, float d, int k) {
+    // interpolate_gpu.cu:37-48; the reference compares in double, which orders float values identically
+    if (d < t.d3) {
+        if (d < t.d1) {
+            t.d3 = t.d2; t.i3 = t.i2;
+            t.d2 = t.d1; t.i2 = t.i1;
+            t.d1 = d;    t.i1 = k;
+        } else if (d < t.d2) {
+            t.d3 = t.d2; t.i3 = t.i2;
+            t.d2 = d;    t.i2 = k;
+        } else {
+            t.d3 = d;    t.i3 = k;
+        }
+    }
+}
+
+__device__ __forceinline__ Top3 three_nn_scan(int m, const float *__restrict__ known, float ux, float uy, float uz,
+                                              float4 *tile) {
+    Top3 t;
+    t.d1 = t.d2 = t.d3 = __int_as_float(0x7f800000);  // (float)1e40 == +inf, interpolate_gpu.cu:28,50
+    t.i1 = t.i2 = t.i3 = 0;
+    for (int base = 0; base < m; base += NN_TILE) {
+        const int tn = min(NN_TILE, m - base);
+        __syncthreads();
+        for (int p = threadIdx.x; p < tn; p += NN_THREADS) {
+            const float *s = known + (size_t)(base + p) * 3;
+            tile[p] = make_float4(s[0], s[1], s[2], 0.f);
+        }
+        __syncthreads();
+        int p = 0;
+        for (; p + 4 <= tn; p += 4) {
+            float d[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 kp = tile[p + u];
+                d[u] = dist_ref(ux, uy, uz, kp.x, kp.y, kp.z);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) top3_insert(t, d[u], base + p + u);
+        }
+        for (; p < tn; ++p) {
+            const float4 kp = tile[p];
+            top3_insert(t, dist_ref(ux, uy, uz, kp.x, kp.y, kp.z), base + p);
+        }
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(NN_THREADS)
+three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known,
+                float *__restrict__ dist2, int32_t *__restrict__ idx) {
+    __shared__ float4 tile[NN_TILE];
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * NN_THREADS + threadIdx.x;
+    const int ic = min(i, n - 1);
+    const float *u = unknown + ((size_t)b * n + ic) * 3;
+    const Top3 t = three_nn_scan(m, known + (size_t)b * m * 3, u[0], u[1], u[2], tile);
+    if (i < n) {
+        float *od = dist2 + ((size_t)b * n + i) * 3;
+        int32_t *oi = idx + ((size_t)b * n + i) * 3;
+        od[0] = t.d1; od[1] = t.d2; od[2] = t.d3;
+        oi[0] = t.i1; oi[1] = t.i2; oi[2] = t.i3;
+    }
+}
+
+// three_nn + the reference's weight formula (model/pointnet2_utils.py:97, model/pointnet_util.py:206-208):
+// dist = sqrt(d2); dist[dist < 1e-10] = 1e-10; w = 1/dist; w = w / (w0 + w1 + w2)
+__global__ void __launch_bounds__(NN_THREADS)
+three_nn_weights_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known,
+                        int32_t *__restrict__ idx, float *__restrict__ weight) {
+    __shared__ float4 tile[NN_TILE];
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * NN_THREADS + threadIdx.x;
+    const int ic = min(i, n - 1);
+    const float *u = unknown + ((size_t)b * n + ic) * 3;
+    const Top3 t = three_nn_scan(m, known + (size_t)b * m * 3, u[0], u[1], u[2], tile);
+    if (i < n) {
+        float e1 = __fsqrt_rn(t.d1), e2 = __fsqrt_rn(t.d2), e3 = __fsqrt_rn(t.d3);
+        e1 = e1 < 1e-10f ? 1e-10f : e1;
+        e2 = e2 < 1e-10f ? 1e-10f : e2;
+        e3 = e3 < 1e-10f ? 1e-10f : e3;
+        const float w1 = __fdiv_rn(1.0f, e1), w2 = __fdiv_rn(1.0f, e2), w3 = __fdiv_rn(1.0f, e3);
+        const float s = __fadd_rn(__fadd_rn(w1, w2), w3);
+        float *ow = weight + ((size_t)b * n + i) * 3;
+        int32_t *oi = idx + ((size_t)b * n + i) * 3;
+        ow[0] = __fdiv_rn(w1, s); ow[1] = __fdiv_rn(w2, s); ow[2] = __fdiv_rn(w3, s);
+        oi[0] = t.i1; oi[1] = t.i2; oi[2] = t.i3;
+    }
+}
+
+constexpr int TI_THREADS = 256;
+constexpr int TI_CH = 8;
+
+// out[b,c,i] = fma(w2, f[b,c,i2], fma(w0, f[b,c,i0], rn(w1 * f[b,c,i1])))   (the reference's contraction,
+// SURVEY.md 2.2 K8)
+__global__ void __launch_bounds__(TI_THREADS)
+three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points, const int32_t *__restrict__ idx,
+                         const float *__restrict__ weight, float *__restrict__ out) {
+    const int i = blockIdx.x * TI_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * TI_CH;
+    const int32_t *id = idx + ((size_t)b * n + i) * 3;
+    const float *w = weight + ((size_t)b * n + i) * 3;
+    const int i0 = id[0], i1 = id[1], i2 = id[2];
+    const float w0 = w[0], w1 = w[1], w2 = w[2];
+    const float *f = points + ((size_t)b * c + c0) * m;
+    float *o = out + ((size_t)b * c + c0) * n + i;
+    const int cc = min(TI_CH, c - c0);
+    float a0[TI_CH], a1[TI_CH], a2[TI_CH];
+#pragma unroll
+    for (int k = 0; k < TI_CH; ++k)
+        if (k < cc) {
+            a0[k] = __ldg(f + (size_t)k * m + i0);
+            a1[k] = __ldg(f + (size_t)k * m + i1);
+            a2[k] = __ldg(f + (size_t)k * m + i2);
+        }
+#pragma unroll
+    for (int k = 0; k < TI_CH; ++k)
+        if (k < cc) __stcs(o + (size_t)k * n, __fmaf_rn(w2, a2[k], __fmaf_rn(w0, a0[k], __fmul_rn(w1, a1[k]))));
+}
+
+// grad_points[b,c,idx_j] += grad_out[b,c,i] * w_j   (interpolate_gpu.cu:120-142)
+__global__ void __launch_bounds__(TI_THREADS)
+three_interpolate_grad_kernel(int c, int n, int m, const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
+                              const float *__restrict__ weight, float *__restrict__ grad_points) {
+    const int i = blockIdx.x * TI_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * TI_CH;
+    const int32_t *id = idx + ((size_t)b * n + i) * 3;
+    const float *w = weight + ((size_t)b * n + i) * 3;
+    const int i0 = id[0], i1 = id[1], i2 = id[2];
+    const float w0 = w[0], w1 = w[1], w2 = w[2];
+    const float *g = grad_out + ((size_t)b * c + c0) * n + i;
+    float *gp = grad_points + ((size_t)b * c + c0) * m;
+    const int cc = min(TI_CH, c - c0);
+#pragma unroll
+    for (int k = 0; k < TI_CH; ++k)
+        if (k < cc) {
+            const float go = __ldcs(g + (size_t)k * n);
+            atomicAdd(gp + (size_t)k * m + i0, __fmul_rn(go, w0));
+            atomicAdd(gp + (size_t)k * m + i1, __fmul_rn(go, w1));
+            atomicAdd(gp + (size_t)k * m + i2, __fmul_rn(go, w2));
+        }
+}
+
+}  // namespace
+}  // namespace pn2
+
+extern "C" int pn2_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int32_t *idx,
+                            void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(b >= 0 && n >= 0 && m >= 0, "three_nn: bad dims b=%d n=%d m=%d", b, n, m);
+    if (b == 0 || n == 0) return PN2_OK;
+    PN2_REQUIRE(unknown && dist2 && idx && (known || m == 0), "three_nn: null pointer");
+    PN2_REQUIRE(b <= 65535, "three_nn: b exceeds the grid limit");
+    dim3 grid(ceil_div(n, NN_THREADS), b);
+    three_nn_kernel<<<grid, NN_THREADS, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+    PN2_LAUNCH_OK("three_nn");
+    return PN2_OK;
+}
+
+extern "C" int pn2_three_nn_weights(int b, int n, int m, const float *unknown, const float *known, int32_t *idx,
+                                    float *weight, void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(b >= 0 && n >= 0 && m >= 0, "three_nn_weights: bad dims b=%d n=%d m=%d", b, n, m);
+    if (b == 0 || n == 0) return PN2_OK;
+    PN2_REQUIRE(unknown && weight && idx && (known || m == 0), "three_nn_weights: null pointer");
+    PN2_REQUIRE(b <= 65535, "three_nn_weights: b exceeds the grid limit");
+    dim3 grid(ceil_div(n, NN_THREADS), b);
+    three_nn_weights_kernel<<<grid, NN_THREADS, 0, (cudaStream_t)stream>>>(n, m, unknown, known, idx, weight);
+    PN2_LAUNCH_OK("three_nn_weights");
+    return PN2_OK;
+}
+
+extern "C" int pn2_three_interpolate(int b, int c, int m, int n, const float *points, const int32_t *idx,
+                                     const float *weight, float *out, void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(b >= 0 && c >= 0 && m >= 1 && n >= 0, "three_interpolate: bad dims b=%d c=%d m=%d n=%d", b, c, m, n);
+    if (b == 0 || c == 0 || n == 0) return PN2_OK;
+    PN2_REQUIRE(points && idx && weight && out, "three_interpolate: null pointer");
+    PN2_REQUIRE(b <= 65535 && ceil_div(c, TI_CH) <= 65535, "three_interpolate: b or c exceeds the grid limits");
+    dim3 grid(ceil_div(n, TI_THREADS), ceil_div(c, TI_CH), b);
+    three_interpolate_kernel<<<grid, TI_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, points, idx, weight, out);
+    PN2_LAUNCH_OK("three_interpolate");
+    return PN2_OK;
+}
+
+extern "C" int pn2_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int32_t *idx,
+                                          const float *weight, float *grad_points, void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(b >= 0 && c >= 0 && m >= 1 && n >= 0, "three_interpolate_grad: bad dims b=%d c=%d n=%d m=%d", b, c, n, m);
+    if (b == 0 || c == 0 || n == 0) return PN2_OK;
+    PN2_REQUIRE(grad_out && idx && weight && grad_points, "three_interpolate_grad: null pointer");
+    PN2_REQUIRE(b <= 65535 && ceil_div(c, TI_CH) <= 65535, "three_interpolate_grad: b or c exceeds the grid limits");
+    dim3 grid(ceil_div(n, TI_THREADS), ceil_div(c, TI_CH), b);
+    three_interpolate_grad_kernel<<<grid, TI_THREADS, 0, (cudaStream_t)stream>>>(c, n, m, grad_out, idx, weight, grad_points);
+    PN2_LAUNCH_OK("three_interpolate_grad");
+    return PN2_OK;
+}

@@ -1,0 +1,433 @@
+// row_mlp.cu -- fused "gather -> shared MLP -> pool/store" blocks, fp32.
+//
+// Replaces, per set-abstraction scale (model/pointnet_util.py:37-41,101-109 / 152-166):
+//     grouping_operation(xyz) + centre subtraction + grouping_operation(feat) + concat + permutes
+//     + L x (Conv2d 1x1 -> BatchNorm2d(eval) -> ReLU) + max over nsample
+// and per feature-propagation block (model/pointnet_util.py:209-220, model/pointnet2.py:158-159):
+//     three_interpolate + concat + permutes + L x (Conv1d 1x1 -> BatchNorm1d(eval) -> ReLU)
+//     (+ the head's conv1/bn1/relu/conv2 appended as two more layers)
+// which the reference runs as ~5 custom launches + ~8 layout copies + 3 x (cuDNN conv, BN, ReLU) +
+// max, writing every intermediate activation to HBM (~100 MB per scene in sa1).
+//
+// Here one CTA owns a tile of TR rows (a row = one (centroid, sample) pair, or one point).  The
+// gathered input, every intermediate activation and the pooled result stay in shared memory; the
+// only HBM traffic is the gathered input rows, the weights (L2 resident) and the final output.
+// Activations are stored k-major ([channel][row], row stride TR+4) so that a thread's A fragment
+// is one or two LDS.128 and its 8 interleaved output columns land conflict-free; weight k-chunks
+// are staged through a double-buffered tile with their columns permuted to match.
+// BatchNorm is folded into (W, bias) by the caller (eval mode), see pn2_b200/pointnet_util.py.
+//
+// fp32 FFMA throughout (the 1e-5 parity path).  The bf16 tcgen05 variant lives in row_mlp_tc.cu.
+#include "common.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int RM_THREADS = 256;
+constexpr int KC = 16;          // k-chunk of the staged weight tile
+constexpr int WSP = 128 + 4;    // row stride of the weight tile (floats)
+
+enum { MODE_SA = 0, MODE_FP = 1 };
+
+struct RowMlpParams {
+    int mode;
+    int num_layers;
+    int cin[PN2_MAX_LAYERS], cout[PN2_MAX_LAYERS], relu[PN2_MAX_LAYERS];
+    const float *w[PN2_MAX_LAYERS];
+    const float *bias[PN2_MAX_LAYERS];
+    int buf_a_floats, buf_b_floats;  // ping / pong activation buffers (floats)
+    // SA
+    int n, m, k, d, order;
+    long long groups;  // B*M
+    const float *xyz, *feat, *new_xyz;
+    const int32_t *idx;
+    float *out;
+    int out_stride, out_offset;
+    // FP
+    long long rows;  // B*n
+    int d1, d2, fp_m;
+    const float *feat1, *feat2, *weight;
+};
+
+__host__ __device__ inline int pick_nt(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : 128); }
+__host__ __device__ inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// One n-tile of one layer: acc = X_in[.,rows] * W[n0 + cols, .]^T, then bias/ReLU and a k-major store.
+template <int TR, int NT>
+__device__ __forceinline__ void layer_tile(const float *__restrict__ xin, float *__restrict__ xout, int out_ch0,
+                                           const float *__restrict__ W, const float *__restrict__ bias, int cin,
+                                           int cout, int n0, int relu, float *ws) {
+    constexpr int TRP = TR + 4;
+    constexpr int TM = (TR == 128 && NT >= 64) ? 8 : 4;
+    constexpr int TY = TR / TM;
+    constexpr int TXN = RM_THREADS / TY;
+    constexpr int TN = NT / TXN;
+    constexpr int EPT = KC * NT / RM_THREADS;  // weight elements staged per thread per chunk
+    static_assert(TN >= 1 && EPT >= 1, "bad tile");
+    const int tid = threadIdx.x;
+    const int tx = tid % TXN, ty = tid / TXN;
+
+    // staging coordinates: smem position p <-> logical column (p / TN) + TXN * (p % TN)
+    const int sp = tid % NT, sg = tid / NT;
+    const int scol = n0 + (sp / TN) + TXN * (sp % TN);
+    const float *wrow = W + (size_t)scol * cin;
+    const bool col_ok = scol < cout;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float wreg[EPT];
+    const int nchunks = (cin + KC - 1) / KC;
+    // prologue: stage chunk 0
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int k = sg * EPT + e;
+        wreg[e] = (col_ok && k < cin) ? __ldg(wrow + k) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) ws[(sg * EPT + e) * WSP + sp] = wreg[e];
+    __syncthreads();
+
+    for (int c = 0; c < nchunks; ++c) {
+        float *wcur = ws + (c & 1) * (KC * WSP);
+        float *wnxt = ws + ((c + 1) & 1) * (KC * WSP);
+        const bool more = (c + 1) < nchunks;
+        if (more) {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int k = (c + 1) * KC + sg * EPT + e;
+                wreg[e] = (col_ok && k < cin) ? __ldg(wrow + k) : 0.f;
+            }
+        }
+        const float *xa = xin + (size_t)(c * KC) * TRP + ty * TM;
+        const int kk_end = min(KC, cin - c * KC);
+#pragma unroll 4
+        for (int kk = 0; kk < kk_end; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(xa + kk * TRP + i);
+                a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+            }
+            const float *wb = wcur + kk * WSP + tx * TN;
+            if constexpr (TN >= 4) {
+#pragma unroll
+                for (int j = 0; j < TN; j += 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(wb + j);
+                    b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+                }
+            } else if constexpr (TN == 2) {
+                const float2 v = *reinterpret_cast<const float2 *>(wb);
+                b[0] = v.x; b[1] = v.y;
+            } else {
+                b[0] = wb[0];
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (more) {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) wnxt[(sg * EPT + e) * WSP + sp] = wreg[e];
+        }
+        __syncthreads();
+    }
+
+    // epilogue: bias + activation, k-major store (channel = out_ch0 + logical column offset)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        const int col = n0 + tx + TXN * j;
+        const float bv = col < cout ? __ldg(bias + col) : 0.f;
+        float *dst = xout + (size_t)(out_ch0 + tx + TXN * j) * TRP + ty * TM;
+#pragma unroll
+        for (int i = 0; i < TM; i += 4) {
+            float4 v;
+            v.x = acc[i][j] + bv; v.y = acc[i + 1][j] + bv; v.z = acc[i + 2][j] + bv; v.w = acc[i + 3][j] + bv;
+            if (relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            *reinterpret_cast<float4 *>(dst + i) = v;
+        }
+    }
+}
+
+template <int TR>
+__device__ __forceinline__ void gather_sa(const RowMlpParams &p, float *x0, long long tile) {
+    constexpr int TRP = TR + 4;
+    const int K = p.k, D = p.d, C0 = 3 + D;
+    const int gpt = TR / K;  // groups per tile
+    const int xyz_off = p.order == PN2_ORDER_XYZ_FIRST ? 0 : D;
+    const int feat_off = p.order == PN2_ORDER_XYZ_FIRST ? 3 : 0;
+    const int cpad = round_up(C0, KC);
+    if (C0 <= 16) {
+        // few channels: consecutive threads take consecutive rows (conflict-free stores)
+        for (int e = threadIdx.x; e < cpad * TR; e += RM_THREADS) {
+            const int r = e % TR, c = e / TR;
+            const long long g = tile * gpt + r / K;
+            float v = 0.f;
+            if (g < p.groups && c < C0) {
+                const int b = (int)(g / p.m);
+                const int pt = __ldg(p.idx + g * K + (r % K));
+                const size_t src = (size_t)b * p.n + pt;
+                if (c >= xyz_off && c < xyz_off + 3) {
+                    const int a = c - xyz_off;
+                    v = __fsub_rn(__ldg(p.xyz + src * 3 + a), __ldg(p.new_xyz + g * 3 + a));
+                } else {
+                    v = __ldg(p.feat + src * D + (c - feat_off));
+                }
+            }
+            x0[(size_t)c * TRP + r] = v;
+        }
+    } else {
+        // wide rows: one warp per row, lanes along the (contiguous, channel-last) feature row
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int r = warp; r < TR; r += RM_THREADS / 32) {
+            const long long g = tile * gpt + r / K;
+            const bool ok = g < p.groups;
+            int pt = 0, b = 0;
+            if (ok) {
+                b = (int)(g / p.m);
+                pt = __ldg(p.idx + g * K + (r % K));
+            }
+            const size_t src = (size_t)b * p.n + pt;
+            if (lane < 3)
+                x0[(size_t)(xyz_off + lane) * TRP + r] =
+                    ok ? __fsub_rn(__ldg(p.xyz + src * 3 + lane), __ldg(p.new_xyz + g * 3 + lane)) : 0.f;
+            for (int c = lane; c < D; c += 32) x0[(size_t)(feat_off + c) * TRP + r] = ok ? __ldg(p.feat + src * D + c) : 0.f;
+            for (int c = C0 + lane; c < cpad; c += 32) x0[(size_t)c * TRP + r] = 0.f;
+        }
+    }
+}
+
+template <int TR>
+__device__ __forceinline__ void gather_fp(const RowMlpParams &p, float *x0, long long tile) {
+    constexpr int TRP = TR + 4;
+    const int D1 = p.d1, D2 = p.d2, C0 = D1 + D2;
+    const int cpad = round_up(C0, KC);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = p.n;
+    for (int r = warp; r < TR; r += RM_THREADS / 32) {
+        const long long row = tile * TR + r;
+        const bool ok = row < p.rows;
+        const int b = ok ? (int)(row / n) : 0;
+        if (D1 > 0) {
+            const float *f1 = p.feat1 + (size_t)row * D1;
+            for (int c = lane; c < D1; c += 32) x0[(size_t)c * TRP + r] = ok ? __ldg(f1 + c) : 0.f;
+        }
+        if (p.fp_m == 1) {
+            // S == 1: the single coarse feature row is repeated (model/pointnet_util.py:202-203)
+            const float *f2 = p.feat2 + (size_t)b * D2;
+            for (int c = lane; c < D2; c += 32) x0[(size_t)(D1 + c) * TRP + r] = ok ? __ldg(f2 + c) : 0.f;
+        } else {
+            int i0 = 0, i1 = 0, i2 = 0;
+            float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+            if (ok) {
+                const int32_t *id = p.idx + (size_t)row * 3;
+                const float *w = p.weight + (size_t)row * 3;
+                i0 = __ldg(id); i1 = __ldg(id + 1); i2 = __ldg(id + 2);
+                w0 = __ldg(w); w1 = __ldg(w + 1); w2 = __ldg(w + 2);
+            }
+            const float *f2 = p.feat2 + (size_t)b * p.fp_m * D2;
+            const float *r0 = f2 + (size_t)i0 * D2, *r1 = f2 + (size_t)i1 * D2, *r2 = f2 + (size_t)i2 * D2;
+            for (int c = lane; c < D2; c += 32) {
+                // same rounding sequence as three_interpolate (interpolate.cu)
+                const float v = __fmaf_rn(w2, __ldg(r2 + c), __fmaf_rn(w0, __ldg(r0 + c), __fmul_rn(w1, __ldg(r1 + c))));
+                x0[(size_t)(D1 + c) * TRP + r] = ok ? v : 0.f;
+            }
+        }
+        for (int c = C0 + lane; c < cpad; c += 32) x0[(size_t)c * TRP + r] = 0.f;
+    }
+}
+
+template <int TR>
+__global__ void __launch_bounds__(RM_THREADS, 1) row_mlp_kernel(const __grid_constant__ RowMlpParams p) {
+    constexpr int TRP = TR + 4;
+    // shared memory layout: [ping: buf_a_floats][pong: buf_b_floats][weight tiles: 2*KC*WSP]
+    extern __shared__ __align__(16) float smem[];
+    float *buf[2] = {smem, smem + p.buf_a_floats};
+    float *ws = buf[1] + p.buf_b_floats;
+    const long long tile = blockIdx.x;
+
+    if (p.mode == MODE_SA)
+        gather_sa<TR>(p, buf[0], tile);
+    else
+        gather_fp<TR>(p, buf[0], tile);
+    __syncthreads();
+
+    for (int l = 0; l < p.num_layers; ++l) {
+        const float *xin = buf[l & 1];
+        float *xout = buf[(l + 1) & 1];
+        const bool last = (l == p.num_layers - 1);
+        const int cin = p.cin[l], cout = p.cout[l];
+        const int nt = pick_nt(cout);
+        for (int n0 = 0; n0 < cout; n0 += nt) {
+            const int ch0 = last ? 0 : n0;
+            if (nt == 128)
+                layer_tile<TR, 128>(xin, xout, ch0, p.w[l], p.bias[l], cin, cout, n0, p.relu[l], ws);
+            else if (nt == 64)
+                layer_tile<TR, 64>(xin, xout, ch0, p.w[l], p.bias[l], cin, cout, n0, p.relu[l], ws);
+            else
+                layer_tile<TR, 32>(xin, xout, ch0, p.w[l], p.bias[l], cin, cout, n0, p.relu[l], ws);
+            if (!last) continue;
+            __syncthreads();
+            const int nv = min(nt, cout - n0);  // valid columns of this n-tile
+            if (p.mode == MODE_SA) {
+                // max over the K rows of each group (torch.max(new_points, 2)[0], pointnet_util.py:109)
+                const int K = p.k, gpt = TR / K;
+                for (int e = threadIdx.x; e < gpt * nv; e += RM_THREADS) {
+                    const int col = e % nv, gl = e / nv;
+                    const long long g = tile * gpt + gl;
+                    if (g >= p.groups) continue;
+                    const float *src = xout + (size_t)col * TRP + gl * K;
+                    float mx = src[0];
+                    for (int s = 1; s < K; ++s) mx = fmaxf(mx, src[s]);
+                    p.out[(size_t)g * p.out_stride + p.out_offset + n0 + col] = mx;
+                }
+            } else {
+                for (int e = threadIdx.x; e < TR * nv; e += RM_THREADS) {
+                    const int col = e % nv, r = e / nv;
+                    const long long row = tile * TR + r;
+                    if (row >= p.rows) continue;
+                    p.out[(size_t)row * cout + n0 + col] = xout[(size_t)col * TRP + r];
+                }
+            }
+            __syncthreads();
+        }
+        // layer_tile ends with a barrier after its last chunk, but its epilogue stores come after
+        // that barrier: make them visible before the next layer reads them.
+        __syncthreads();
+    }
+}
+
+struct Layout {
+    int buf_a, buf_b;  // floats
+    size_t bytes;
+};
+
+Layout make_layout(int tr, int c0, const pn2_mlp *mlp) {
+    const int trp = tr + 4;
+    int a = round_up(c0, KC) * trp, b = 0;
+    for (int l = 0; l < mlp->num_layers; ++l) {
+        const int nt = pick_nt(mlp->cout[l]);
+        const int ch = (l == mlp->num_layers - 1) ? nt : round_up(mlp->cout[l], nt);
+        if (((l + 1) & 1) == 1)
+            b = b > ch * trp ? b : ch * trp;
+        else
+            a = a > ch * trp ? a : ch * trp;
+        // inputs are read up to round_up(cin, KC) channels only through kk_end, no extra space needed
+    }
+    Layout L;
+    L.buf_a = a;
+    L.buf_b = b;
+    L.bytes = (size_t)(a + b + 2 * KC * WSP) * sizeof(float);
+    return L;
+}
+
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+int check_mlp(const char *op, const pn2_mlp *mlp, int c0) {
+    PN2_REQUIRE(mlp, "%s: null mlp", op);
+    PN2_REQUIRE(mlp->num_layers >= 1 && mlp->num_layers <= PN2_MAX_LAYERS, "%s: num_layers %d outside 1..%d", op,
+                mlp->num_layers, PN2_MAX_LAYERS);
+    int c = c0;
+    for (int l = 0; l < mlp->num_layers; ++l) {
+        PN2_REQUIRE(mlp->cin[l] == c, "%s: layer %d expects cin=%d but the previous stage produces %d", op, l, mlp->cin[l], c);
+        PN2_REQUIRE(mlp->cout[l] >= 1, "%s: layer %d has cout=%d", op, l, mlp->cout[l]);
+        PN2_REQUIRE(mlp->weight[l] && mlp->bias[l], "%s: layer %d has a null weight or bias", op, l);
+        c = mlp->cout[l];
+    }
+    return PN2_OK;
+}
+
+template <int TR>
+int launch(const RowMlpParams &p, const Layout &L, long long tiles, cudaStream_t s) {
+    PN2_REQUIRE(tiles <= 2147483647ll, "row_mlp: too many tiles");
+    PN2_CUDA(cudaFuncSetAttribute(row_mlp_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
+    row_mlp_kernel<TR><<<(unsigned)tiles, RM_THREADS, L.bytes, s>>>(p);
+    PN2_LAUNCH_OK("row_mlp_kernel");
+    return PN2_OK;
+}
+
+// Picks the largest row tile whose buffers fit in shared memory, then shrinks it while the grid
+// would leave SMs idle.
+int dispatch(RowMlpParams &p, const pn2_mlp *mlp, int c0, long long total_rows, int min_tr, cudaStream_t s) {
+    const int cands[3] = {128, 64, 32};
+    int chosen = -1;
+    for (int i = 0; i < 3; ++i) {
+        const int tr = cands[i];
+        if (tr < min_tr || tr % min_tr) continue;
+        if (make_layout(tr, c0, mlp).bytes > SMEM_LIMIT) continue;
+        chosen = tr;
+        const long long tiles = (total_rows + tr - 1) / tr;
+        if (tiles >= 2ll * sm_count()) break;  // enough CTAs; otherwise try a smaller tile
+    }
+    if (chosen < 0)
+        return set_error(PN2_ERR_UNSUPPORTED, "row_mlp: channel widths need more than %zu bytes of shared memory", SMEM_LIMIT);
+    const Layout L = make_layout(chosen, c0, mlp);
+    p.buf_a_floats = L.buf_a;
+    p.buf_b_floats = L.buf_b;
+    const long long tiles = (total_rows + chosen - 1) / chosen;
+    switch (chosen) {
+        case 128: return launch<128>(p, L, tiles, s);
+        case 64: return launch<64>(p, L, tiles, s);
+        default: return launch<32>(p, L, tiles, s);
+    }
+}
+
+void copy_mlp(RowMlpParams &p, const pn2_mlp *mlp) {
+    p.num_layers = mlp->num_layers;
+    for (int l = 0; l < mlp->num_layers; ++l) {
+        p.cin[l] = mlp->cin[l];
+        p.cout[l] = mlp->cout[l];
+        p.relu[l] = mlp->relu[l];
+        p.w[l] = mlp->weight[l];
+        p.bias[l] = mlp->bias[l];
+    }
+}
+
+}  // namespace
+}  // namespace pn2
+
+extern "C" int pn2_sa_mlp_max(int b, int n, int m, int k, int d, const float *xyz, const float *feat, const float *new_xyz,
+                              const int32_t *idx, int order, const pn2_mlp *mlp, float *out, int out_stride,
+                              int out_offset, void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(b >= 0 && n >= 1 && m >= 0 && k >= 1 && d >= 0, "sa_mlp_max: bad dims b=%d n=%d m=%d k=%d d=%d", b, n, m, k, d);
+    PN2_REQUIRE(order == PN2_ORDER_XYZ_FIRST || order == PN2_ORDER_FEAT_FIRST, "sa_mlp_max: unknown concat order %d", order);
+    if (int st = check_mlp("sa_mlp_max", mlp, 3 + d)) return st;
+    if (b == 0 || m == 0) return PN2_OK;
+    PN2_REQUIRE(xyz && new_xyz && idx && out && (feat || d == 0), "sa_mlp_max: null pointer");
+    const int cl = mlp->cout[mlp->num_layers - 1];
+    PN2_REQUIRE(out_offset >= 0 && out_stride >= out_offset + cl, "sa_mlp_max: out_stride/out_offset do not hold %d channels", cl);
+    if (!(k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32 || k == 64 || k == 128))
+        return set_error(PN2_ERR_UNSUPPORTED, "sa_mlp_max: nsample must be a power of two <= 128 (got %d)", k);
+    RowMlpParams p = {};
+    p.mode = MODE_SA;
+    copy_mlp(p, mlp);
+    p.n = n; p.m = m; p.k = k; p.d = d; p.order = order;
+    p.groups = (long long)b * m;
+    p.xyz = xyz; p.feat = feat; p.new_xyz = new_xyz; p.idx = idx;
+    p.out = out; p.out_stride = out_stride; p.out_offset = out_offset;
+    return dispatch(p, mlp, 3 + d, p.groups * k, k < 32 ? 32 : k, (cudaStream_t)stream);
+}
+
+extern "C" int pn2_fp_mlp(int b, int n, int m, int d1, int d2, const float *feat1, const float *feat2, const int32_t *idx,
+                          const float *weight, const pn2_mlp *mlp, float *out, void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(b >= 0 && n >= 0 && m >= 1 && d1 >= 0 && d2 >= 1, "fp_mlp: bad dims b=%d n=%d m=%d d1=%d d2=%d", b, n, m, d1, d2);
+    if (int st = check_mlp("fp_mlp", mlp, d1 + d2)) return st;
+    if (b == 0 || n == 0) return PN2_OK;
+    PN2_REQUIRE(feat2 && out && (feat1 || d1 == 0) && (m == 1 || (idx && weight)), "fp_mlp: null pointer");
+    RowMlpParams p = {};
+    p.mode = MODE_FP;
+    copy_mlp(p, mlp);
+    p.n = n; p.fp_m = m; p.d1 = d1; p.d2 = d2;
+    p.rows = (long long)b * n;
+    p.feat1 = feat1; p.feat2 = feat2; p.idx = idx; p.weight = weight;
+    p.out = out;
+    return dispatch(p, mlp, d1 + d2, p.rows, 32, (cudaStream_t)stream);
+}

@@ -1,0 +1,386 @@
+"""Geometry modules: the call surface of the reference's model/pointnet_util.py.
+
+    sample_and_group (:20-47)          sample_and_group_all (:50-67)
+    PointNetSetAbstraction (:70-111)   PointNetSetAbstractionMsg (:114-171)
+    PointNetFeaturePropagation (:174-221)
+
+Constructor arguments, forward signatures, tensor layouts (channel-first (B, C, N) in and out) and
+state_dict keys (mlp_convs.i / mlp_bns.i / conv_blocks.i.j / bn_blocks.i.j) are the reference's, so
+checkpoints and calling code carry over unchanged.
+
+Two execution paths per module:
+  * inference (module.eval() and no gradient needed): ONE fused kernel per SA scale / FP block --
+    grouping, centring, concat, every 1x1 conv with its eval BatchNorm folded in, ReLU and the max
+    over nsample never leave shared memory (csrc/row_mlp.cu).  Activations are channel-last inside;
+    `forward_cl` exposes that layout so a whole network can stay in it (pn2_b200/models.py).
+  * training (batch statistics / autograd): the reference's own composition of operators -- our
+    kernels for the geometry, torch.nn for conv/BN -- with identical semantics.
+"""
+from time import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, pointnet2_utils
+from ._lib import Pn2Mlp, ptr
+
+
+def timeit(tag, t):
+    print("{}: {}s".format(tag, time() - t))
+    return time()
+
+
+def pc_normalize(pc):
+    centroid = np.mean(pc, axis=0)
+    pc = pc - centroid
+    m = np.max(np.sqrt(np.sum(pc ** 2, axis=1)))
+    return pc / m
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused-path helpers
+# ---------------------------------------------------------------------------------------------------
+
+def fold_conv_bn(conv, bn):
+    """(W, b) of y = BN_eval(conv(x)) as one affine map.  conv: 1x1 Conv1d/Conv2d; bn may be None."""
+    w = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).to(torch.float32)
+    b = conv.bias.detach().to(torch.float32) if conv.bias is not None else torch.zeros(
+        conv.out_channels, device=w.device, dtype=torch.float32)
+    if bn is not None:
+        scale = bn.weight.detach() * torch.rsqrt(bn.running_var.detach() + bn.eps) if bn.affine else torch.rsqrt(
+            bn.running_var.detach() + bn.eps)
+        shift = bn.bias.detach() if bn.affine else 0.0
+        w = w * scale[:, None]
+        b = (b - bn.running_mean.detach()) * scale + shift
+    return w.contiguous(), b.contiguous()
+
+
+class FoldedMlp:
+    """A stack of folded (W, b, relu) layers resident on the device, plus the pn2_mlp descriptor."""
+
+    def __init__(self, layers):
+        self.layers = [(w.contiguous(), b.contiguous(), bool(r)) for (w, b, r) in layers]
+        if not 1 <= len(self.layers) <= _lib.PN2_MAX_LAYERS:
+            raise _lib.Pn2Error("a fused MLP holds 1..%d layers (got %d)" % (_lib.PN2_MAX_LAYERS, len(self.layers)))
+        d = Pn2Mlp()
+        d.num_layers = len(self.layers)
+        for i, (w, b, r) in enumerate(self.layers):
+            d.cin[i], d.cout[i], d.relu[i] = w.shape[1], w.shape[0], int(r)
+            d.weight[i], d.bias[i] = w.data_ptr(), b.data_ptr()
+        self.desc = d
+        self.cin = self.layers[0][0].shape[1]
+        self.cout = self.layers[-1][0].shape[0]
+
+    def extended(self, more):
+        return FoldedMlp(self.layers + list(more))
+
+
+def _param_key(mods):
+    key = []
+    for m in mods:
+        for t in list(m.parameters()) + list(m.buffers()):
+            key.append((t.data_ptr(), t._version))
+    return tuple(key)
+
+
+class _FoldCache:
+    """Re-folds only when a parameter / running statistic changed (version counters)."""
+
+    def __init__(self):
+        self.key, self.value = None, None
+
+    def get(self, convs, bns, relus):
+        mods = list(convs) + [b for b in bns if b is not None]
+        key = _param_key(mods)
+        if key != self.key:
+            self.value = FoldedMlp([fold_conv_bn(c, b) + (r,) for c, b, r in zip(convs, bns, relus)])
+            self.key = key
+        return self.value
+
+
+def _fusable(module, *tensors):
+    if module.training:
+        return False
+    if torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in tensors)
+                                    or any(p.requires_grad for p in module.parameters())):
+        return False
+    return all(t is None or t.is_cuda for t in tensors)
+
+
+def to_channel_last(x):
+    """(B, C, N) -> contiguous (B, N, C)"""
+    if x is None:
+        return None
+    B, C, N = x.shape
+    x = x.contiguous()
+    out = torch.empty((B, N, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("pn2_transpose", B, C, N, ptr(x), ptr(out), _lib.stream_ptr(x.device))
+    return out
+
+
+def to_channel_first(x):
+    """(B, N, C) -> contiguous (B, C, N)"""
+    B, N, C = x.shape
+    x = x.contiguous()
+    out = torch.empty((B, C, N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("pn2_transpose", B, N, C, ptr(x), ptr(out), _lib.stream_ptr(x.device))
+    return out
+
+
+def fps_gather_cl(xyz_cl, npoint):
+    """xyz (B, N, 3) -> (idx (B, npoint) int32, new_xyz (B, npoint, 3)); the sampler writes the picked
+    coordinates itself, replacing gather_operation + two layout copies (model/pointnet_util.py:34-35)."""
+    B, N, _ = xyz_cl.shape
+    idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz_cl.device)
+    new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz_cl.device)
+    temp = torch.empty((B, N), dtype=torch.float32, device=xyz_cl.device) if N > 8192 else None
+    with torch.cuda.device(xyz_cl.device):
+        _lib.call("pn2_fps_gather", B, N, npoint, ptr(xyz_cl), ptr(temp), ptr(idx), ptr(new_xyz),
+                  _lib.stream_ptr(xyz_cl.device))
+    return idx, new_xyz
+
+
+def sa_mlp_max_cl(xyz_cl, feat_cl, new_xyz_cl, idx, order, mlp, out=None, out_offset=0):
+    """Fused grouping + MLP + max.  Returns (B, M, cout) (or writes a channel slice of `out`)."""
+    B, N, _ = xyz_cl.shape
+    M, K = idx.shape[1], idx.shape[2]
+    D = 0 if feat_cl is None else feat_cl.shape[2]
+    if out is None:
+        out = torch.empty((B, M, mlp.cout), dtype=torch.float32, device=xyz_cl.device)
+    with torch.cuda.device(xyz_cl.device):
+        _lib.call("pn2_sa_mlp_max", B, N, M, K, D, ptr(xyz_cl), ptr(feat_cl), ptr(new_xyz_cl), ptr(idx), order,
+                  mlp.desc, ptr(out), out.shape[2], out_offset, _lib.stream_ptr(xyz_cl.device))
+    return out
+
+
+def three_nn_weights_cl(xyz1_cl, xyz2_cl):
+    """-> idx (B, n, 3) int32, weight (B, n, 3): three_nn + sqrt + clamp + inverse-distance weights
+    (model/pointnet_util.py:205-208) in one kernel."""
+    B, n, _ = xyz1_cl.shape
+    m = xyz2_cl.shape[1]
+    idx = torch.empty((B, n, 3), dtype=torch.int32, device=xyz1_cl.device)
+    w = torch.empty((B, n, 3), dtype=torch.float32, device=xyz1_cl.device)
+    with torch.cuda.device(xyz1_cl.device):
+        _lib.call("pn2_three_nn_weights", B, n, m, ptr(xyz1_cl), ptr(xyz2_cl), ptr(idx), ptr(w),
+                  _lib.stream_ptr(xyz1_cl.device))
+    return idx, w
+
+
+def fp_mlp_cl(feat1_cl, feat2_cl, idx, weight, mlp, n):
+    B, m, D2 = feat2_cl.shape
+    D1 = 0 if feat1_cl is None else feat1_cl.shape[2]
+    out = torch.empty((B, n, mlp.cout), dtype=torch.float32, device=feat2_cl.device)
+    with torch.cuda.device(feat2_cl.device):
+        _lib.call("pn2_fp_mlp", B, n, m, D1, D2, ptr(feat1_cl), ptr(feat2_cl), ptr(idx), ptr(weight), mlp.desc, ptr(out),
+                  _lib.stream_ptr(feat2_cl.device))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference surface
+# ---------------------------------------------------------------------------------------------------
+
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):
+    """xyz (B, N, 3), points (B, N, D) -> new_xyz (B, npoint, 3), new_points (B, npoint, nsample, 3 + D)
+    with the centred xyz channels FIRST (reference :41)."""
+    B, N, C = xyz.shape
+    xyz_c = xyz.contiguous()
+    xyz_cf = xyz.permute(0, 2, 1).contiguous()
+    fps_idx = pointnet2_utils.furthest_point_sample(xyz_c, npoint)
+    new_xyz = pointnet2_utils.gather_operation(xyz_cf, fps_idx).permute(0, 2, 1).contiguous()
+    idx = pointnet2_utils.ball_query(radius, nsample, xyz_c, new_xyz)
+    grouped_xyz = pointnet2_utils.grouping_operation(xyz_cf, idx).permute(0, 2, 3, 1).contiguous()
+    grouped_xyz_norm = grouped_xyz - new_xyz.view(B, npoint, 1, C)
+    if points is not None:
+        grouped_points = pointnet2_utils.grouping_operation(points.permute(0, 2, 1).contiguous(), idx)
+        new_points = torch.cat([grouped_xyz_norm, grouped_points.permute(0, 2, 3, 1).contiguous()], dim=-1)
+    else:
+        new_points = grouped_xyz_norm
+    if returnfps:
+        return new_xyz, new_points, grouped_xyz, fps_idx
+    return new_xyz, new_points
+
+
+def sample_and_group_all(xyz, points):
+    """One group of all N points; new_xyz is zeros and xyz is NOT centred (reference :50-67)."""
+    B, N, C = xyz.shape
+    new_xyz = torch.zeros(B, 1, C, device=xyz.device, dtype=xyz.dtype)
+    grouped_xyz = xyz.reshape(B, 1, N, C)
+    if points is not None:
+        new_points = torch.cat([grouped_xyz, points.reshape(B, 1, N, -1)], dim=-1)
+    else:
+        new_points = grouped_xyz
+    return new_xyz, new_points
+
+
+class PointNetSetAbstraction(nn.Module):
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all):
+        super().__init__()
+        self.npoint, self.radius, self.nsample = npoint, radius, nsample
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last = in_channel  # includes the 3 xyz channels (the caller adds them, reference :134)
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv2d(last, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(out_channel))
+            last = out_channel
+        self.group_all = group_all
+        self._fold = _FoldCache()
+
+    def folded(self):
+        return self._fold.get(self.mlp_convs, self.mlp_bns, [True] * len(self.mlp_convs))
+
+    def forward_cl(self, xyz_cl, feat_cl, geometry=None):
+        """Channel-last fused path: xyz (B, N, 3), feat (B, N, D) or None -> new_xyz (B, S, 3), (B, S, D').
+        `geometry` = (new_xyz, ball_idx) lets several modules share one sampling / ball query."""
+        if geometry is None:
+            _, new_xyz = fps_gather_cl(xyz_cl, self.npoint)
+            idx = pointnet2_utils.ball_query(self.radius, self.nsample, xyz_cl, new_xyz)
+        else:
+            new_xyz, idx = geometry
+        out = sa_mlp_max_cl(xyz_cl, feat_cl, new_xyz, idx, _lib.ORDER_XYZ_FIRST, self.folded())
+        return new_xyz, out
+
+    def forward(self, xyz, points):
+        """xyz (B, 3, N), points (B, D, N) or None -> new_xyz (B, 3, S), new_points (B, D', S)"""
+        if not self.group_all and _fusable(self, xyz, points):
+            new_xyz, out = self.forward_cl(to_channel_last(xyz), to_channel_last(points))
+            return new_xyz.permute(0, 2, 1), to_channel_first(out)
+        xyz_t = xyz.permute(0, 2, 1)
+        pts_t = points.permute(0, 2, 1) if points is not None else None
+        if self.group_all:
+            new_xyz, new_points = sample_and_group_all(xyz_t, pts_t)
+        else:
+            new_xyz, new_points = sample_and_group(self.npoint, self.radius, self.nsample, xyz_t, pts_t)
+        new_points = new_points.permute(0, 3, 2, 1)  # (B, C+D, nsample, npoint)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            new_points = F.relu(bn(conv(new_points)))
+        new_points = torch.max(new_points, 2)[0]
+        return new_xyz.permute(0, 2, 1), new_points
+
+
+class PointNetSetAbstractionMsg(nn.Module):
+    def __init__(self, npoint, radius_list, nsample_list, in_channel, mlp_list):
+        super().__init__()
+        self.npoint, self.radius_list, self.nsample_list = npoint, radius_list, nsample_list
+        self.conv_blocks = nn.ModuleList()
+        self.bn_blocks = nn.ModuleList()
+        for mlp in mlp_list:
+            convs, bns = nn.ModuleList(), nn.ModuleList()
+            last = in_channel + 3  # here in_channel EXCLUDES xyz (reference :125)
+            for out_channel in mlp:
+                convs.append(nn.Conv2d(last, out_channel, 1))
+                bns.append(nn.BatchNorm2d(out_channel))
+                last = out_channel
+            self.conv_blocks.append(convs)
+            self.bn_blocks.append(bns)
+        self._folds = [_FoldCache() for _ in mlp_list]
+
+    def folded(self, i):
+        return self._folds[i].get(self.conv_blocks[i], self.bn_blocks[i], [True] * len(self.conv_blocks[i]))
+
+    def forward_cl(self, xyz_cl, feat_cl, geometry=None):
+        """geometry = (new_xyz, [ball_idx per scale]) to share sampling / queries between modules."""
+        if geometry is None:
+            _, new_xyz = fps_gather_cl(xyz_cl, self.npoint)
+            idxs = [pointnet2_utils.ball_query(r, k, xyz_cl, new_xyz) for r, k in zip(self.radius_list, self.nsample_list)]
+        else:
+            new_xyz, idxs = geometry
+        mlps = [self.folded(i) for i in range(len(self.radius_list))]
+        B = xyz_cl.shape[0]
+        out = torch.empty((B, self.npoint, sum(m.cout for m in mlps)), dtype=torch.float32, device=xyz_cl.device)
+        off = 0
+        for idx, mlp in zip(idxs, mlps):
+            # features first, centred xyz last (reference :157); scales concatenated in order (:170)
+            sa_mlp_max_cl(xyz_cl, feat_cl, new_xyz, idx, _lib.ORDER_FEAT_FIRST, mlp, out=out, out_offset=off)
+            off += mlp.cout
+        return new_xyz, out
+
+    def forward(self, xyz, points):
+        if _fusable(self, xyz, points):
+            new_xyz, out = self.forward_cl(to_channel_last(xyz), to_channel_last(points))
+            return new_xyz.permute(0, 2, 1), to_channel_first(out)
+        xyz_t = xyz.permute(0, 2, 1)
+        pts_cf = points.contiguous() if points is not None else None
+        B, N, C = xyz_t.shape
+        S = self.npoint
+        xyz_c, xyz_cf = xyz_t.contiguous(), xyz.contiguous()
+        new_xyz = pointnet2_utils.gather_operation(
+            xyz_cf, pointnet2_utils.furthest_point_sample(xyz_c, S)).permute(0, 2, 1).contiguous()
+        outs = []
+        for i, radius in enumerate(self.radius_list):
+            K = self.nsample_list[i]
+            idx = pointnet2_utils.ball_query(radius, K, xyz_c, new_xyz)
+            grouped_xyz = pointnet2_utils.grouping_operation(xyz_cf, idx).permute(0, 2, 3, 1).contiguous()
+            grouped_xyz = grouped_xyz - new_xyz.view(B, S, 1, C)
+            if pts_cf is not None:
+                gp = pointnet2_utils.grouping_operation(pts_cf, idx).permute(0, 2, 3, 1).contiguous()
+                grouped = torch.cat([gp, grouped_xyz], dim=-1)
+            else:
+                grouped = grouped_xyz
+            grouped = grouped.permute(0, 3, 2, 1)  # (B, D, K, S)
+            for conv, bn in zip(self.conv_blocks[i], self.bn_blocks[i]):
+                grouped = F.relu(bn(conv(grouped)))
+            outs.append(torch.max(grouped, 2)[0])
+        return new_xyz.permute(0, 2, 1), torch.cat(outs, dim=1)
+
+
+class PointNetFeaturePropagation(nn.Module):
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv1d(last, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(out_channel))
+            last = out_channel
+        self._fold = _FoldCache()
+
+    def folded(self):
+        return self._fold.get(self.mlp_convs, self.mlp_bns, [True] * len(self.mlp_convs))
+
+    def forward_cl(self, xyz1_cl, xyz2_cl, feat1_cl, feat2_cl, mlp=None, nn_weights=None):
+        """xyz1 (B, N, 3), xyz2 (B, S, 3), feat1 (B, N, D1) or None, feat2 (B, S, D2) -> (B, N, D').
+        `mlp` overrides the folded stack (a network appends its head to the last block);
+        `nn_weights` = (idx, weight) computed elsewhere (e.g. on a side stream)."""
+        mlp = mlp if mlp is not None else self.folded()
+        n, m = xyz1_cl.shape[1], xyz2_cl.shape[1]
+        if m == 1:
+            idx = w = None
+        elif nn_weights is not None:
+            idx, w = nn_weights
+        else:
+            idx, w = three_nn_weights_cl(xyz1_cl, xyz2_cl)
+        return fp_mlp_cl(feat1_cl, feat2_cl, idx, w, mlp, n)
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        """xyz1 (B, 3, N), xyz2 (B, 3, S), points1 (B, D1, N) or None, points2 (B, D2, S) -> (B, D', N)"""
+        if _fusable(self, xyz1, xyz2, points1, points2):
+            out = self.forward_cl(to_channel_last(xyz1), to_channel_last(xyz2), to_channel_last(points1),
+                                  to_channel_last(points2))
+            return to_channel_first(out)
+        xyz1_t = xyz1.permute(0, 2, 1).contiguous()
+        xyz2_t = xyz2.permute(0, 2, 1).contiguous()
+        B, N, _ = xyz1_t.shape
+        S = xyz2_t.shape[1]
+        if S == 1:
+            interpolated = points2.permute(0, 2, 1).repeat(1, N, 1)
+        else:
+            dist, idx = pointnet2_utils.three_nn(xyz1_t, xyz2_t)
+            dist = torch.where(dist < 1e-10, torch.full_like(dist, 1e-10), dist)
+            weight = 1.0 / dist
+            weight = weight / torch.sum(weight, dim=-1).view(B, N, 1)
+            interpolated = pointnet2_utils.three_interpolate(points2.contiguous(), idx, weight).permute(0, 2, 1)
+        if points1 is not None:
+            new_points = torch.cat([points1.permute(0, 2, 1), interpolated], dim=-1)  # skip features FIRST (:213)
+        else:
+            new_points = interpolated
+        new_points = new_points.permute(0, 2, 1)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            new_points = F.relu(bn(conv(new_points)))
+        return new_points
