@@ -1,0 +1,334 @@
+"""bench.py -- scenes/sec of the PointNet++ SSG semseg SA+FP forward (8192-point ScanNet-shaped scenes).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference path on the host CPU cores
+
+A "step" is one forward of PointNet2SemSeg (model/pointnet2.py:131-162: 4 SA + 4 FP + head) over one batch
+of `--batch` synthetic scenes per GPU (weak scaling: per-GPU work is fixed).  One JSON line is printed by
+rank 0; see DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "multi-modal-learning-on-3d-point-clouds_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+NPOINTS = 8192
+NUM_CLASSES = 21
+METRIC = "scenes/sec PointNet++ SSG semseg SA+FP forward (8192 pts)"
+# 2 * MACs of the C1 network per scene
+FLOPS_PER_SCENE = 2 * 1250.6e6
+FP1_HEAD_FLOPS_PER_SCENE = 2 * (405.8e6 + 156.2e6)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(device):
+    from pn2_b200.models import PointNet2SemSeg
+    torch.manual_seed(0)
+    return PointNet2SemSeg(NUM_CLASSES).eval().to(device)
+
+
+def host_batches(rank, batch, count):
+    """`count` distinct pinned host batches in the loader's layout (B, N, 6) [xyz | rgb]."""
+    from pn2_b200 import scenes
+    out = []
+    for i in range(count):
+        a = torch.from_numpy(scenes.scannet_batch(100000 * rank + i * batch, batch, NPOINTS))
+        out.append(a.pin_memory() if torch.cuda.is_available() else a)
+    return out
+
+
+def cpu_reference_scenes_per_sec(steps, warmup, sample_scenes):
+    """The reference path on the host: oracle geometry (C, OpenMP) + torch CPU conv/BN, all host threads."""
+    from oracle import modules_ref
+    from oracle import oracle as orc
+    from pn2_b200 import scenes
+    from pn2_b200.models import PointNet2SemSeg
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = PointNet2SemSeg(NUM_CLASSES).eval()
+    pts = torch.from_numpy(scenes.scannet_batch(0, sample_scenes, NPOINTS)).permute(0, 2, 1).contiguous()
+    xyz, rgb = pts[:, :3], pts[:, 3:]
+    for _ in range(warmup):
+        modules_ref.semseg_forward_ref(model, xyz, rgb)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        modules_ref.semseg_forward_ref(model, xyz, rgb)
+    dt = time.perf_counter() - t0
+    return sample_scenes * steps / dt, dt / steps * 1e3, max(cores, orc.num_threads())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 4
+    value, ms, cores = cpu_reference_scenes_per_sec(args.steps, args.warmup, sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PointNet2SemSeg SSG forward, ScanNet-shaped synthetic scenes, 8192 pts; CPU step = %d scenes" % sample,
+                   "npoints": NPOINTS, "batch_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "scenes/s", "cores": cores, "kind": "port",
+                         "sample": "%d scenes per step x %d steps; restated CPU path (the reference ships no CPU implementation): "
+                                   "C oracle geometry with OpenMP + torch CPU conv/BN" % (sample, args.steps)},
+        "e2e": {"value": value, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def time_ref_gpu(model, device, batch):
+    """The reference's own CUDA kernels + cuDNN modules on this GPU (oracle/_ref), a few steps."""
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        return None
+    from oracle import ref_gpu_model
+    x = host_batches(7, batch, 1)[0].to(device).permute(0, 2, 1).contiguous()
+    xyz, rgb = x[:, :3], x[:, 3:]
+    for _ in range(3):
+        ref_gpu_model.semseg_forward(model, xyz, rgb)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        ref_gpu_model.semseg_forward(model, xyz, rgb)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    return {"value": batch / ms * 1e3, "unit": "scenes/s", "ms_per_step": ms,
+            "what": "reference CUDA kernels compiled verbatim (oracle/_ref/ref_cuda.so) + stock torch Conv/BN (cuDNN, "
+                    "TF32 allowed as torch defaults), batch %d, inputs resident, 5 steps" % batch}
+
+
+def op_rooflines(device, batch, pk):
+    """HBM-roofline figures of the standalone gather / interpolate kernels at the C1 shapes (timed alone -> burst peak)."""
+    from pn2_b200 import pointnet2_utils as pu
+    from pn2_b200.pointnet_util import fps_gather_cl, three_nn_weights_cl
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    x = host_batches(5, batch, 1)[0].to(device)
+    xyz = x[:, :, :3].contiguous()
+
+    def t_ms(fn, iters=5):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    out = {}
+    ms = t_ms(lambda: fps_gather_cl(xyz, 1024))
+    out["fps_8192_to_1024"] = {"ms": ms, "us_per_cloud_per_sm": ms * 1e3 * min(batch, 148) / batch,
+                               "clouds_in_flight": min(batch, 148), "algorithmic_gbs": batch * (12 * NPOINTS + 16 * 1024) / ms / 1e6,
+                               "note": "latency-bound (1023 dependent rounds); one CTA per cloud"}
+    _, new_xyz = fps_gather_cl(xyz, 1024)
+    i3, w3 = three_nn_weights_cl(xyz, new_xyz)
+    feats = torch.randn(batch, 128, 1024, device=device)
+    ms = t_ms(lambda: pu.three_interpolate(feats, i3, w3))
+    byts = batch * (24 * NPOINTS + 4 * 128 * 1024 + 4 * 128 * NPOINTS)
+    out["three_interpolate_c128"] = {"ms": ms, "gbs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm_gbs"]}
+    bq = pu.ball_query(0.1, 32, xyz, new_xyz)
+    f64 = torch.randn(batch, 64, NPOINTS, device=device)
+    ms = t_ms(lambda: pu.grouping_operation(f64, bq))
+    byts = batch * (4 * 1024 * 32 + 4 * 64 * NPOINTS + 4 * 64 * 1024 * 32)
+    out["group_points_c64"] = {"ms": ms, "gbs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm_gbs"]}
+    return out
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from pn2_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    pk = peaks()
+    B = args.batch
+    model = build_model(device)
+    n_rot = 4
+    hosts = host_batches(rank, B, n_rot)
+    devs = [h.to(device).permute(0, 2, 1).contiguous() for h in hosts]  # (B, 6, N) resident, as the train script feeds it
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    out_host = torch.empty((B, NPOINTS, NUM_CLASSES), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        x = devs[i % n_rot]
+        return model(x[:, :3], x[:, 3:])
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        # ---- device-resident throughput -----------------------------------------------------------
+        timers = {}
+        model.timers = timers
+        launches0 = _lib.launch_count()
+        evs = []
+        with ClockSampler(local) as clocks:
+            barrier()
+            for i in range(args.steps):
+                flush.zero_()  # L2 flush between timed steps (outside the timed events)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                step(i)
+                b.record()
+                evs.append((a, b))
+            barrier()
+        launches = _lib.launch_count() - launches0
+        model.timers = None
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        dom_ms = [a.elapsed_time(b) for a, b in timers.get("fp1_head", [])]
+        # ---- end to end: pinned host input -> H2D -> forward -> D2H of the logits --------------------
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            x = hosts[i % n_rot].to(device, non_blocking=True).permute(0, 2, 1)
+            y = model(x[:, :3], x[:, 3:])
+            out_host.copy_(y, non_blocking=True)
+        b.record()
+        barrier()
+        e2e_ms = a.elapsed_time(b)
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = t.tolist()
+    if rank == 0:
+        value = world * B * args.steps / (total_ms / 1e3)
+        e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": model.compute_dtype, "data": "synthetic",
+            "config": {"workload": "PointNet2SemSeg SSG forward (4 SA + 4 FP + head), ScanNet-shaped synthetic scenes drawn with "
+                                   "replacement, 8192 pts, batch %d per GPU, scene-sharded (no collective)" % B,
+                       "npoints": NPOINTS, "batch_per_gpu": B, "global_batch": B * world, "parallelism": "scene-sharded x%d" % world,
+                       "l2": "256 MiB flush between timed steps + %d rotating input batches" % n_rot},
+            "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": B * NPOINTS * 6 * 4,
+                    "d2h_bytes_per_step": B * NPOINTS * NUM_CLASSES * 4, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "tflops": value * FLOPS_PER_SCENE / 1e12,
+        }
+        if dom_ms:
+            ms = float(np.mean(dom_ms))
+            achieved = B * FP1_HEAD_FLOPS_PER_SCENE / (ms / 1e3) / 1e12
+            peak = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
+            line["roofline"] = {"kernel": "row_mlp (fp1 + head: 131-128-128-128-128-21 over %d rows)" % (B * NPOINTS),
+                                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                                "traffic": None, "ms": ms, "share_of_step": ms * len(dom_ms) / total_ms,
+                                "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step)"}
+        if world == 1 and not args.no_extras:
+            line["kernels"] = op_rooflines(device, B, pk)
+            line["ref_gpu"] = time_ref_gpu(model, device, B)
+            cpu_v, cpu_ms, cores = cpu_reference_scenes_per_sec(3, 1, 4)
+            line["cpu_baseline"] = {"value": cpu_v, "unit": "scenes/s", "cores": cores, "kind": "port",
+                                    "sample": "4 scenes per step x 3 steps (+1 warm-up); restated CPU path (the reference ships "
+                                              "no CPU implementation): C oracle geometry with OpenMP + torch CPU conv/BN"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=32, help="scenes per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the op rooflines / ref_gpu / cpu_baseline legs (for ncu runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

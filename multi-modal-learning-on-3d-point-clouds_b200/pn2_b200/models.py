@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, _FoldCache, _fusable, fold_conv_bn,
+from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, _FoldCache, _fusable, three_nn_weights_cl,
                             to_channel_last)
 
 
@@ -32,6 +32,8 @@ class PointNet2SemSeg(nn.Module):
         self.drop1 = nn.Dropout(0.5)
         self.conv2 = nn.Conv1d(128, num_classes, 1)
         self._head_fold = _FoldCache()
+        self.timers = None  # bench.py: dict name -> [(start_event, end_event)] recorded on the current stream
+        self.compute_dtype = "f32"
 
     def _fp1_with_head(self):
         """fp1's three layers + conv1/bn1/relu (+ eval dropout = identity) + conv2 as ONE fused stack."""
@@ -50,7 +52,15 @@ class PointNet2SemSeg(nn.Module):
         l3 = self.fp4.forward_cl(l3_xyz, l4_xyz, l3, l4)
         l2 = self.fp3.forward_cl(l2_xyz, l3_xyz, l2, l3)
         l1 = self.fp2.forward_cl(l1_xyz, l2_xyz, l1, l2)
-        return self.fp1.forward_cl(xyz_cl, l1_xyz, feat_cl, l1, mlp=self._fp1_with_head())
+        nnw = three_nn_weights_cl(xyz_cl, l1_xyz)
+        if self.timers is None:
+            return self.fp1.forward_cl(xyz_cl, l1_xyz, feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        out = self.fp1.forward_cl(xyz_cl, l1_xyz, feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw)
+        end.record()
+        self.timers.setdefault("fp1_head", []).append((start, end))
+        return out
 
     def forward(self, xyz, points):
         if _fusable(self, xyz, points):

@@ -114,8 +114,10 @@ def test_unfused_training_path_matches_fused(cuda):
     unfused.sum().backward()
     assert feat_g.grad is not None and torch.isfinite(feat_g.grad).all() and feat_g.grad.abs().sum() > 0
     fp = PointNetFeaturePropagation(8 + 32, [16]).to(cuda).train()
-    out = fp(xyz, xyz[:, :, :64].contiguous(), feat_g, unfused)
+    feat_g.grad = None
+    out = fp(xyz, xyz[:, :, :64].contiguous(), feat_g, unfused.detach())
     out.mean().backward()
+    assert feat_g.grad is not None and torch.isfinite(feat_g.grad).all()
 
 
 @pytest.mark.parametrize("B,N", [(2, 8192), (3, 2048)])
