@@ -134,6 +134,22 @@ int pn2_sa_mlp_max(int b, int n, int m, int k, int d, const float *xyz, const fl
 int pn2_fp_mlp(int b, int n, int m, int d1, int d2, const float *feat1, const float *feat2, const int32_t *idx,
                const float *weight, const pn2_mlp *mlp, float *out, void *stream);
 
+/* ---- the same two blocks on the tcgen05 tensor cores: bf16 operands, fp32 accumulation in TMEM ----
+ * Outputs agree with the fp32 entry points within bf16 rounding (2e-2 relative).  Weights are packed once
+ * (bf16, pre-swizzled UMMA tiles) with pn2_mlp_pack_bf16; biases are still read from `mlp`.
+ *
+ * first_layer_rotate: the kernels build the first operand as [features | centred xyz] (SA) or
+ * [interpolated | skip] (FP); packing rotates the first layer's weight columns to match:
+ *   SA with PN2_ORDER_XYZ_FIRST weights -> 3 (0 when d == 0);  PN2_ORDER_FEAT_FIRST -> 0;  FP -> d1. */
+int pn2_mlp_bf16_supported(const pn2_mlp *mlp);       /* 1 if the widths fit shared memory / TMEM */
+long long pn2_mlp_pack_bf16_size(const pn2_mlp *mlp); /* bytes of the packed image (16-byte aligned buffer) */
+int pn2_mlp_pack_bf16(const pn2_mlp *mlp, int first_layer_rotate, void *packed, void *stream);
+int pn2_sa_mlp_max_bf16(int b, int n, int m, int k, int d, const float *xyz, const float *feat, const float *new_xyz,
+                        const int32_t *idx, const pn2_mlp *mlp, const void *packed, float *out, int out_stride,
+                        int out_offset, void *stream);
+int pn2_fp_mlp_bf16(int b, int n, int m, int d1, int d2, const float *feat1, const float *feat2, const int32_t *idx,
+                    const float *weight, const pn2_mlp *mlp, const void *packed, float *out, void *stream);
+
 /* three_nn followed by the reference's weight computation (model/pointnet_util.py:205-208):
  * dist = sqrt(dist2); clamp 1e-10; w = 1/dist; w /= sum.  -> idx (B,n,3), weight (B,n,3) */
 int pn2_three_nn_weights(int b, int n, int m, const float *unknown, const float *known, int32_t *idx, float *weight, void *stream);

@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["abi.cu", "fps.cu", "gather_group.cu", "ball_query.cu", "interpolate.cu", "lift.cu", "row_mlp.cu"]
+SOURCES = ["abi.cu", "fps.cu", "gather_group.cu", "ball_query.cu", "interpolate.cu", "lift.cu", "row_mlp.cu", "row_mlp_tc.cu"]
 HEADERS = ["common.cuh", os.path.join(ROOT, "include", "pn2_abi.h")]
 OUT = os.path.join(HERE, "libpn2_b200.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
         results = list(ex.map(compile_one, srcs))
     objs = [o for o, _ in results]
     if force or any(changed for _, changed in results) or not os.path.exists(OUT):
-        subprocess.check_call(["nvcc", "-shared", "-o", OUT] + objs + ["-lcudart"])
+        subprocess.check_call(["nvcc", "-shared", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs + ["-lcudart"])
     return OUT
 
 

@@ -210,7 +210,7 @@ __global__ void fps_tiny_kernel(int b, int n, int m, int bs, int lg, const float
 template <int T, int P>
 int launch_reg(int b, int n, int m, const float *xyz, int32_t *idx, float *new_xyz, cudaStream_t s) {
     const size_t smem = (size_t)3 * T * P * sizeof(float);
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)  // static shared memory (the reduction slots) counts against the 48 KB default too
         PN2_CUDA(cudaFuncSetAttribute(fps_reg_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fps_reg_kernel<T, P><<<b, T, smem, s>>>(n, m, xyz, idx, new_xyz);
     PN2_LAUNCH_OK("fps_reg_kernel");

@@ -1,0 +1,655 @@
+// row_mlp_tc.cu -- fused "gather -> shared MLP -> pool/store" blocks on the 5th-gen tensor cores (bf16
+// operands, fp32 accumulation in TMEM).  Same operator contract as row_mlp.cu (the fp32 path); outputs
+// agree with it within bf16 rounding (2e-2 relative, BASELINE.json north_star).
+//
+// One CTA owns a tile of 128 rows (= UMMA M).  For every layer
+//     D[128 x N] (TMEM, fp32) = A[128 x K] (smem, bf16, K-major, 128B swizzle) * W[N x K]^T (smem, same layout)
+//   * A of layer 0 is written by the gather (grouped xyz/features, or 3-NN interpolation + skip rows);
+//     A of layer l+1 is written by the epilogue of layer l straight from TMEM (bias + ReLU + bf16 pack)
+//     into the SAME shared-memory buffer -- all MMAs of a layer are committed before its epilogue runs;
+//   * W arrives as pre-swizzled tiles (packed once by pn2_mlp_pack_bf16) through a ring of bulk-async
+//     copies (cp.async.bulk, TMA unit) that runs ahead across layer boundaries;
+//   * tcgen05.mma is issued by ONE thread, accumulators never touch registers until the epilogue's
+//     tcgen05.ld, and the final max over nsample is a CREDUX per column inside each epilogue warp
+//     (TMEM lane == row, so warp w holds exactly the 32 samples of one centroid when nsample = 32).
+// Warp roles: 0-3 gather + epilogue (TMEM lanes 32w..32w+31), 4 weight producer, 5 TMEM alloc + MMA issue.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_ROWS = 128;
+constexpr int KBLK = 64;                       // bf16 elements per 128-byte swizzle row
+constexpr int A_BLOCK_BYTES = TC_ROWS * 128;   // one k-block of A: 128 rows x 128 B
+constexpr int MAX_STAGES = 4;
+
+enum { MODE_SA = 0, MODE_FP = 1 };
+
+struct TcLayer {
+    int cin, cout;       // logical widths
+    int kpad;            // cin rounded up to 16 (MMA K granularity)
+    int npad;            // cout rounded up to 32 (MMA N, and the epilogue's 32-column loads)
+    int nblk;            // rows of one weight tile: min(npad, 256)
+    int relu;
+    const float *bias;
+    long long w_off;     // byte offset of this layer's first tile in the packed buffer
+};
+
+struct TcParams {
+    int mode, num_layers;
+    TcLayer layer[PN2_MAX_LAYERS];
+    const unsigned char *packed;
+    int stages, stage_bytes, a_bytes, tmem_cols;
+    // SA
+    int n, m, k, d;
+    long long groups;
+    const float *xyz, *feat, *new_xyz;
+    const int32_t *idx;
+    float *out;
+    int out_stride, out_offset;
+    // FP
+    long long rows;
+    int d1, d2, fp_m;
+    const float *feat1, *feat2, *weight;
+};
+
+// ---- PTX helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t <-> lane base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
+// (cute/arch/mma_sm100_desc.hpp: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;             // LBO (unused for swizzled K-major; canonical value 1)
+    d |= (uint64_t)(1024 >> 4) << 32;   // SBO: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n  (cute UMMA::InstrDescriptor)
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+}
+
+// byte offset of the 16-byte chunk holding elements [8*c8, 8*c8+8) of row r in a [rows x K] operand
+__device__ __forceinline__ uint32_t swz_chunk(int r, int c8, int rows) {
+    const int kb = c8 >> 3, c = c8 & 7;
+    return (uint32_t)(kb * rows * 128 + r * 128 + ((c ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+__device__ __forceinline__ void st_chunk(unsigned char *a, int r, int c8, const float (&v)[8]) {
+    uint4 q;
+    q.x = pack_bf16(v[0], v[1]);
+    q.y = pack_bf16(v[2], v[3]);
+    q.z = pack_bf16(v[4], v[5]);
+    q.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4 *>(a + swz_chunk(r, c8, TC_ROWS)) = q;
+}
+
+// ---- layer-0 operand: one thread per row, layout [block0 | block1 | zero pad] ---------------------------
+// SA: block0 = grouped features (D), block1 = centred xyz (3).  FP: block0 = interpolated (D2), block1 = skip (D1).
+// (pn2_mlp_pack_bf16 permutes the first layer's weight columns to this order.)
+__device__ __forceinline__ void gather_rows_tc(const TcParams &p, unsigned char *a, long long tile, int r) {
+    const int kpad = p.layer[0].kpad;
+    if (p.mode == MODE_SA) {
+        const int K = p.k, D = p.d;
+        const long long g = tile * (TC_ROWS / K) + r / K;
+        const bool ok = g < p.groups;
+        const float *f = nullptr;
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (ok) {
+            const int b = (int)(g / p.m);
+            const int pt = __ldg(p.idx + g * K + (r % K));
+            const size_t src = (size_t)b * p.n + pt;
+            f = p.feat + src * D;
+            dx = __fsub_rn(__ldg(p.xyz + src * 3 + 0), __ldg(p.new_xyz + g * 3 + 0));
+            dy = __fsub_rn(__ldg(p.xyz + src * 3 + 1), __ldg(p.new_xyz + g * 3 + 1));
+            dz = __fsub_rn(__ldg(p.xyz + src * 3 + 2), __ldg(p.new_xyz + g * 3 + 2));
+        }
+        const bool vec = ok && (D % 4 == 0);
+        for (int c8 = 0; c8 * 8 < kpad; ++c8) {
+            float v[8];
+            const int c0 = c8 * 8;
+            if (vec && c0 + 8 <= D) {
+                const float4 u0 = __ldg(reinterpret_cast<const float4 *>(f + c0));
+                const float4 u1 = __ldg(reinterpret_cast<const float4 *>(f + c0 + 4));
+                v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
+                v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + j;
+                    float x = 0.f;
+                    if (ok) {
+                        if (c < D) x = __ldg(f + c);
+                        else if (c == D) x = dx;
+                        else if (c == D + 1) x = dy;
+                        else if (c == D + 2) x = dz;
+                    }
+                    v[j] = x;
+                }
+            }
+            st_chunk(a, r, c8, v);
+        }
+    } else {
+        const int D1 = p.d1, D2 = p.d2;
+        const long long row = tile * TC_ROWS + r;
+        const bool ok = row < p.rows;
+        const float *r0 = nullptr, *r1 = nullptr, *r2 = nullptr, *f1 = nullptr;
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+        if (ok) {
+            const int b = (int)(row / p.n);
+            const float *f2 = p.feat2 + (size_t)b * p.fp_m * D2;
+            if (p.fp_m == 1) {
+                r0 = r1 = r2 = f2;  // S == 1: the coarse row is repeated (weights 1, 0, 0)
+                w0 = 1.f;
+            } else {
+                const int32_t *id = p.idx + (size_t)row * 3;
+                const float *w = p.weight + (size_t)row * 3;
+                r0 = f2 + (size_t)__ldg(id) * D2;
+                r1 = f2 + (size_t)__ldg(id + 1) * D2;
+                r2 = f2 + (size_t)__ldg(id + 2) * D2;
+                w0 = __ldg(w); w1 = __ldg(w + 1); w2 = __ldg(w + 2);
+            }
+            f1 = p.feat1 + (size_t)row * D1;
+        }
+        const bool single = p.fp_m == 1;
+        const bool vec = ok && (D2 % 4 == 0);
+        for (int c8 = 0; c8 * 8 < kpad; ++c8) {
+            float v[8];
+            const int c0 = c8 * 8;
+            if (vec && c0 + 8 <= D2) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float4 a0 = __ldg(reinterpret_cast<const float4 *>(r0 + c0 + 4 * h));
+                    if (single) {
+                        v[4 * h] = a0.x; v[4 * h + 1] = a0.y; v[4 * h + 2] = a0.z; v[4 * h + 3] = a0.w;
+                    } else {
+                        const float4 a1 = __ldg(reinterpret_cast<const float4 *>(r1 + c0 + 4 * h));
+                        const float4 a2 = __ldg(reinterpret_cast<const float4 *>(r2 + c0 + 4 * h));
+                        v[4 * h + 0] = __fmaf_rn(w2, a2.x, __fmaf_rn(w0, a0.x, __fmul_rn(w1, a1.x)));
+                        v[4 * h + 1] = __fmaf_rn(w2, a2.y, __fmaf_rn(w0, a0.y, __fmul_rn(w1, a1.y)));
+                        v[4 * h + 2] = __fmaf_rn(w2, a2.z, __fmaf_rn(w0, a0.z, __fmul_rn(w1, a1.z)));
+                        v[4 * h + 3] = __fmaf_rn(w2, a2.w, __fmaf_rn(w0, a0.w, __fmul_rn(w1, a1.w)));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + j;
+                    float x = 0.f;
+                    if (ok) {
+                        if (c < D2)
+                            x = single ? __ldg(r0 + c)
+                                       : __fmaf_rn(w2, __ldg(r2 + c), __fmaf_rn(w0, __ldg(r0 + c), __fmul_rn(w1, __ldg(r1 + c))));
+                        else if (c < D2 + D1)
+                            x = __ldg(f1 + (c - D2));
+                    }
+                    v[j] = x;
+                }
+            }
+            st_chunk(a, r, c8, v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment for the 128B-swizzled operand tiles
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char *a_buf = smem;
+    unsigned char *w_ring = smem + p.a_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(w_ring + (size_t)p.stages * p.stage_bytes);
+    // bars: [0..S) full, [S..2S) empty, [2S] a_ready, [2S+1] acc_ready; then the TMEM base slot
+    const int S = p.stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 2);
+    float *xchg = reinterpret_cast<float *>(tmem_slot + 4);  // [4 warps][32] for nsample > 32
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long tile = blockIdx.x;
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
+    const uint32_t bar_a = smem_u32(bars + 2 * MAX_STAGES), bar_acc = smem_u32(bars + 2 * MAX_STAGES + 1);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_a, TC_ROWS);
+        mbar_init(bar_acc, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===== weight producer: every tile of every layer, in MMA order, through the ring =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int l = 0; l < p.num_layers; ++l) {
+                const TcLayer &L = p.layer[l];
+                const int nkb = (L.kpad + KBLK - 1) / KBLK;
+                const int nnb = L.npad / L.nblk;
+                const uint32_t bytes = (uint32_t)L.nblk * 128u;
+                const unsigned char *src = p.packed + L.w_off;
+                for (int t = 0; t < nnb * nkb; ++t) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(bar_full + 8 * stage, bytes);
+                    bulk_g2s(smem_u32(w_ring + (size_t)stage * p.stage_bytes), src + (size_t)t * bytes, bytes,
+                             bar_full + 8 * stage);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t a_addr = smem_u32(a_buf);
+            for (int l = 0; l < p.num_layers; ++l) {
+                const TcLayer &L = p.layer[l];
+                const int nkb = (L.kpad + KBLK - 1) / KBLK;
+                const int nnb = L.npad / L.nblk;
+                const uint32_t idesc = umma_idesc(L.nblk);
+                mbar_wait(bar_a, (uint32_t)(l & 1));  // A of this layer is in shared memory
+                tc_fence_after();
+                for (int nb = 0; nb < nnb; ++nb) {
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t w_addr = smem_u32(w_ring + (size_t)stage * p.stage_bytes);
+                        const int k16n = min(KBLK, L.kpad - kb * KBLK) / 16;
+                        for (int k = 0; k < k16n; ++k) {
+                            const uint64_t ad = umma_desc(a_addr + kb * A_BLOCK_BYTES + k * 32);
+                            const uint64_t bd = umma_desc(w_addr + k * 32);
+                            tc_mma(tmem_base + (uint32_t)(nb * L.nblk), ad, bd, idesc, (uint32_t)((kb | k) != 0));
+                        }
+                        tc_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
+                        if (++stage == S) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+                tc_commit(bar_acc);  // accumulators of layer l complete
+            }
+        }
+    } else {
+        // ===== gather + epilogue warps: thread <-> row <-> TMEM lane =====
+        const int r = threadIdx.x;  // 0..127
+        gather_rows_tc(p, a_buf, tile, r);
+        fence_proxy_async();
+        mbar_arrive(bar_a);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int l = 0; l < p.num_layers; ++l) {
+            const TcLayer &L = p.layer[l];
+            const bool last = (l == p.num_layers - 1);
+            mbar_wait(bar_acc, (uint32_t)(l & 1));
+            tc_fence_after();
+            for (int c0 = 0; c0 < L.npad; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(lane_base + (uint32_t)c0, acc);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = c0 + j;
+                    const float bv = col < L.cout ? __ldg(L.bias + col) : 0.f;
+                    float x = __uint_as_float(acc[j]) + bv;
+                    v[j] = L.relu ? fmaxf(x, 0.f) : x;
+                }
+                if (!last) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float w8[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) w8[j] = v[8 * q + j];
+                        st_chunk(a_buf, r, (c0 >> 3) + q, w8);
+                    }
+                } else if (p.mode == MODE_SA) {
+                    // max over the nsample rows of each group (rows of a group are consecutive TMEM lanes)
+                    const int K = p.k;
+                    float keep = 0.f;
+                    if (K >= 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            // post-ReLU values are >= 0, so the unsigned order of the bits is the float order
+                            const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v[j], 0.f)));
+                            if (lane == j) keep = __uint_as_float(mx);
+                        }
+                        int gl = warp;           // group index within the tile
+                        if (K > 32) {
+                            // nsample 64 / 128: combine the per-warp maxima through shared memory
+                            xchg[warp * 32 + lane] = keep;
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            const int wpg = K / 32;
+                            if (warp % wpg == 0)
+                                for (int q = 1; q < wpg; ++q) keep = fmaxf(keep, xchg[(warp + q) * 32 + lane]);
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            gl = warp / wpg;
+                            if (warp % wpg != 0) gl = -1;
+                        }
+                        const long long g = tile * (TC_ROWS / K) + gl;
+                        const int col = c0 + lane;
+                        if (gl >= 0 && g < p.groups && col < L.cout)
+                            p.out[(size_t)g * p.out_stride + p.out_offset + col] = keep;
+                    } else {
+                        // nsample 16 / 8 / ...: segmented butterflies inside the warp
+                        const int gpw = 32 / K;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float x = v[j];
+                            for (int o = K / 2; o >= 1; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+                            v[j] = x;
+                        }
+                        // lane s*K of segment s holds the maxima of its group; every lane does: write 32/gpw... keep simple
+                        if (lane % K == 0) {
+                            const long long g = tile * (TC_ROWS / K) + warp * gpw + lane / K;
+                            if (g < p.groups) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const int col = c0 + j;
+                                    if (col < L.cout) p.out[(size_t)g * p.out_stride + p.out_offset + col] = v[j];
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    // FP: rows are independent; stage through the (now idle) A buffer for coalesced stores
+                    float *stg = reinterpret_cast<float *>(a_buf) + warp * (32 * 33);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+                    __syncwarp();
+                    const long long row0 = tile * TC_ROWS + warp * 32;
+                    const int col = c0 + lane;
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const long long row = row0 + rr;
+                        if (row < p.rows && col < L.cout) p.out[(size_t)row * L.cout + col] = stg[rr * 33 + lane];
+                    }
+                    __syncwarp();
+                }
+            }
+            if (!last) {
+                tc_fence_before();    // TMEM reads done before the next layer's MMAs overwrite the accumulators
+                fence_proxy_async();  // bf16 activations visible to the tensor core (async proxy)
+                mbar_arrive(bar_a);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---- weight packing -----------------------------------------------------------------------------------
+// Packed image of one layer: for nb in n-blocks, for kb in k-blocks: a [nblk rows x 64 bf16] tile, row n at n*128 B,
+// its 16-byte chunk c stored at position c ^ (n & 7) (128B swizzle), zero padded.  `perm_split` > 0 rotates the
+// source columns of layer 0 so that operand column k reads W[:, (k + perm_split) mod cin] for k < cin
+// (the gather writes [big block | small block]).
+__global__ void pack_layer_kernel(const float *__restrict__ w, int cin, int cout, int kpad, int npad, int nblk,
+                                  int perm_split, __nv_bfloat16 *__restrict__ dst) {
+    const int nkb = (kpad + KBLK - 1) / KBLK;
+    const long long total = (long long)npad * nkb * KBLK;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int k_in = (int)(e % KBLK);
+        const long long t = e / KBLK;
+        const int n_in = (int)(t % nblk);
+        const long long tt = t / nblk;
+        const int kb = (int)(tt % nkb), nb = (int)(tt / nkb);
+        const int n = nb * nblk + n_in, k = kb * KBLK + k_in;
+        float v = 0.f;
+        if (n < cout && k < cin) {
+            const int src = perm_split > 0 ? (k + perm_split) % cin : k;
+            v = w[(size_t)n * cin + src];
+        }
+        const size_t tile_off = ((size_t)nb * nkb + kb) * (size_t)nblk * KBLK;
+        const int c = k_in >> 3;
+        const size_t off = tile_off + (size_t)n_in * KBLK + (size_t)((c ^ (n_in & 7)) << 3) + (k_in & 7);
+        dst[off] = __float2bfloat16_rn(v);
+    }
+}
+
+struct Plan {
+    TcLayer layer[PN2_MAX_LAYERS];
+    int num_layers;
+    long long packed_bytes;
+    int a_bytes, stage_bytes, stages, tmem_cols;
+    size_t smem_bytes;
+    bool fits;
+};
+
+constexpr size_t TC_SMEM_LIMIT = 227 * 1024;
+constexpr int TC_TAIL_BYTES = (2 * MAX_STAGES + 2) * 8 + 16 + 4 * 32 * 4;  // barriers, TMEM slot, exchange
+
+Plan make_plan(const pn2_mlp *mlp) {
+    Plan P = {};
+    P.num_layers = mlp->num_layers;
+    long long off = 0;
+    int amax = 0, smax = 0, nmax = 32;
+    for (int l = 0; l < mlp->num_layers; ++l) {
+        TcLayer &L = P.layer[l];
+        L.cin = mlp->cin[l];
+        L.cout = mlp->cout[l];
+        L.kpad = (L.cin + 15) / 16 * 16;
+        L.npad = (L.cout + 31) / 32 * 32;
+        L.nblk = L.npad < 256 ? L.npad : 256;
+        if (L.npad % L.nblk) L.npad = (L.npad + L.nblk - 1) / L.nblk * L.nblk;
+        L.relu = mlp->relu[l];
+        L.bias = mlp->bias[l];
+        L.w_off = off;
+        const int nkb = (L.kpad + KBLK - 1) / KBLK;
+        off += (long long)L.npad * nkb * 128;
+        amax = amax > nkb ? amax : nkb;                                   // operand of this layer
+        if (l + 1 < mlp->num_layers) {
+            const int okb = (L.npad + KBLK - 1) / KBLK;                    // its epilogue writes npad columns
+            amax = amax > okb ? amax : okb;
+        }
+        smax = smax > L.nblk * 128 ? smax : L.nblk * 128;
+        nmax = nmax > L.npad ? nmax : L.npad;
+    }
+    P.packed_bytes = off;
+    P.a_bytes = amax * A_BLOCK_BYTES;
+    if (P.a_bytes < 4 * 32 * 33 * 4) P.a_bytes = ((4 * 32 * 33 * 4) + 1023) / 1024 * 1024;  // FP store staging
+    P.stage_bytes = smax;
+    P.tmem_cols = 32;
+    while (P.tmem_cols < nmax) P.tmem_cols *= 2;
+    P.fits = false;
+    for (int s = MAX_STAGES; s >= 2; --s) {
+        const size_t need = 1024 + (size_t)P.a_bytes + (size_t)s * P.stage_bytes + TC_TAIL_BYTES;
+        if (need <= TC_SMEM_LIMIT) {
+            P.stages = s;
+            P.smem_bytes = need;
+            P.fits = nmax <= 512;
+            break;
+        }
+    }
+    return P;
+}
+
+int check_mlp_tc(const char *op, const pn2_mlp *mlp, int c0) {
+    PN2_REQUIRE(mlp, "%s: null mlp", op);
+    PN2_REQUIRE(mlp->num_layers >= 1 && mlp->num_layers <= PN2_MAX_LAYERS, "%s: num_layers %d outside 1..%d", op,
+                mlp->num_layers, PN2_MAX_LAYERS);
+    int c = c0;
+    for (int l = 0; l < mlp->num_layers; ++l) {
+        PN2_REQUIRE(mlp->cin[l] == c, "%s: layer %d expects cin=%d but the previous stage produces %d", op, l, mlp->cin[l], c);
+        PN2_REQUIRE(mlp->cout[l] >= 1 && mlp->bias[l], "%s: layer %d is malformed", op, l);
+        c = mlp->cout[l];
+    }
+    return PN2_OK;
+}
+
+int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, cudaStream_t s) {
+    PN2_REQUIRE(tiles <= 2147483647ll, "row_mlp_tc: too many tiles");
+    PN2_REQUIRE(((uintptr_t)packed & 15) == 0, "row_mlp_tc: packed weights must be 16-byte aligned");
+    p.num_layers = P.num_layers;
+    for (int l = 0; l < P.num_layers; ++l) p.layer[l] = P.layer[l];
+    p.packed = (const unsigned char *)packed;
+    p.stages = P.stages;
+    p.stage_bytes = P.stage_bytes;
+    p.a_bytes = P.a_bytes;
+    p.tmem_cols = P.tmem_cols;
+    PN2_CUDA(cudaFuncSetAttribute(row_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+    row_mlp_tc_kernel<<<(unsigned)tiles, TC_THREADS, P.smem_bytes, s>>>(p);
+    PN2_LAUNCH_OK("row_mlp_tc_kernel");
+    return PN2_OK;
+}
+
+}  // namespace
+}  // namespace pn2
+
+extern "C" int pn2_mlp_bf16_supported(const pn2_mlp *mlp) {
+    if (!mlp || mlp->num_layers < 1 || mlp->num_layers > PN2_MAX_LAYERS) return 0;
+    return pn2::make_plan(mlp).fits ? 1 : 0;
+}
+
+extern "C" long long pn2_mlp_pack_bf16_size(const pn2_mlp *mlp) {
+    if (!mlp || mlp->num_layers < 1 || mlp->num_layers > PN2_MAX_LAYERS) return -1;
+    return pn2::make_plan(mlp).packed_bytes;
+}
+
+extern "C" int pn2_mlp_pack_bf16(const pn2_mlp *mlp, int first_layer_rotate, void *packed, void *stream) {
+    using namespace pn2;
+    if (int st = check_mlp_tc("mlp_pack_bf16", mlp, mlp ? mlp->cin[0] : 0)) return st;
+    PN2_REQUIRE(packed, "mlp_pack_bf16: null destination");
+    PN2_REQUIRE(first_layer_rotate >= 0 && first_layer_rotate < mlp->cin[0], "mlp_pack_bf16: rotate %d outside [0, cin)", first_layer_rotate);
+    const Plan P = make_plan(mlp);
+    for (int l = 0; l < P.num_layers; ++l) {
+        const TcLayer &L = P.layer[l];
+        PN2_REQUIRE(mlp->weight[l], "mlp_pack_bf16: layer %d has a null weight", l);
+        const long long total = (long long)L.npad * ((L.kpad + KBLK - 1) / KBLK) * KBLK;
+        const int blocks = (int)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024);
+        pack_layer_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+            mlp->weight[l], L.cin, L.cout, L.kpad, L.npad, L.nblk, l == 0 ? first_layer_rotate : 0,
+            reinterpret_cast<__nv_bfloat16 *>((unsigned char *)packed + L.w_off));
+        PN2_LAUNCH_OK("pack_layer_kernel");
+    }
+    return PN2_OK;
+}
+
+extern "C" int pn2_sa_mlp_max_bf16(int b, int n, int m, int k, int d, const float *xyz, const float *feat,
+                                   const float *new_xyz, const int32_t *idx, const pn2_mlp *mlp, const void *packed,
+                                   float *out, int out_stride, int out_offset, void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(b >= 0 && n >= 1 && m >= 0 && k >= 1 && d >= 0, "sa_mlp_max_bf16: bad dims b=%d n=%d m=%d k=%d d=%d", b, n, m, k, d);
+    if (int st = check_mlp_tc("sa_mlp_max_bf16", mlp, 3 + d)) return st;
+    if (b == 0 || m == 0) return PN2_OK;
+    PN2_REQUIRE(xyz && new_xyz && idx && out && packed && (feat || d == 0), "sa_mlp_max_bf16: null pointer");
+    const int cl = mlp->cout[mlp->num_layers - 1];
+    PN2_REQUIRE(out_offset >= 0 && out_stride >= out_offset + cl, "sa_mlp_max_bf16: out_stride/out_offset do not hold %d channels", cl);
+    if (!(k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32 || k == 64 || k == 128))
+        return set_error(PN2_ERR_UNSUPPORTED, "sa_mlp_max_bf16: nsample must be a power of two <= 128 (got %d)", k);
+    for (int l = 0; l < mlp->num_layers; ++l)
+        if (!mlp->relu[l]) return set_error(PN2_ERR_UNSUPPORTED, "sa_mlp_max_bf16: every SA layer must end in ReLU");
+    const Plan P = make_plan(mlp);
+    if (!P.fits) return set_error(PN2_ERR_UNSUPPORTED, "sa_mlp_max_bf16: channel widths exceed shared memory / TMEM; use the fp32 path");
+    TcParams p = {};
+    p.mode = MODE_SA;
+    p.n = n; p.m = m; p.k = k; p.d = d;
+    p.groups = (long long)b * m;
+    p.xyz = xyz; p.feat = feat; p.new_xyz = new_xyz; p.idx = idx;
+    p.out = out; p.out_stride = out_stride; p.out_offset = out_offset;
+    const long long tiles = (p.groups * k + TC_ROWS - 1) / TC_ROWS;
+    return launch_tc(p, P, packed, tiles, (cudaStream_t)stream);
+}
+
+extern "C" int pn2_fp_mlp_bf16(int b, int n, int m, int d1, int d2, const float *feat1, const float *feat2,
+                               const int32_t *idx, const float *weight, const pn2_mlp *mlp, const void *packed, float *out,
+                               void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(b >= 0 && n >= 0 && m >= 1 && d1 >= 0 && d2 >= 1, "fp_mlp_bf16: bad dims b=%d n=%d m=%d d1=%d d2=%d", b, n, m, d1, d2);
+    if (int st = check_mlp_tc("fp_mlp_bf16", mlp, d1 + d2)) return st;
+    if (b == 0 || n == 0) return PN2_OK;
+    PN2_REQUIRE(feat2 && out && packed && (feat1 || d1 == 0) && (m == 1 || (idx && weight)), "fp_mlp_bf16: null pointer");
+    const Plan P = make_plan(mlp);
+    if (!P.fits) return set_error(PN2_ERR_UNSUPPORTED, "fp_mlp_bf16: channel widths exceed shared memory / TMEM; use the fp32 path");
+    TcParams p = {};
+    p.mode = MODE_FP;
+    p.n = n; p.fp_m = m; p.d1 = d1; p.d2 = d2;
+    p.rows = (long long)b * n;
+    p.feat1 = feat1; p.feat2 = feat2; p.idx = idx; p.weight = weight;
+    p.out = out;
+    const long long tiles = (p.rows + TC_ROWS - 1) / TC_ROWS;
+    return launch_tc(p, P, packed, tiles, (cudaStream_t)stream);
+}

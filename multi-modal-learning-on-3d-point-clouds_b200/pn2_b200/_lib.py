@@ -44,6 +44,9 @@ _SIGNATURES = {
     "pn2_lift_views": [_c_int] * 6 + [_vp] * 7 + [ctypes.POINTER(_c_float)] + [_c_float] * 3 + [_c_int] + [_vp] * 4,
     "pn2_sa_mlp_max": [_c_int] * 5 + [_vp] * 4 + [_c_int, ctypes.POINTER(Pn2Mlp), _vp, _c_int, _c_int, _vp],
     "pn2_fp_mlp": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp],
+    "pn2_mlp_pack_bf16": [ctypes.POINTER(Pn2Mlp), _c_int, _vp, _vp],
+    "pn2_sa_mlp_max_bf16": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp, _c_int, _c_int, _vp],
+    "pn2_fp_mlp_bf16": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp, _vp],
     "pn2_three_nn_weights": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "pn2_transpose": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
 }
@@ -51,6 +54,8 @@ _OTHER = {
     "pn2_last_error": ([], ctypes.c_char_p),
     "pn2_abi_version": ([], _c_int),
     "pn2_launch_count": ([], ctypes.c_uint64),
+    "pn2_mlp_bf16_supported": ([ctypes.POINTER(Pn2Mlp)], _c_int),
+    "pn2_mlp_pack_bf16_size": ([ctypes.POINTER(Pn2Mlp)], ctypes.c_longlong),
 }
 
 EXPORTS = sorted(list(_SIGNATURES) + list(_OTHER))

@@ -12,7 +12,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, _FoldCache, _fusable, three_nn_weights_cl,
+from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, _FoldCache, _fusable, get_mlp_precision,
+                            three_nn_weights_cl,
                             to_channel_last)
 
 
@@ -33,7 +34,10 @@ class PointNet2SemSeg(nn.Module):
         self.conv2 = nn.Conv1d(128, num_classes, 1)
         self._head_fold = _FoldCache()
         self.timers = None  # bench.py: dict name -> [(start_event, end_event)] recorded on the current stream
-        self.compute_dtype = "f32"
+
+    @property
+    def compute_dtype(self):
+        return "bf16" if get_mlp_precision() == "bf16" else "f32"
 
     def _fp1_with_head(self):
         """fp1's three layers + conv1/bn1/relu (+ eval dropout = identity) + conv2 as ONE fused stack."""

@@ -16,6 +16,7 @@ Two execution paths per module:
   * training (batch statistics / autograd): the reference's own composition of operators -- our
     kernels for the geometry, torch.nn for conv/BN -- with identical semantics.
 """
+import ctypes
 from time import time
 
 import numpy as np
@@ -72,9 +73,47 @@ class FoldedMlp:
         self.desc = d
         self.cin = self.layers[0][0].shape[1]
         self.cout = self.layers[-1][0].shape[0]
+        self._packed = {}
+        self._bf16_ok = None
 
     def extended(self, more):
         return FoldedMlp(self.layers + list(more))
+
+    def bf16_ok(self):
+        """True when the widths fit the tensor-core kernel's shared memory / TMEM budget."""
+        if self._bf16_ok is None:
+            self._bf16_ok = bool(_lib.load().pn2_mlp_bf16_supported(ctypes.byref(self.desc)))
+        return self._bf16_ok
+
+    def packed(self, rotate):
+        """bf16 pre-swizzled UMMA weight tiles (pn2_mlp_pack_bf16), cached per first-layer column rotation."""
+        buf = self._packed.get(rotate)
+        if buf is None:
+            dev = self.layers[0][0].device
+            size = int(_lib.load().pn2_mlp_pack_bf16_size(ctypes.byref(self.desc)))
+            buf = torch.empty(size, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.call("pn2_mlp_pack_bf16", ctypes.byref(self.desc), int(rotate), ptr(buf), _lib.stream_ptr(dev))
+            self._packed[rotate] = buf
+        return buf
+
+
+_PRECISION = "bf16"
+
+
+def set_mlp_precision(precision):
+    """Arithmetic of the fused shared-MLP kernels: "bf16" (tcgen05 tensor cores, fp32 accumulate; outputs within
+    2e-2 relative of fp32) or "fp32" (FFMA; within 1e-5 relative of the reference).  Returns the previous value.
+    Blocks whose widths do not fit the tensor-core kernel always run in fp32."""
+    global _PRECISION
+    if precision not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    prev, _PRECISION = _PRECISION, precision
+    return prev
+
+
+def get_mlp_precision():
+    return _PRECISION
 
 
 def _param_key(mods):
@@ -152,8 +191,13 @@ def sa_mlp_max_cl(xyz_cl, feat_cl, new_xyz_cl, idx, order, mlp, out=None, out_of
     if out is None:
         out = torch.empty((B, M, mlp.cout), dtype=torch.float32, device=xyz_cl.device)
     with torch.cuda.device(xyz_cl.device):
-        _lib.call("pn2_sa_mlp_max", B, N, M, K, D, ptr(xyz_cl), ptr(feat_cl), ptr(new_xyz_cl), ptr(idx), order,
-                  mlp.desc, ptr(out), out.shape[2], out_offset, _lib.stream_ptr(xyz_cl.device))
+        if _PRECISION == "bf16" and mlp.bf16_ok():
+            rotate = (3 % mlp.cin) if order == _lib.ORDER_XYZ_FIRST else 0
+            _lib.call("pn2_sa_mlp_max_bf16", B, N, M, K, D, ptr(xyz_cl), ptr(feat_cl), ptr(new_xyz_cl), ptr(idx),
+                      mlp.desc, ptr(mlp.packed(rotate)), ptr(out), out.shape[2], out_offset, _lib.stream_ptr(xyz_cl.device))
+        else:
+            _lib.call("pn2_sa_mlp_max", B, N, M, K, D, ptr(xyz_cl), ptr(feat_cl), ptr(new_xyz_cl), ptr(idx), order,
+                      mlp.desc, ptr(out), out.shape[2], out_offset, _lib.stream_ptr(xyz_cl.device))
     return out
 
 
@@ -175,8 +219,12 @@ def fp_mlp_cl(feat1_cl, feat2_cl, idx, weight, mlp, n):
     D1 = 0 if feat1_cl is None else feat1_cl.shape[2]
     out = torch.empty((B, n, mlp.cout), dtype=torch.float32, device=feat2_cl.device)
     with torch.cuda.device(feat2_cl.device):
-        _lib.call("pn2_fp_mlp", B, n, m, D1, D2, ptr(feat1_cl), ptr(feat2_cl), ptr(idx), ptr(weight), mlp.desc, ptr(out),
-                  _lib.stream_ptr(feat2_cl.device))
+        if _PRECISION == "bf16" and mlp.bf16_ok():
+            _lib.call("pn2_fp_mlp_bf16", B, n, m, D1, D2, ptr(feat1_cl), ptr(feat2_cl), ptr(idx), ptr(weight), mlp.desc,
+                      ptr(mlp.packed(D1)), ptr(out), _lib.stream_ptr(feat2_cl.device))
+        else:
+            _lib.call("pn2_fp_mlp", B, n, m, D1, D2, ptr(feat1_cl), ptr(feat2_cl), ptr(idx), ptr(weight), mlp.desc, ptr(out),
+                      _lib.stream_ptr(feat2_cl.device))
     return out
 
 
