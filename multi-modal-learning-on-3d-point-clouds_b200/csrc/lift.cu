@@ -150,7 +150,7 @@ extern "C" int pn2_lift_views(int b, int n, int v, int c, int h, int w, const fl
     if (v > LV_MAXV) return set_error(PN2_ERR_UNSUPPORTED, "lift_views: at most %d views per cloud (got %d)", LV_MAXV, v);
     PN2_REQUIRE(reduce == PN2_REDUCE_MAX || reduce == PN2_REDUCE_FIRST, "lift_views: unknown reduce %d", reduce);
     if (b == 0 || n == 0) return PN2_OK;
-    PN2_REQUIRE(points && feats && depth && w2c && corner2 && corner4 && normals && intr && out, "lift_views: null pointer");
+    PN2_REQUIRE(points && depth && w2c && corner2 && corner4 && normals && intr && ((feats && out) || c == 0), "lift_views: null pointer");
     PN2_REQUIRE(b <= 65535, "lift_views: b exceeds the grid limit");
     dim3 grid(ceil_div(n, LV_THREADS), b);
     lift_views_kernel<<<grid, LV_THREADS, 0, (cudaStream_t)stream>>>(n, v, c, h, w, points, feats, depth, w2c, corner2, corner4,

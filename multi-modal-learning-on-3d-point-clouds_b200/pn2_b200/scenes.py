@@ -101,3 +101,55 @@ def uniform_cloud(seed, n, scale=1.0):
     """Microbench cloud: n points uniform in [0, scale)^3."""
     rng = np.random.default_rng(seed)
     return (rng.random((n, 3)) * scale).astype(np.float32)
+
+
+# ---- multi-view inputs (SURVEY.md 8d config 3) -------------------------------------------------------
+
+SCANNET_INTRINSIC = np.array([[37.01983, 0, 20, 0], [0, 38.52470, 15.5, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float32)
+SCANNET_IMAGE_DIMS = [41, 32]          # [W, H]  (train_scannet_multiview_semseg.py:109-110)
+SCANNET_DEPTH_RANGE = (0.1, 4.0)
+SCANNET_ACCURACY = 0.05
+
+
+def look_at_pose(eye, target):
+    """camera_to_world (4, 4) of a pinhole camera at `eye` looking at `target` (x right, y down, z forward)."""
+    fwd = target - eye
+    fwd = fwd / np.linalg.norm(fwd)
+    right = np.cross(fwd, np.array([0.0, 0.0, 1.0]))
+    right = right / np.linalg.norm(right)
+    down = np.cross(fwd, right)
+    m = np.eye(4)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = right, down, fwd, eye
+    return m.astype(np.float32)
+
+
+def multiview_inputs(scene_id, xyz, num_views=3, channels=128):
+    """Poses, z-buffered depth maps and random feature maps for one scene.
+
+    xyz (N, 3).  Cameras sit 1.5-3 m from the column centre looking at it; each depth map is the
+    z-buffer of the scene's own points on the 41x32 grid, so front-most points pass the 0.05 m test.
+    -> feats (V, C, 32, 41) ~ N(0,1), depth (V, 32, 41), poses (V, 4, 4)"""
+    rng = np.random.default_rng(3000 + int(scene_id))
+    W, H = SCANNET_IMAGE_DIMS
+    fx, fy, cx, cy = SCANNET_INTRINSIC[0, 0], SCANNET_INTRINSIC[1, 1], SCANNET_INTRINSIC[0, 2], SCANNET_INTRINSIC[1, 2]
+    centre = xyz.mean(0).astype(np.float64)
+    poses, depths = [], []
+    for _ in range(num_views):
+        ang = rng.uniform(0, 2 * np.pi)
+        dist = rng.uniform(1.5, 3.0)
+        eye = centre + np.array([np.cos(ang) * dist, np.sin(ang) * dist, rng.uniform(0.3, 1.5)])
+        pose = look_at_pose(eye, centre)
+        w2c = np.linalg.inv(pose.astype(np.float64))
+        cam = xyz.astype(np.float64) @ w2c[:3, :3].T + w2c[:3, 3]
+        z = cam[:, 2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = np.rint(cam[:, 0] * fx / z + cx)
+            v = np.rint(cam[:, 1] * fy / z + cy)
+        ok = (z > 0.05) & (u >= 0) & (u < W) & (v >= 0) & (v < H)
+        depth = np.full(H * W, np.inf)
+        np.minimum.at(depth, (v[ok] * W + u[ok]).astype(np.int64), z[ok])
+        depth[~np.isfinite(depth)] = 0.0
+        poses.append(pose)
+        depths.append(depth.reshape(H, W).astype(np.float32))
+    feats = rng.standard_normal((num_views, channels, H, W)).astype(np.float32)
+    return feats, np.stack(depths), np.stack(poses)

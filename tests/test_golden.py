@@ -1,0 +1,41 @@
+"""Pins the CPU oracle to golden vectors produced by the REFERENCE's own CUDA kernels on a B200
+(tests/golden/ref_cuda_r1.npz, made by tests/golden/make_golden.py).  Runs without a GPU."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NPZ = os.path.join(HERE, "golden", "ref_cuda_r1.npz")
+spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+mg = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(mg)
+
+pytestmark = pytest.mark.skipif(not os.path.exists(NPZ), reason="golden fixture not generated yet")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(NPZ)
+
+
+@pytest.mark.parametrize("name", list(mg.CASES))
+def test_oracle_matches_reference_kernels(gold, name):
+    xyz, feats, M, radius = mg.golden_inputs(name)
+    fps = orc.furthest_point_sample(xyz, M)
+    np.testing.assert_array_equal(fps, gold[name + "/fps"])
+    new_xyz = np.ascontiguousarray(orc.gather_operation(xyz.transpose(0, 2, 1), fps).transpose(0, 2, 1))
+    ball = orc.ball_query(radius, 16, xyz, new_xyz)
+    np.testing.assert_array_equal(ball, gold[name + "/ball"])
+    grouped = orc.grouping_operation(feats, ball)
+    np.testing.assert_allclose(grouped.astype(np.float64).sum((2, 3)), gold[name + "/grouped_sum"], rtol=1e-12, atol=1e-9)
+    dist, nn_idx = orc.three_nn(xyz, new_xyz)
+    np.testing.assert_array_equal(nn_idx, gold[name + "/nn_idx"])
+    np.testing.assert_array_equal(dist, gold[name + "/nn_dist"])
+    w = orc.fp_weights(dist)
+    np.testing.assert_allclose(w, gold[name + "/weight"], rtol=1e-6, atol=1e-9)
+    interp = orc.three_interpolate(np.ascontiguousarray(feats[:, :, :M]), nn_idx, gold[name + "/weight"])
+    np.testing.assert_array_equal(interp, gold[name + "/interp"])
