@@ -36,13 +36,15 @@ struct TcLayer {
     int relu;
     const float *bias;
     long long w_off;     // byte offset of this layer's first tile in the packed buffer
+    int bias_off;        // float offset of this layer's (zero padded) bias in the shared-memory copy
 };
 
 struct TcParams {
     int mode, num_layers;
     TcLayer layer[PN2_MAX_LAYERS];
     const unsigned char *packed;
-    int stages, stage_bytes, a_bytes, tmem_cols;
+    int stages, stage_bytes, a_bytes, tmem_cols, bias_floats;
+    long long tiles;
     // SA
     int n, m, k, d;
     long long groups;
@@ -54,6 +56,8 @@ struct TcParams {
     long long rows;
     int d1, d2, fp_m;
     const float *feat1, *feat2, *weight;
+    int feat_aligned;  // gathered feature rows are 16-byte aligned (float4 loads allowed)
+    long long *dbg;    // optional phase timestamps of CTA 0 / warp 0 (developer profiling; NULL in production)
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------
@@ -180,8 +184,23 @@ __device__ __forceinline__ void gather_rows_tc(const TcParams &p, unsigned char 
             dy = __fsub_rn(__ldg(p.xyz + src * 3 + 1), __ldg(p.new_xyz + g * 3 + 1));
             dz = __fsub_rn(__ldg(p.xyz + src * 3 + 2), __ldg(p.new_xyz + g * 3 + 2));
         }
-        const bool vec = ok && (D % 4 == 0);
-        for (int c8 = 0; c8 * 8 < kpad; ++c8) {
+        const bool vec = ok && (D % 4 == 0) && p.feat_aligned;
+        int c8 = 0;
+        if (vec) {
+            // 4 chunks (32 channels, 8 x LDG.128) in flight per thread before the first use
+            for (; (c8 + 4) * 8 <= D; c8 += 4) {
+                float4 u[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) u[q] = __ldg(reinterpret_cast<const float4 *>(f + c8 * 8 + 4 * q));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float v[8] = {u[2 * q].x, u[2 * q].y, u[2 * q].z, u[2 * q].w,
+                                        u[2 * q + 1].x, u[2 * q + 1].y, u[2 * q + 1].z, u[2 * q + 1].w};
+                    st_chunk(a, r, c8 + q, v);
+                }
+            }
+        }
+        for (; c8 * 8 < kpad; ++c8) {
             float v[8];
             const int c0 = c8 * 8;
             if (vec && c0 + 8 <= D) {
@@ -228,8 +247,34 @@ __device__ __forceinline__ void gather_rows_tc(const TcParams &p, unsigned char 
             f1 = p.feat1 + (size_t)row * D1;
         }
         const bool single = p.fp_m == 1;
-        const bool vec = ok && (D2 % 4 == 0);
-        for (int c8 = 0; c8 * 8 < kpad; ++c8) {
+        const bool vec = ok && (D2 % 4 == 0) && p.feat_aligned;
+        int c8 = 0;
+        if (vec && !single) {
+            // 2 chunks (16 channels) of the three neighbour rows: 12 x LDG.128 in flight per thread
+            for (; (c8 + 2) * 8 <= D2; c8 += 2) {
+                float4 a0[4], a1[4], a2[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    a0[q] = __ldg(reinterpret_cast<const float4 *>(r0 + c8 * 8 + 4 * q));
+                    a1[q] = __ldg(reinterpret_cast<const float4 *>(r1 + c8 * 8 + 4 * q));
+                    a2[q] = __ldg(reinterpret_cast<const float4 *>(r2 + c8 * 8 + 4 * q));
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float4 x0 = a0[2 * h + q], x1 = a1[2 * h + q], x2 = a2[2 * h + q];
+                        v[4 * q + 0] = __fmaf_rn(w2, x2.x, __fmaf_rn(w0, x0.x, __fmul_rn(w1, x1.x)));
+                        v[4 * q + 1] = __fmaf_rn(w2, x2.y, __fmaf_rn(w0, x0.y, __fmul_rn(w1, x1.y)));
+                        v[4 * q + 2] = __fmaf_rn(w2, x2.z, __fmaf_rn(w0, x0.z, __fmul_rn(w1, x1.z)));
+                        v[4 * q + 3] = __fmaf_rn(w2, x2.w, __fmaf_rn(w0, x0.w, __fmul_rn(w1, x1.w)));
+                    }
+                    st_chunk(a, r, c8 + h, v);
+                }
+            }
+        }
+        for (; c8 * 8 < kpad; ++c8) {
             float v[8];
             const int c0 = c8 * 8;
             if (vec && c0 + 8 <= D2) {
@@ -274,13 +319,13 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
     unsigned char *a_buf = smem;
     unsigned char *w_ring = smem + p.a_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(w_ring + (size_t)p.stages * p.stage_bytes);
-    // bars: [0..S) full, [S..2S) empty, [2S] a_ready, [2S+1] acc_ready; then the TMEM base slot
+    // bars: [0..4) full, [4..8) empty, [8] a_ready, [9] acc_ready; then the TMEM base slot, exchange, biases
     const int S = p.stages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 2);
     float *xchg = reinterpret_cast<float *>(tmem_slot + 4);  // [4 warps][32] for nsample > 32
+    float *sbias = xchg + 4 * 32;                            // all layers' biases, zero padded to npad
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long tile = blockIdx.x;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
     const uint32_t bar_a = smem_u32(bars + 2 * MAX_STAGES), bar_acc = smem_u32(bars + 2 * MAX_STAGES + 1);
 
@@ -293,31 +338,39 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
         mbar_init(bar_acc, 1);
         fence_mbar_init();
     }
+    for (int l = 0; l < p.num_layers; ++l) {
+        const TcLayer &L = p.layer[l];
+        for (int c = threadIdx.x; c < L.npad; c += TC_THREADS) sbias[L.bias_off + c] = c < L.cout ? __ldg(L.bias + c) : 0.f;
+    }
     if (warp == 5) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; barriers, TMEM and biases are set
+    // up once.  Several CTAs share an SM, so one CTA's gather / epilogue overlaps another's MMAs.
     if (warp == 4) {
         // ===== weight producer: every tile of every layer, in MMA order, through the ring =====
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int l = 0; l < p.num_layers; ++l) {
-                const TcLayer &L = p.layer[l];
-                const int nkb = (L.kpad + KBLK - 1) / KBLK;
-                const int nnb = L.npad / L.nblk;
-                const uint32_t bytes = (uint32_t)L.nblk * 128u;
-                const unsigned char *src = p.packed + L.w_off;
-                for (int t = 0; t < nnb * nkb; ++t) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * stage, bytes);
-                    bulk_g2s(smem_u32(w_ring + (size_t)stage * p.stage_bytes), src + (size_t)t * bytes, bytes,
-                             bar_full + 8 * stage);
-                    if (++stage == S) {
-                        stage = 0;
-                        phase ^= 1;
+            for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                for (int l = 0; l < p.num_layers; ++l) {
+                    const TcLayer &L = p.layer[l];
+                    const int nkb = (L.kpad + KBLK - 1) / KBLK;
+                    const int nnb = L.npad / L.nblk;
+                    const uint32_t bytes = (uint32_t)L.nblk * 128u;
+                    const unsigned char *src = p.packed + L.w_off;
+                    for (int t = 0; t < nnb * nkb; ++t) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        mbar_expect_tx(bar_full + 8 * stage, bytes);
+                        bulk_g2s(smem_u32(w_ring + (size_t)stage * p.stage_bytes), src + (size_t)t * bytes, bytes,
+                                 bar_full + 8 * stage);
+                        if (++stage == S) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
                 }
             }
@@ -326,135 +379,154 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
         // ===== MMA issuer =====
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, it = 0;
             const uint32_t a_addr = smem_u32(a_buf);
-            for (int l = 0; l < p.num_layers; ++l) {
-                const TcLayer &L = p.layer[l];
-                const int nkb = (L.kpad + KBLK - 1) / KBLK;
-                const int nnb = L.npad / L.nblk;
-                const uint32_t idesc = umma_idesc(L.nblk);
-                mbar_wait(bar_a, (uint32_t)(l & 1));  // A of this layer is in shared memory
-                tc_fence_after();
-                for (int nb = 0; nb < nnb; ++nb) {
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        mbar_wait(bar_full + 8 * stage, phase);
-                        tc_fence_after();
-                        const uint32_t w_addr = smem_u32(w_ring + (size_t)stage * p.stage_bytes);
-                        const int k16n = min(KBLK, L.kpad - kb * KBLK) / 16;
-                        for (int k = 0; k < k16n; ++k) {
-                            const uint64_t ad = umma_desc(a_addr + kb * A_BLOCK_BYTES + k * 32);
-                            const uint64_t bd = umma_desc(w_addr + k * 32);
-                            tc_mma(tmem_base + (uint32_t)(nb * L.nblk), ad, bd, idesc, (uint32_t)((kb | k) != 0));
-                        }
-                        tc_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
-                        if (++stage == S) {
-                            stage = 0;
-                            phase ^= 1;
+            for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                for (int l = 0; l < p.num_layers; ++l, ++it) {
+                    const TcLayer &L = p.layer[l];
+                    const int nkb = (L.kpad + KBLK - 1) / KBLK;
+                    const int nnb = L.npad / L.nblk;
+                    const uint32_t idesc = umma_idesc(L.nblk);
+                    mbar_wait(bar_a, it & 1);  // A of this layer is in shared memory
+                    tc_fence_after();
+                    for (int nb = 0; nb < nnb; ++nb) {
+                        for (int kb = 0; kb < nkb; ++kb) {
+                            mbar_wait(bar_full + 8 * stage, phase);
+                            tc_fence_after();
+                            const uint32_t w_addr = smem_u32(w_ring + (size_t)stage * p.stage_bytes);
+                            const int k16n = min(KBLK, L.kpad - kb * KBLK) / 16;
+                            for (int k = 0; k < k16n; ++k) {
+                                const uint64_t ad = umma_desc(a_addr + kb * A_BLOCK_BYTES + k * 32);
+                                const uint64_t bd = umma_desc(w_addr + k * 32);
+                                tc_mma(tmem_base + (uint32_t)(nb * L.nblk), ad, bd, idesc, (uint32_t)((kb | k) != 0));
+                            }
+                            tc_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
+                            if (++stage == S) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
                         }
                     }
+                    tc_commit(bar_acc);  // accumulators of layer l complete
                 }
-                tc_commit(bar_acc);  // accumulators of layer l complete
             }
         }
     } else {
         // ===== gather + epilogue warps: thread <-> row <-> TMEM lane =====
         const int r = threadIdx.x;  // 0..127
-        gather_rows_tc(p, a_buf, tile, r);
-        fence_proxy_async();
-        mbar_arrive(bar_a);
         const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int l = 0; l < p.num_layers; ++l) {
-            const TcLayer &L = p.layer[l];
-            const bool last = (l == p.num_layers - 1);
-            mbar_wait(bar_acc, (uint32_t)(l & 1));
-            tc_fence_after();
-            for (int c0 = 0; c0 < L.npad; c0 += 32) {
-                uint32_t acc[32];
-                tmem_ld32(lane_base + (uint32_t)c0, acc);
-                float v[32];
+        uint32_t it = 0;
+        long long *dbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg : nullptr;
+        int di = 0;
+        for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            if (dbg && di < 240) dbg[di++] = clock64();
+            gather_rows_tc(p, a_buf, tile, r);
+            fence_proxy_async();
+            mbar_arrive(bar_a);
+            if (dbg && di < 240) dbg[di++] = clock64();
+            for (int l = 0; l < p.num_layers; ++l, ++it) {
+                const TcLayer &L = p.layer[l];
+                const bool last = (l == p.num_layers - 1);
+                const int npad = L.npad, cout = L.cout, relu = L.relu;
+                const float *bl = sbias + L.bias_off;
+                mbar_wait(bar_acc, it & 1);
+                tc_fence_after();
+                if (dbg && di < 240) dbg[di++] = clock64();
+                for (int c0 = 0; c0 < npad; c0 += 32) {
+                    uint32_t acc[32];
+                    tmem_ld32(lane_base + (uint32_t)c0, acc);
+                    float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = c0 + j;
-                    const float bv = col < L.cout ? __ldg(L.bias + col) : 0.f;
-                    float x = __uint_as_float(acc[j]) + bv;
-                    v[j] = L.relu ? fmaxf(x, 0.f) : x;
-                }
-                if (!last) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float w8[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) w8[j] = v[8 * q + j];
-                        st_chunk(a_buf, r, (c0 >> 3) + q, w8);
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bv = *reinterpret_cast<const float4 *>(bl + c0 + 4 * q);
+                        v[4 * q + 0] = __uint_as_float(acc[4 * q + 0]) + bv.x;
+                        v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + bv.y;
+                        v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + bv.z;
+                        v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + bv.w;
                     }
-                } else if (p.mode == MODE_SA) {
-                    // max over the nsample rows of each group (rows of a group are consecutive TMEM lanes)
-                    const int K = p.k;
-                    float keep = 0.f;
-                    if (K >= 32) {
+                    if (relu) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            // post-ReLU values are >= 0, so the unsigned order of the bits is the float order
-                            const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(v[j], 0.f)));
-                            if (lane == j) keep = __uint_as_float(mx);
-                        }
-                        int gl = warp;           // group index within the tile
-                        if (K > 32) {
-                            // nsample 64 / 128: combine the per-warp maxima through shared memory
-                            xchg[warp * 32 + lane] = keep;
-                            asm volatile("bar.sync 1, 128;" ::: "memory");
-                            const int wpg = K / 32;
-                            if (warp % wpg == 0)
-                                for (int q = 1; q < wpg; ++q) keep = fmaxf(keep, xchg[(warp + q) * 32 + lane]);
-                            asm volatile("bar.sync 1, 128;" ::: "memory");
-                            gl = warp / wpg;
-                            if (warp % wpg != 0) gl = -1;
-                        }
-                        const long long g = tile * (TC_ROWS / K) + gl;
-                        const int col = c0 + lane;
-                        if (gl >= 0 && g < p.groups && col < L.cout)
-                            p.out[(size_t)g * p.out_stride + p.out_offset + col] = keep;
-                    } else {
-                        // nsample 16 / 8 / ...: segmented butterflies inside the warp
-                        const int gpw = 32 / K;
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (!last) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float x = v[j];
-                            for (int o = K / 2; o >= 1; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
-                            v[j] = x;
-                        }
-                        // lane s*K of segment s holds the maxima of its group; every lane does: write 32/gpw... keep simple
-                        if (lane % K == 0) {
-                            const long long g = tile * (TC_ROWS / K) + warp * gpw + lane / K;
-                            if (g < p.groups) {
+                        for (int q = 0; q < 4; ++q) {
+                            float w8[8];
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    const int col = c0 + j;
-                                    if (col < L.cout) p.out[(size_t)g * p.out_stride + p.out_offset + col] = v[j];
+                            for (int j = 0; j < 8; ++j) w8[j] = v[8 * q + j];
+                            st_chunk(a_buf, r, (c0 >> 3) + q, w8);
+                        }
+                    } else if (p.mode == MODE_SA) {
+                        // max over the nsample rows of each group (rows of a group are consecutive TMEM lanes)
+                        const int K = p.k;
+                        float keep = 0.f;
+                        if (K >= 32) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                // post-ReLU values are >= 0, so the unsigned order of the bits is the float order
+                                const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(v[j]));
+                                if (lane == j) keep = __uint_as_float(mx);
+                            }
+                            int gl = warp;  // group index within the tile
+                            if (K > 32) {
+                                // nsample 64 / 128: combine the per-warp maxima through shared memory
+                                xchg[warp * 32 + lane] = keep;
+                                asm volatile("bar.sync 1, 128;" ::: "memory");
+                                const int wpg = K / 32;
+                                if (warp % wpg == 0)
+                                    for (int q = 1; q < wpg; ++q) keep = fmaxf(keep, xchg[(warp + q) * 32 + lane]);
+                                asm volatile("bar.sync 1, 128;" ::: "memory");
+                                gl = (warp % wpg == 0) ? warp / wpg : -1;
+                            }
+                            const long long g = tile * (TC_ROWS / K) + gl;
+                            const int col = c0 + lane;
+                            if (gl >= 0 && g < p.groups && col < cout)
+                                p.out[(size_t)g * p.out_stride + p.out_offset + col] = keep;
+                        } else {
+                            // nsample < 32: segmented butterflies inside the warp
+                            const int gpw = 32 / K;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float x = v[j];
+                                for (int o = K / 2; o >= 1; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+                                v[j] = x;
+                            }
+                            if (lane % K == 0) {
+                                const long long g = tile * (TC_ROWS / K) + warp * gpw + lane / K;
+                                if (g < p.groups) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) {
+                                        const int col = c0 + j;
+                                        if (col < cout) p.out[(size_t)g * p.out_stride + p.out_offset + col] = v[j];
+                                    }
                                 }
                             }
                         }
-                    }
-                } else {
-                    // FP: rows are independent; stage through the (now idle) A buffer for coalesced stores
-                    float *stg = reinterpret_cast<float *>(a_buf) + warp * (32 * 33);
+                    } else {
+                        // FP: rows are independent; stage through the (now idle) A buffer for coalesced stores
+                        float *stg = reinterpret_cast<float *>(a_buf) + warp * (32 * 33);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
-                    __syncwarp();
-                    const long long row0 = tile * TC_ROWS + warp * 32;
-                    const int col = c0 + lane;
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const long long row = row0 + rr;
-                        if (row < p.rows && col < L.cout) p.out[(size_t)row * L.cout + col] = stg[rr * 33 + lane];
+                        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+                        __syncwarp();
+                        const long long row0 = tile * TC_ROWS + warp * 32;
+                        const int col = c0 + lane;
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const long long row = row0 + rr;
+                            if (row < p.rows && col < cout) p.out[(size_t)row * cout + col] = stg[rr * 33 + lane];
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
+                if (!last) {
+                    tc_fence_before();    // TMEM reads done before the next layer's MMAs overwrite the accumulators
+                    fence_proxy_async();  // bf16 activations visible to the tensor core (async proxy)
+                    mbar_arrive(bar_a);
+                }
+                if (dbg && di < 240) dbg[di++] = clock64();
             }
-            if (!last) {
-                tc_fence_before();    // TMEM reads done before the next layer's MMAs overwrite the accumulators
-                fence_proxy_async();  // bf16 activations visible to the tensor core (async proxy)
-                mbar_arrive(bar_a);
-            }
+            // the FP store staging aliases other warps' rows of A: all four warps leave the tile together
+            tc_fence_before();
+            asm volatile("bar.sync 2, 128;" ::: "memory");
         }
     }
     tc_fence_before();
@@ -494,19 +566,19 @@ struct Plan {
     TcLayer layer[PN2_MAX_LAYERS];
     int num_layers;
     long long packed_bytes;
-    int a_bytes, stage_bytes, stages, tmem_cols;
+    int a_bytes, stage_bytes, stages, tmem_cols, bias_floats;
     size_t smem_bytes;
     bool fits;
 };
 
 constexpr size_t TC_SMEM_LIMIT = 227 * 1024;
-constexpr int TC_TAIL_BYTES = (2 * MAX_STAGES + 2) * 8 + 16 + 4 * 32 * 4;  // barriers, TMEM slot, exchange
+constexpr int TC_TAIL_BYTES = (2 * MAX_STAGES + 2) * 8 + 16 + 4 * 32 * 4;  // barriers, TMEM slot, exchange (+ biases)
 
 Plan make_plan(const pn2_mlp *mlp) {
     Plan P = {};
     P.num_layers = mlp->num_layers;
     long long off = 0;
-    int amax = 0, smax = 0, nmax = 32;
+    int amax = 0, smax = 0, nmax = 32, boff = 0;
     for (int l = 0; l < mlp->num_layers; ++l) {
         TcLayer &L = P.layer[l];
         L.cin = mlp->cin[l];
@@ -518,6 +590,8 @@ Plan make_plan(const pn2_mlp *mlp) {
         L.relu = mlp->relu[l];
         L.bias = mlp->bias[l];
         L.w_off = off;
+        L.bias_off = boff;
+        boff += L.npad;
         const int nkb = (L.kpad + KBLK - 1) / KBLK;
         off += (long long)L.npad * nkb * 128;
         amax = amax > nkb ? amax : nkb;                                   // operand of this layer
@@ -534,15 +608,20 @@ Plan make_plan(const pn2_mlp *mlp) {
     P.stage_bytes = smax;
     P.tmem_cols = 32;
     while (P.tmem_cols < nmax) P.tmem_cols *= 2;
+    P.bias_floats = boff;
     P.fits = false;
-    for (int s = MAX_STAGES; s >= 2; --s) {
-        const size_t need = 1024 + (size_t)P.a_bytes + (size_t)s * P.stage_bytes + TC_TAIL_BYTES;
-        if (need <= TC_SMEM_LIMIT) {
-            P.stages = s;
-            P.smem_bytes = need;
-            P.fits = nmax <= 512;
-            break;
-        }
+    // Ring depth: prefer the deepest ring that still lets TWO CTAs share an SM (their phases overlap); fall back
+    // to whatever fits one CTA.
+    const size_t fixed = 1024 + (size_t)P.a_bytes + TC_TAIL_BYTES + (size_t)boff * 4;
+    int best = 0;
+    for (int s = MAX_STAGES; s >= 2 && !best; --s)
+        if (2 * (fixed + (size_t)s * P.stage_bytes) <= TC_SMEM_LIMIT + 1024) best = s;
+    for (int s = MAX_STAGES; s >= 2 && !best; --s)
+        if (fixed + (size_t)s * P.stage_bytes <= TC_SMEM_LIMIT) best = s;
+    if (best) {
+        P.stages = best;
+        P.smem_bytes = fixed + (size_t)best * P.stage_bytes;
+        P.fits = nmax <= 512;
     }
     return P;
 }
@@ -560,7 +639,12 @@ int check_mlp_tc(const char *op, const pn2_mlp *mlp, int c0) {
     return PN2_OK;
 }
 
+}  // namespace
+long long *take_tc_dbg();
+namespace {
+
 int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, cudaStream_t s) {
+    p.dbg = take_tc_dbg();
     PN2_REQUIRE(tiles <= 2147483647ll, "row_mlp_tc: too many tiles");
     PN2_REQUIRE(((uintptr_t)packed & 15) == 0, "row_mlp_tc: packed weights must be 16-byte aligned");
     p.num_layers = P.num_layers;
@@ -570,8 +654,17 @@ int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, c
     p.stage_bytes = P.stage_bytes;
     p.a_bytes = P.a_bytes;
     p.tmem_cols = P.tmem_cols;
+    p.bias_floats = P.bias_floats;
+    p.tiles = tiles;
     PN2_CUDA(cudaFuncSetAttribute(row_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    row_mlp_tc_kernel<<<(unsigned)tiles, TC_THREADS, P.smem_bytes, s>>>(p);
+    // persistent grid: as many CTAs as can be resident (shared memory, 512 TMEM columns, threads), at most one per tile
+    int per_sm = (int)((TC_SMEM_LIMIT + 1024) / P.smem_bytes);
+    if (per_sm > 512 / P.tmem_cols) per_sm = 512 / P.tmem_cols;
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)per_sm * sm_count();
+    if (grid > tiles) grid = tiles;
+    row_mlp_tc_kernel<<<(unsigned)grid, TC_THREADS, P.smem_bytes, s>>>(p);
     PN2_LAUNCH_OK("row_mlp_tc_kernel");
     return PN2_OK;
 }
@@ -630,6 +723,7 @@ extern "C" int pn2_sa_mlp_max_bf16(int b, int n, int m, int k, int d, const floa
     p.groups = (long long)b * m;
     p.xyz = xyz; p.feat = feat; p.new_xyz = new_xyz; p.idx = idx;
     p.out = out; p.out_stride = out_stride; p.out_offset = out_offset;
+    p.feat_aligned = (((uintptr_t)feat) & 15) == 0;
     const long long tiles = (p.groups * k + TC_ROWS - 1) / TC_ROWS;
     return launch_tc(p, P, packed, tiles, (cudaStream_t)stream);
 }
@@ -650,6 +744,13 @@ extern "C" int pn2_fp_mlp_bf16(int b, int n, int m, int d1, int d2, const float 
     p.rows = (long long)b * n;
     p.feat1 = feat1; p.feat2 = feat2; p.idx = idx; p.weight = weight;
     p.out = out;
+    p.feat_aligned = (((uintptr_t)feat2) & 15) == 0;
     const long long tiles = (p.rows + TC_ROWS - 1) / TC_ROWS;
     return launch_tc(p, P, packed, tiles, (cudaStream_t)stream);
 }
+
+// Developer hook: the next pn2_*_bf16 launch on this thread records phase timestamps (clock64 of CTA 0, thread 0:
+// tile start, gather done, then per layer accumulator-ready / epilogue-done) into `buf` (>= 240 int64, device).
+static thread_local long long *g_tc_dbg = nullptr;
+extern "C" void pn2_debug_set_tc_timestamps(long long *buf) { g_tc_dbg = buf; }
+namespace pn2 { long long *take_tc_dbg() { long long *b = g_tc_dbg; g_tc_dbg = nullptr; return b; } }

@@ -12,8 +12,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, _FoldCache, _fusable, get_mlp_precision,
-                            three_nn_weights_cl,
+from . import pointnet2_utils
+from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, _FoldCache, _fusable, fps_gather_cl,
+                            get_mlp_precision, three_nn_weights_cl,
                             to_channel_last)
 
 
@@ -34,6 +35,7 @@ class PointNet2SemSeg(nn.Module):
         self.conv2 = nn.Conv1d(128, num_classes, 1)
         self._head_fold = _FoldCache()
         self.timers = None  # bench.py: dict name -> [(start_event, end_event)] recorded on the current stream
+        self._streams = None
 
     @property
     def compute_dtype(self):
@@ -47,23 +49,71 @@ class PointNet2SemSeg(nn.Module):
         return self._head_fold.get(convs, bns, relus)
 
     def forward_fused(self, xyz, points):
-        """xyz (B, 3, N), points (B, D, N) -> (B, N, num_classes), contiguous."""
+        """xyz (B, 3, N), points (B, D, N) -> (B, N, num_classes), contiguous.
+
+        The geometry of every level depends on coordinates only, so it runs ahead of the feature path on two side
+        streams: FPS chain + 3-NN on one, ball queries on another; the fused SA/FP kernels follow on the caller's
+        stream as their indices become ready.  No collective, no host synchronisation."""
+        main = torch.cuda.current_stream(xyz.device)
+        if self._streams is None or self._streams[0].device != xyz.device:
+            self._streams = (torch.cuda.Stream(xyz.device), torch.cuda.Stream(xyz.device))
+        s_fps, s_bq = self._streams
         xyz_cl, feat_cl = to_channel_last(xyz), to_channel_last(points)
-        l1_xyz, l1 = self.sa1.forward_cl(xyz_cl, feat_cl)
-        l2_xyz, l2 = self.sa2.forward_cl(l1_xyz, l1)
-        l3_xyz, l3 = self.sa3.forward_cl(l2_xyz, l2)
-        l4_xyz, l4 = self.sa4.forward_cl(l3_xyz, l3)
-        l3 = self.fp4.forward_cl(l3_xyz, l4_xyz, l3, l4)
-        l2 = self.fp3.forward_cl(l2_xyz, l3_xyz, l2, l3)
-        l1 = self.fp2.forward_cl(l1_xyz, l2_xyz, l1, l2)
-        nnw = three_nn_weights_cl(xyz_cl, l1_xyz)
+        sas = [self.sa1, self.sa2, self.sa3, self.sa4]
+        fps_done, bq_done, nn_done = [], [], []
+        start = torch.cuda.Event()
+        start.record(main)
+        keep = []  # tensors produced on side streams and consumed on the main stream
+
+        with torch.cuda.stream(s_fps):
+            s_fps.wait_event(start)
+            levels = [xyz_cl]
+            for sa in sas:
+                _, new_xyz = fps_gather_cl(levels[-1], sa.npoint)
+                levels.append(new_xyz)
+                ev = torch.cuda.Event()
+                ev.record(s_fps)
+                fps_done.append(ev)
+        with torch.cuda.stream(s_bq):
+            balls = []
+            for i, sa in enumerate(sas):
+                s_bq.wait_event(fps_done[i])
+                balls.append(pointnet2_utils.ball_query(sa.radius, sa.nsample, levels[i], levels[i + 1]))
+                ev = torch.cuda.Event()
+                ev.record(s_bq)
+                bq_done.append(ev)
+        with torch.cuda.stream(s_fps):
+            nnw = []
+            for lvl in (3, 2, 1, 0):  # fp4 .. fp1: fine level `lvl`, coarse level `lvl + 1`
+                nnw.append(three_nn_weights_cl(levels[lvl], levels[lvl + 1]) if levels[lvl + 1].shape[1] > 1 else None)
+                ev = torch.cuda.Event()
+                ev.record(s_fps)
+                nn_done.append(ev)
+        keep += levels[1:] + balls + [t for pair in nnw if pair is not None for t in pair]
+        if not torch.cuda.is_current_stream_capturing():
+            for t in keep:
+                t.record_stream(main)
+
+        feats = [feat_cl]
+        for i, sa in enumerate(sas):
+            main.wait_event(bq_done[i])
+            _, out = sa.forward_cl(levels[i], feats[i], geometry=(levels[i + 1], balls[i]))
+            feats.append(out)
+        l1, l2, l3, l4 = feats[1:]
+        main.wait_event(nn_done[0])
+        l3 = self.fp4.forward_cl(levels[3], levels[4], l3, l4, nn_weights=nnw[0])
+        main.wait_event(nn_done[1])
+        l2 = self.fp3.forward_cl(levels[2], levels[3], l2, l3, nn_weights=nnw[1])
+        main.wait_event(nn_done[2])
+        l1 = self.fp2.forward_cl(levels[1], levels[2], l1, l2, nn_weights=nnw[2])
+        main.wait_event(nn_done[3])
         if self.timers is None:
-            return self.fp1.forward_cl(xyz_cl, l1_xyz, feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw)
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
-        out = self.fp1.forward_cl(xyz_cl, l1_xyz, feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw)
-        end.record()
-        self.timers.setdefault("fp1_head", []).append((start, end))
+            return self.fp1.forward_cl(xyz_cl, levels[1], feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw[3])
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        out = self.fp1.forward_cl(xyz_cl, levels[1], feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw[3])
+        t1.record()
+        self.timers.setdefault("fp1_head", []).append((t0, t1))
         return out
 
     def forward(self, xyz, points):
@@ -120,3 +170,30 @@ class PointNet2Backbone(nn.Module):
         l2_points = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points)
         l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
         return self.fp1(xyz, l1_xyz, None, l1_points)
+
+
+class GraphedForward:
+    """CUDA-graph replay of a fused forward for a fixed input shape: the ~20 launches on three streams become
+    one graph launch (no per-kernel Python / driver overhead).  `run(x)` copies x (device or pinned host, (B, C, N))
+    into the static input and returns the static output tensor (valid until the next run)."""
+
+    def __init__(self, model, example_xyz, example_points, warmup=3):
+        self.model = model
+        self.xyz = example_xyz.clone()
+        self.points = example_points.clone()
+        side = torch.cuda.Stream(example_xyz.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                model.forward_fused(self.xyz, self.points)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = model.forward_fused(self.xyz, self.points)
+
+    def run(self, xyz, points):
+        self.xyz.copy_(xyz, non_blocking=True)
+        self.points.copy_(points, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -59,6 +59,14 @@ def main():
     with torch.no_grad():
         t = timeit(lambda: model(x6[:, :3], x6[:, 3:]))
     print("semseg forward: med %.3f ms min %.3f -> %.0f scenes/s" % (t + (B / t[0] * 1e3,)))
+    from pn2_b200.models import GraphedForward
+    g = GraphedForward(model, x6[:, :3].contiguous(), x6[:, 3:].contiguous())
+    xa, xb = x6[:, :3].contiguous(), x6[:, 3:].contiguous()
+    t = timeit(lambda: g.run(xa, xb))
+    print("semseg forward (CUDA graph): med %.3f ms min %.3f -> %.0f scenes/s" % (t + (B / t[0] * 1e3,)))
+    with torch.no_grad():
+        ref = model(x6[:, :3], x6[:, 3:])
+    print("graph vs eager max diff", (g.run(xa, xb) - ref).abs().max().item())
     # per-stage breakdown
     from pn2_b200.pointnet_util import to_channel_last
     with torch.no_grad():
