@@ -115,6 +115,185 @@ fps_reg_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__restr
     }
 }
 
+// ---- thread-block-cluster variant ---------------------------------------------------------------------
+// One CLUSTER of C CTAs per cloud (C*T threads = 1024 = the reference block size, so the tie key of a thread's
+// points is still (bitrev(g) << QB) | i with g the thread's rank in the cluster).  Each round costs one quarter
+// (C = 4) of the single-CTA instruction issue; the CTAs exchange their warps' winners -- key and coordinates --
+// through distributed shared memory: every warp pushes one 20-byte record into each CTA of the cluster with
+// st.async, whose completion is counted (complete_tx) by that CTA's mbarrier; a CTA continues when all
+// NW*C = 32 records of the round have landed.  There is NO block barrier in the round; records and barriers are double
+// buffered by round parity.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+    return r;
+}
+
+__device__ long long *g_fps_dbg = nullptr;
+}  // namespace
+const void *g_fps_dbg_ref();
+namespace {
+
+template <int T, int P, int C>
+__global__ void __launch_bounds__(T, 1)
+fps_cluster_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__restrict__ idx_all,
+                   float *__restrict__ new_xyz_all) {
+    constexpr int NW = T / 32;
+    constexpr int G = T * C;          // threads per cloud
+    static_assert(G == 1024 && NW * C == 32, "cluster FPS assumes 1024 threads and 32 warp records per cloud");
+    extern __shared__ float smem[];
+    float *sx = smem, *sy = smem + T * P, *sz = smem + 2 * T * P;
+    __shared__ __align__(16) uint4 rec[2][32];   // {dist bits, ~tie key, x bits, y bits}
+    __shared__ float rec_z[2][32];
+    __shared__ __align__(8) unsigned long long mbar[2];
+
+    const uint32_t rank = cluster_ctarank();
+    const int cloud = blockIdx.x / C;
+    const float *xyz = xyz_all + (size_t)cloud * n * 3;
+    int32_t *idx = idx_all + (size_t)cloud * m;
+    float *new_xyz = new_xyz_all ? new_xyz_all + (size_t)cloud * m * 3 : nullptr;
+    const int tl = threadIdx.x, lane = tl & 31, warp = tl >> 5;
+    const int g = (int)rank * T + tl;
+
+    float x[P], y[P], z[P], tm[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int k = g + i * G;
+        const bool ok = k < n;
+        x[i] = ok ? xyz[3 * k + 0] : 0.f;
+        y[i] = ok ? xyz[3 * k + 1] : 0.f;
+        z[i] = ok ? xyz[3 * k + 2] : 0.f;
+        tm[i] = ok ? 1e10f : 0.f;
+        sx[i * T + tl] = x[i];
+        sy[i * T + tl] = y[i];
+        sz[i * T + tl] = z[i];
+    }
+    // Tie key of the cluster kernel: (bitrev10(g) << 22) | (i << 5) | slot.  The slot (= g / 32, the record index of
+    // this warp) is a function of g, so appending it below i does not change the order; it lets the receiver find
+    // the winning record without a ballot.
+    const int my_slot = (int)rank * NW + warp;
+    const uint32_t inv_base = 0xFFFFFFFFu - (((__brev((uint32_t)g) >> 22) << QB) | (uint32_t)my_slot);
+    if (tl == 0) {
+        const uint32_t b0 = (uint32_t)__cvta_generic_to_shared(&mbar[0]);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b0), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b0 + 8), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();  // every CTA's barriers exist before anyone stores remotely
+
+    float x1 = __ldg(xyz), y1 = __ldg(xyz + 1), z1 = __ldg(xyz + 2);
+    if (g == 0) {
+        idx[0] = 0;
+        if (new_xyz) {
+            new_xyz[0] = x1; new_xyz[1] = y1; new_xyz[2] = z1;
+        }
+    }
+    const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(&rec[0][0]);
+    const uint32_t recz_base = (uint32_t)__cvta_generic_to_shared(&rec_z[0][0]);
+    const uint32_t bar_base = (uint32_t)__cvta_generic_to_shared(&mbar[0]);
+    // remote addresses of this warp's record slot / z slot / barrier in every CTA of the cluster (parity 0)
+    uint32_t ra[C], rz[C], rb[C];
+#pragma unroll
+    for (int d = 0; d < C; ++d) {
+        ra[d] = map_to_cta(rec_base + (uint32_t)my_slot * 16u, (uint32_t)d);
+        rz[d] = map_to_cta(recz_base + (uint32_t)my_slot * 4u, (uint32_t)d);
+        rb[d] = map_to_cta(bar_base, (uint32_t)d);
+    }
+
+    for (int j = 1; j < m; ++j) {
+        const int par = j & 1;
+        // arm this round's barrier: one local arrival + 32 records x 20 bytes delivered by st.async
+        if (tl == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_base + (uint32_t)par * 8u), "r"(32 * 20)
+                         : "memory");
+        long long *dbg = (g_fps_dbg && blockIdx.x == 0 && tl == 0 && j >= 100 && j < 110) ? g_fps_dbg + (j - 100) * 4 : nullptr;
+        if (dbg) dbg[0] = clock64();
+        // update the running minima, then a pairwise (log-depth) in-thread arg-max; on ties the lower i wins
+        float bv[P];
+        int bi[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            tm[i] = fminf(dist_ref(x[i], y[i], z[i], x1, y1, z1), tm[i]);
+            bv[i] = tm[i];
+            bi[i] = i;
+        }
+#pragma unroll
+        for (int s2 = 1; s2 < P; s2 *= 2) {
+#pragma unroll
+            for (int i = 0; i + s2 < P; i += 2 * s2) {
+                const bool take = bv[i + s2] > bv[i];
+                bv[i] = take ? bv[i + s2] : bv[i];
+                bi[i] = take ? bi[i + s2] : bi[i];
+            }
+        }
+        const float best = bv[0];
+        const int besti = bi[0];
+        const uint32_t hi = __float_as_uint(best), lo = inv_base - ((uint32_t)besti << 5);
+        uint32_t whi = hi, wlo = lo;
+        warp_argmax(whi, wlo);
+        if (dbg) dbg[1] = clock64();
+        if (hi == whi && lo == wlo) {
+            // the warp's winning lane delivers (key, coordinates) to every CTA; completion is counted on that
+            // CTA's barrier (st.async + complete_tx: no fences, no block barrier)
+            const float cx = sx[besti * T + tl], cy = sy[besti * T + tl], cz = sz[besti * T + tl];
+#pragma unroll
+            for (int d = 0; d < C; ++d) {
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                                 ra[d] + (uint32_t)par * 512u),
+                             "r"(whi), "r"(wlo), "r"(__float_as_uint(cx)), "r"(__float_as_uint(cy)), "r"(rb[d] + (uint32_t)par * 8u)
+                             : "memory");
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(
+                                 rz[d] + (uint32_t)par * 128u),
+                             "r"(__float_as_uint(cz)), "r"(rb[d] + (uint32_t)par * 8u)
+                             : "memory");
+            }
+        }
+        // wait until all 32 records of this round are in OUR shared memory
+        {
+            const uint32_t bar = bar_base + (uint32_t)par * 8u;
+            const uint32_t parity = (uint32_t)((j - 1) >> 1) & 1u;  // each barrier is used every other round
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "CWAIT:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra CDONE;\n\t"
+                "bra CWAIT;\n\t"
+                "CDONE:\n\t"
+                "}" ::"r"(bar), "r"(parity)
+                : "memory");
+        }
+        if (dbg) dbg[2] = clock64();
+        const uint2 key = *reinterpret_cast<const uint2 *>(&rec[par][lane]);
+        uint32_t ghi = key.x, glo = key.y;
+        warp_argmax(ghi, glo);
+        const uint32_t tie = 0xFFFFFFFFu - glo;
+        const int src = (int)(tie & 31u);
+        const uint4 win = rec[par][src];  // broadcast read of the winning record
+        x1 = __uint_as_float(win.z);
+        y1 = __uint_as_float(win.w);
+        z1 = rec_z[par][src];
+        if (dbg) dbg[3] = clock64() + (long long)(z1 != 12345.f ? 0 : 1);
+        if (g == 0) {
+            const int k = (int)((tie & QMASK) >> 5) * 1024 + (int)(__brev(tie >> QB) >> 22);
+            idx[j] = k;
+            if (new_xyz) {
+                new_xyz[3 * j] = x1; new_xyz[3 * j + 1] = y1; new_xyz[3 * j + 2] = z1;
+            }
+        }
+    }
+    cluster_sync_all();  // nobody leaves while a peer may still write into its shared memory
+}
+
 // Any N >= 1024 with the running minima in global memory (`temp`, caller scratch as in the
 // reference).  Used only when the cloud exceeds what the on-chip kernels hold.
 __global__ void __launch_bounds__(1024, 1)
@@ -217,6 +396,29 @@ int launch_reg(int b, int n, int m, const float *xyz, int32_t *idx, float *new_x
     return PN2_OK;
 }
 
+template <int P>
+int launch_cluster(int b, int n, int m, const float *xyz, int32_t *idx, float *new_xyz, cudaStream_t s) {
+    constexpr int T = 256, C = 4;
+    const size_t smem = (size_t)3 * T * P * sizeof(float);
+    if (smem > 40 * 1024)
+        PN2_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<T, P, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)b * C);
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PN2_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<T, P, C>, n, m, xyz, idx, new_xyz));
+    count_launch();
+    return PN2_OK;
+}
+
 template <int T>
 int launch_reg_small(int b, int n, int m, const float *xyz, int32_t *idx, float *new_xyz, cudaStream_t s) {
     return n <= T ? launch_reg<T, 1>(b, n, m, xyz, idx, new_xyz, s) : launch_reg<T, 2>(b, n, m, xyz, idx, new_xyz, s);
@@ -225,8 +427,14 @@ int launch_reg_small(int b, int n, int m, const float *xyz, int32_t *idx, float 
 }  // namespace
 }  // namespace pn2
 
+// 0 = automatic, 1 = always one CTA per cloud, 2 = always the cluster kernel (tests / benchmarking)
+static int g_fps_mode = 0;
+extern "C" void pn2_debug_set_fps_mode(int mode) { g_fps_mode = mode; }
+extern "C" void pn2_debug_set_fps_stamps(long long *buf) { cudaMemcpyToSymbol(pn2::g_fps_dbg_ref(), &buf, sizeof(buf)); }
+
 namespace pn2 {
 namespace {
+int fps_force_mode() { return g_fps_mode; }
 int fps_impl(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, float *new_xyz, void *stream) {
     PN2_REQUIRE(b >= 0 && n >= 1, "fps: need b >= 0 and n >= 1 (got b=%d n=%d)", b, n);
     if (b == 0 || m <= 0) return PN2_OK;  // the reference kernel returns at once for m <= 0 (sampling_gpu.cu:101)
@@ -250,6 +458,15 @@ int fps_impl(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, f
         default: break;
     }
     if (n <= 1024) return launch_reg<1024, 1>(b, n, m, xyz, idx, new_xyz, s);
+    // Few clouds: split each over a 4-CTA cluster (4x less issue per round, DSMEM exchange).  Many clouds: one CTA
+    // per cloud already fills the SMs and avoids the exchange latency.
+    const bool use_cluster = fps_force_mode() == 2 || (fps_force_mode() == 0 && (long long)b * 4 <= sm_count());
+    if (use_cluster || n > 8192) {
+        if (n <= 2048) return launch_cluster<2>(b, n, m, xyz, idx, new_xyz, s);
+        if (n <= 4096) return launch_cluster<4>(b, n, m, xyz, idx, new_xyz, s);
+        if (n <= 8192) return launch_cluster<8>(b, n, m, xyz, idx, new_xyz, s);
+        if (n <= 16384) return launch_cluster<16>(b, n, m, xyz, idx, new_xyz, s);
+    }
     if (n <= 2048) return launch_reg<1024, 2>(b, n, m, xyz, idx, new_xyz, s);
     if (n <= 4096) return launch_reg<1024, 4>(b, n, m, xyz, idx, new_xyz, s);
     if (n <= 8192) return launch_reg<1024, 8>(b, n, m, xyz, idx, new_xyz, s);
@@ -262,6 +479,8 @@ int fps_impl(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, f
 }
 }  // namespace
 }  // namespace pn2
+
+const void *pn2::g_fps_dbg_ref() { return (const void *)&pn2::g_fps_dbg; }
 
 extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int32_t *idx,
                                            void *stream) {

@@ -55,6 +55,8 @@ _OTHER = {
     "pn2_abi_version": ([], _c_int),
     "pn2_launch_count": ([], ctypes.c_uint64),
     "pn2_mlp_bf16_supported": ([ctypes.POINTER(Pn2Mlp)], _c_int),
+    "pn2_debug_set_fps_mode": ([_c_int], None),
+    "pn2_debug_set_tc_timestamps": ([_vp], None),
     "pn2_mlp_pack_bf16_size": ([ctypes.POINTER(Pn2Mlp)], ctypes.c_longlong),
 }
 

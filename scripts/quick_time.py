@@ -41,6 +41,11 @@ def main():
     for (n, m) in [(8192, 1024), (1024, 256), (256, 64), (64, 16)]:
         x = xyz[:, :n].contiguous()
         print("fps %d->%d: med %.3f ms min %.3f" % ((n, m) + timeit(lambda: fps_gather_cl(x, m))))
+    from pn2_b200 import _lib as L
+    for mode in (1, 2):
+        L.load().pn2_debug_set_fps_mode(mode)
+        print("fps 8192->1024 mode %d: med %.3f ms min %.3f" % ((mode,) + timeit(lambda: fps_gather_cl(xyz, 1024))))
+    L.load().pn2_debug_set_fps_mode(0)
     idx, new_xyz = fps_gather_cl(xyz, 1024)
     print("ball_query r=.1: med %.3f min %.3f" % timeit(lambda: pu.ball_query(0.1, 32, xyz, new_xyz)))
     print("three_nn_w 8192x1024: med %.3f min %.3f" % timeit(lambda: three_nn_weights_cl(xyz, new_xyz)))

@@ -51,6 +51,22 @@ def test_fps_bit_exact(cuda, kind, B, N, M):
         np.testing.assert_array_equal(got, ref)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("kind,B,N,M", [("scannet", 3, 8192, 1024), ("dup", 2, 8192, 700), ("lattice", 2, 4096, 300),
+                                        ("dup", 2, 3000, 200), ("uniform", 2, 1025, 64), ("dup", 1, 16384, 300),
+                                        ("uniform", 1, 12000, 150), ("dup", 2, 2048, 2100)])
+def test_fps_single_cta_and_cluster_kernels_agree_with_reference(cuda, mode, kind, B, N, M):
+    """Both on-chip FPS kernels (one CTA per cloud / four-CTA cluster with DSMEM exchange) are bit-exact."""
+    from pn2_b200 import _lib
+    xyz = clouds(kind, B, N, 3 * N + M)
+    _lib.load().pn2_debug_set_fps_mode(mode)
+    try:
+        got = pu.furthest_point_sample(dev(xyz, cuda), M).cpu().numpy()
+    finally:
+        _lib.load().pn2_debug_set_fps_mode(0)
+    np.testing.assert_array_equal(got, orc.furthest_point_sample(xyz, M))
+
+
 def test_fps_properties_full_size(cuda):
     # BASELINE config size, properties that need no oracle: first index 0, unique picks while distinct
     # points remain, and the running minimum distance of the picks is non-increasing.
