@@ -158,6 +158,24 @@ int pn2_three_nn_weights(int b, int n, int m, const float *unknown, const float 
  * in (B,R,Cc) -> out (B,Cc,R) */
 int pn2_transpose(int b, int r, int c, const float *in, float *out, void *stream);
 
+/* ---- exact neighbour search through a per-cloud uniform grid (csrc/grid.cu) ----
+ * Same results as pn2_ball_query / pn2_three_nn (bit-identical), without the brute-force scan.
+ * pn2_grid_build sorts each cloud (n <= pn2_grid_max_points()) by cell:
+ *   sorted (B,n,4) fp32 {x,y,z,bits(original index)}, 16-byte aligned; cell_start (B, pn2_grid_table_stride()) int32;
+ *   order (B,n) int32 = original index of the i-th sorted point (may be NULL); meta (B,8) words;
+ *   cell <= 0 picks a cell size from the bounding box.  For ball queries use cell >= 1.01 * radius. */
+int pn2_grid_max_points(void);
+int pn2_grid_table_stride(void);
+int pn2_grid_build(int b, int n, const float *xyz, float cell, float *sorted, int32_t *cell_start, int32_t *order,
+                   float *meta, void *stream);
+int pn2_ball_query_grid(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
+                        const float *sorted, const int32_t *cell_start, const float *meta, int32_t *idx, void *stream);
+/* grid over the KNOWN set (m points); query_order (B,n) optional processing order of the unknown points;
+ * dist2 (squared) and weight (model/pointnet_util.py:205-208) are optional outputs. */
+int pn2_three_nn_grid(int b, int n, int m, const float *unknown, const float *known, const float *sorted,
+                      const int32_t *cell_start, const float *meta, const int32_t *query_order, float *dist2,
+                      int32_t *idx, float *weight, void *stream);
+
 /* ---- developer hooks (tests / profiling; not part of the operator surface) ---- */
 /* FPS kernel choice for 1024 < n <= 8192: 0 automatic, 1 one CTA per cloud, 2 four-CTA cluster per cloud. */
 void pn2_debug_set_fps_mode(int mode);

@@ -1,0 +1,407 @@
+// grid.cu -- exact neighbour search through a per-cloud uniform grid (cell list).
+//
+// The reference's ball query and 3-NN are brute force: every query scans all N points
+// (utils/src/ball_query_gpu.cu:28-44, interpolate_gpu.cu:30-49).  Their RESULTS are what parity is judged on
+// (first nsample hits in ascending index order; the three smallest (distance, index) pairs), not the scan.
+// Here each cloud is sorted once by grid cell (one CTA per cloud, bitonic sort in shared memory) and a query only
+// tests the points of the cells its ball can touch; candidate distances use the same fp32 rounding sequence
+// (dist_ref), candidate cells are chosen with a safety margin far above fp32 rounding error, and the ordering
+// rules are re-established explicitly (rank by index / lexicographic (d, idx) top-3), so the outputs are
+// bit-identical to the brute-force scan.  Queries whose neighbourhood is too dense for the fixed-size buffers
+// fall back to the ordered brute-force scan inside the same kernel.
+//
+// The sorted order doubles as a spatially coherent row order for the feature-propagation gather (row_mlp_tc.cu).
+#include "common.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int GRID_MAX_N = 8192;        // points per cloud the single-CTA sort handles
+constexpr int GRID_MAX_CELLS = 1 << 16; // cells per cloud (dense start table)
+constexpr int GRID_MAX_DIM = 1024;
+
+struct GridMeta {  // 8 words per cloud
+    float ox, oy, oz, inv_h;
+    int dx, dy, dz, ncells;
+};
+
+__device__ __forceinline__ int cell_coord(float p, float o, float inv_h, int dim) {
+    // monotone non-decreasing in p (fp32 sub / mul are monotone), clamped to the grid
+    float v = (p - o) * inv_h;
+    v = fminf(fmaxf(v, 0.f), (float)(dim - 1));
+    return (int)v;
+}
+
+// One CTA per cloud: bounding box, cell of every point, bitonic sort of (cell, index), dense cell-start table.
+__global__ void __launch_bounds__(1024, 1)
+grid_build_kernel(int n, float h, const float *__restrict__ xyz_all, float4 *__restrict__ sorted_all,
+                  int32_t *__restrict__ cell_start_all, int32_t *__restrict__ order_all, GridMeta *__restrict__ meta_all) {
+    extern __shared__ unsigned long long keys[];  // np2 entries
+    __shared__ float red[6][32];
+    __shared__ GridMeta sm;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float *xyz = xyz_all + (size_t)b * n * 3;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+
+    float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int k = t; k < n; k += 1024) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = xyz[3 * k + a];
+            mn[a] = fminf(mn[a], v);
+            mx[a] = fmaxf(mx[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        if (lane == 0) {
+            red[a][warp] = mn[a];
+            red[3 + a][warp] = mx[a];
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = red[a][0];
+            hi[a] = red[3 + a][0];
+            for (int w = 1; w < 32; ++w) {
+                lo[a] = fminf(lo[a], red[a][w]);
+                hi[a] = fmaxf(hi[a], red[3 + a][w]);
+            }
+        }
+        // h <= 0: pick the cell from the bounding box so that a cell holds about one point
+        float hh = h;
+        if (!(hh > 0.f)) {
+            float e0 = hi[0] - lo[0], e1 = hi[1] - lo[1], e2 = hi[2] - lo[2];
+            const float emax = fmaxf(e0, fmaxf(e1, e2)), emin = fminf(e0, fminf(e1, e2));
+            const float emid = e0 + e1 + e2 - emax - emin;
+            if (emin < 0.05f * emax)
+                hh = sqrtf(fmaxf(emax * fmaxf(emid, 1e-6f * emax), 1e-30f) / (float)n);  // (nearly) planar cloud
+            else
+                hh = cbrtf(e0 * e1 * e2 / (float)n);
+            hh = fmaxf(hh, 1e-6f);
+        }
+        // grow the cell until the dense table fits; a larger cell only adds candidates, never loses one
+        int d[3];
+        for (int iter = 0; iter < 64; ++iter) {
+            const float inv = 1.0f / hh;
+            long long cells = 1;
+            for (int a = 0; a < 3; ++a) {
+                float e = (hi[a] - lo[a]) * inv;
+                e = fminf(e, (float)(GRID_MAX_DIM - 1));
+                d[a] = (int)e + 1;
+                cells *= d[a];
+            }
+            if (cells <= GRID_MAX_CELLS) break;
+            hh *= 1.26f;
+        }
+        sm.ox = lo[0]; sm.oy = lo[1]; sm.oz = lo[2];
+        sm.inv_h = 1.0f / hh;
+        sm.dx = d[0]; sm.dy = d[1]; sm.dz = d[2];
+        sm.ncells = d[0] * d[1] * d[2];
+        meta_all[b] = sm;
+    }
+    __syncthreads();
+    const GridMeta g = sm;
+    for (int k = t; k < np2; k += 1024) {
+        unsigned long long key = ~0ull;
+        if (k < n) {
+            const int cx = cell_coord(xyz[3 * k], g.ox, g.inv_h, g.dx);
+            const int cy = cell_coord(xyz[3 * k + 1], g.oy, g.inv_h, g.dy);
+            const int cz = cell_coord(xyz[3 * k + 2], g.oz, g.inv_h, g.dz);
+            const unsigned cell = (unsigned)(cx + g.dx * (cy + g.dy * cz));
+            key = ((unsigned long long)cell << 32) | (unsigned)k;
+        }
+        keys[k] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = t; i < np2 / 2; i += 1024) {
+                const int lo_i = 2 * i - (i & (stride - 1));   // insert a zero bit at position log2(stride)
+                const int hi_i = lo_i + stride;
+                const bool up = (lo_i & size) == 0;
+                const unsigned long long a = keys[lo_i], c = keys[hi_i];
+                if ((a > c) == up) {
+                    keys[lo_i] = c;
+                    keys[hi_i] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    float4 *sorted = sorted_all + (size_t)b * n;
+    int32_t *order = order_all ? order_all + (size_t)b * n : nullptr;
+    int32_t *cell_start = cell_start_all + (size_t)b * (GRID_MAX_CELLS + 1);
+    for (int i = t; i <= n; i += 1024) {
+        const int c_prev = i > 0 ? (int)(keys[i - 1] >> 32) : -1;
+        const int c_cur = i < n ? (int)(keys[i] >> 32) : g.ncells;
+        for (int c = c_prev + 1; c <= c_cur; ++c) cell_start[c] = i;
+        if (i < n) {
+            const int k = (int)(keys[i] & 0xffffffffu);
+            sorted[i] = make_float4(xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2], __int_as_float(k));
+            if (order) order[i] = k;
+        }
+    }
+}
+
+// ---- ball query ------------------------------------------------------------------------------------------
+constexpr int BQG_WARPS = 8;
+constexpr int BQG_CAP = 128;   // hits buffered per query before falling back to the ordered scan
+constexpr int BQG_MAX_ROWS = 16;
+
+__global__ void __launch_bounds__(BQG_WARPS * 32)
+ball_query_grid_kernel(int n, int m, float radius, int nsample, const float *__restrict__ new_xyz_all,
+                       const float *__restrict__ xyz_all, const float4 *__restrict__ sorted_all,
+                       const int32_t *__restrict__ cell_start_all, const GridMeta *__restrict__ meta_all,
+                       int32_t *__restrict__ idx_all) {
+    __shared__ int hits[BQG_WARPS][BQG_CAP];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * BQG_WARPS + warp;
+    if (q >= m) return;
+    const GridMeta g = meta_all[b];
+    const float4 *sorted = sorted_all + (size_t)b * n;
+    const int32_t *cell_start = cell_start_all + (size_t)b * (GRID_MAX_CELLS + 1);
+    const float *c = new_xyz_all + ((size_t)b * m + q) * 3;
+    const float qx = c[0], qy = c[1], qz = c[2];
+    const float r2 = __fmul_rn(radius, radius);
+    const float rm = fabsf(radius) * 1.001f + 1e-30f;  // candidate margin >> fp32 rounding of the distance
+    int32_t *out = idx_all + ((size_t)b * m + q) * nsample;
+    int *hb = hits[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    const int cx0 = cell_coord(qx - rm, g.ox, g.inv_h, g.dx), cx1 = cell_coord(qx + rm, g.ox, g.inv_h, g.dx);
+    const int cy0 = cell_coord(qy - rm, g.oy, g.inv_h, g.dy), cy1 = cell_coord(qy + rm, g.oy, g.inv_h, g.dy);
+    const int cz0 = cell_coord(qz - rm, g.oz, g.inv_h, g.dz), cz1 = cell_coord(qz + rm, g.oz, g.inv_h, g.dz);
+    const int ny = cy1 - cy0 + 1, nrows = ny * (cz1 - cz0 + 1);
+    int cnt = 0;
+    bool overflow = nrows > BQG_MAX_ROWS || !(radius == radius);
+    if (!overflow) {
+        // lane l < nrows owns row l: the cells (cx0..cx1, cy, cz) are one contiguous run of the sorted cloud
+        int rs = 0, re = 0;
+        if (lane < nrows) {
+            const int cy = cy0 + lane % ny, cz = cz0 + lane / ny;
+            const int base = g.dx * (cy + g.dy * cz);
+            rs = __ldg(cell_start + base + cx0);
+            re = __ldg(cell_start + base + cx1 + 1);
+        }
+        for (int row = 0; row < nrows && !overflow; ++row) {
+            const int s = __shfl_sync(0xffffffffu, rs, row), e = __shfl_sync(0xffffffffu, re, row);
+            for (int p0 = s; p0 < e; p0 += 32) {
+                const int p = p0 + lane;
+                bool hit = false;
+                int k = 0;
+                if (p < e) {
+                    const float4 v = __ldg(sorted + p);
+                    k = __float_as_int(v.w);
+                    hit = dist_ref(qx, qy, qz, v.x, v.y, v.z) < r2;
+                }
+                const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                const int pos = cnt + __popc(mask & lt_mask);
+                if (hit && pos < BQG_CAP) hb[pos] = k;
+                cnt += __popc(mask);
+            }
+            if (cnt > BQG_CAP) overflow = true;
+        }
+    }
+    if (overflow) {
+        // dense neighbourhood (or oversized ball): ordered scan of the original cloud with early exit, as the reference
+        const float *xyz = xyz_all + (size_t)b * n * 3;
+        int c2 = 0, first = 0;
+        for (int p0 = 0; p0 < n && c2 < nsample; p0 += 32) {
+            const int p = p0 + lane;
+            const bool hit = (p < n) && (dist_ref(qx, qy, qz, __ldg(xyz + 3 * p), __ldg(xyz + 3 * p + 1), __ldg(xyz + 3 * p + 2)) < r2);
+            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            if (mask) {
+                if (c2 == 0) first = p0 + __ffs(mask) - 1;
+                const int pos = c2 + __popc(mask & lt_mask);
+                if (hit && pos < nsample) out[pos] = p;
+                c2 += __popc(mask);
+            }
+        }
+        for (int l = c2 + lane; l < nsample; l += 32) out[l] = first;
+        return;
+    }
+    __syncwarp();
+    // the first nsample hits in ascending index order = the nsample smallest indices: rank by counting
+    int first = 0x7fffffff;
+    for (int i = lane; i < cnt; i += 32) {
+        const int mine = hb[i];
+        int rank = 0;
+        for (int j = 0; j < cnt; ++j) rank += (hb[j] < mine);
+        if (rank < nsample) out[rank] = mine;
+        first = min(first, mine);
+    }
+    for (int o = 16; o; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    if (cnt == 0) first = 0;
+    for (int l = cnt + lane; l < nsample; l += 32) out[l] = first;
+}
+
+// ---- three nearest neighbours (+ the reference's interpolation weights) --------------------------------------
+struct Best3 {
+    float d1, d2, d3;
+    int i1, i2, i3;
+};
+
+__device__ __forceinline__ bool before(float d, int i, float bd, int bi) { return d < bd || (d == bd && i < bi); }
+
+// (d, index) lexicographic insertion: the same final state as the reference's ascending strict-'<' scan
+__device__ __forceinline__ void best3_insert(Best3 &t, float d, int k) {
+    if (before(d, k, t.d3, t.i3)) {
+        if (before(d, k, t.d1, t.i1)) {
+            t.d3 = t.d2; t.i3 = t.i2;
+            t.d2 = t.d1; t.i2 = t.i1;
+            t.d1 = d;    t.i1 = k;
+        } else if (before(d, k, t.d2, t.i2)) {
+            t.d3 = t.d2; t.i3 = t.i2;
+            t.d2 = d;    t.i2 = k;
+        } else {
+            t.d3 = d;    t.i3 = k;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+three_nn_grid_kernel(int n, int m, const float *__restrict__ unknown_all, const float *__restrict__ known_all,
+                     const float4 *__restrict__ sorted_all, const int32_t *__restrict__ cell_start_all,
+                     const GridMeta *__restrict__ meta_all, const int32_t *__restrict__ query_order,
+                     float *__restrict__ dist2_out, int32_t *__restrict__ idx_out, float *__restrict__ weight_out) {
+    const int b = blockIdx.y;
+    const int slot = blockIdx.x * 128 + threadIdx.x;
+    if (slot >= n) return;
+    // optional spatially coherent processing order (neighbouring threads then walk the same cells)
+    const int i = query_order ? __ldg(query_order + (size_t)b * n + slot) : slot;
+    const GridMeta g = meta_all[b];
+    const float4 *sorted = sorted_all + (size_t)b * m;
+    const int32_t *cell_start = cell_start_all + (size_t)b * (GRID_MAX_CELLS + 1);
+    const float *u = unknown_all + ((size_t)b * n + i) * 3;
+    const float ux = u[0], uy = u[1], uz = u[2];
+    const float h = 1.0f / g.inv_h;
+    const float INF = __int_as_float(0x7f800000);
+    Best3 t;
+    const int cx = cell_coord(ux, g.ox, g.inv_h, g.dx), cy = cell_coord(uy, g.oy, g.inv_h, g.dy),
+              cz = cell_coord(uz, g.oz, g.inv_h, g.dz);
+    bool done = false;
+    for (int ring = 1; ring <= 2 && !done; ++ring) {
+        t.d1 = t.d2 = t.d3 = INF;
+        t.i1 = t.i2 = t.i3 = 0x7fffffff;
+        const int x0 = max(cx - ring, 0), x1 = min(cx + ring, g.dx - 1);
+        const int y0 = max(cy - ring, 0), y1 = min(cy + ring, g.dy - 1);
+        const int z0 = max(cz - ring, 0), z1 = min(cz + ring, g.dz - 1);
+        for (int zc = z0; zc <= z1; ++zc)
+            for (int yc = y0; yc <= y1; ++yc) {
+                const int base = g.dx * (yc + g.dy * zc);
+                const int s = __ldg(cell_start + base + x0), e = __ldg(cell_start + base + x1 + 1);
+                for (int p = s; p < e; ++p) {
+                    const float4 v = __ldg(sorted + p);
+                    best3_insert(t, dist_ref(ux, uy, uz, v.x, v.y, v.z), __float_as_int(v.w));
+                }
+            }
+        // Every known point outside the scanned block is at least `rho` away: the distance from the query to the
+        // nearest face of the block that still has grid beyond it (faces on the grid boundary bound nothing:
+        // all known points lie inside the grid).
+        float rho = INF;
+        if (cx - ring > 0) rho = fminf(rho, ux - (g.ox + (float)(cx - ring) * h));
+        if (cx + ring < g.dx - 1) rho = fminf(rho, (g.ox + (float)(cx + ring + 1) * h) - ux);
+        if (cy - ring > 0) rho = fminf(rho, uy - (g.oy + (float)(cy - ring) * h));
+        if (cy + ring < g.dy - 1) rho = fminf(rho, (g.oy + (float)(cy + ring + 1) * h) - uy);
+        if (cz - ring > 0) rho = fminf(rho, uz - (g.oz + (float)(cz - ring) * h));
+        if (cz + ring < g.dz - 1) rho = fminf(rho, (g.oz + (float)(cz + ring + 1) * h) - uz);
+        if (rho == INF) {
+            done = true;  // the block covers the whole grid
+        } else if (rho > 0.f) {
+            const float safe = rho * 0.999f;  // margin >> fp32 rounding of cell edges and distances
+            done = t.d3 < safe * safe;
+        }
+    }
+    if (!done) {
+        // sparse neighbourhood: exact scan of the whole known set (original order, strict '<' as the reference)
+        const float *known = known_all + (size_t)b * m * 3;
+        t.d1 = t.d2 = t.d3 = INF;
+        t.i1 = t.i2 = t.i3 = 0x7fffffff;
+        for (int k = 0; k < m; ++k)
+            best3_insert(t, dist_ref(ux, uy, uz, __ldg(known + 3 * k), __ldg(known + 3 * k + 1), __ldg(known + 3 * k + 2)), k);
+    }
+    if (t.d1 == INF) t.i1 = 0;  // fewer than three known points: index 0 / +inf as the reference leaves them
+    if (t.d2 == INF) t.i2 = 0;
+    if (t.d3 == INF) t.i3 = 0;
+    const size_t o = ((size_t)b * n + i) * 3;
+    idx_out[o] = t.i1; idx_out[o + 1] = t.i2; idx_out[o + 2] = t.i3;
+    if (dist2_out) {
+        dist2_out[o] = t.d1; dist2_out[o + 1] = t.d2; dist2_out[o + 2] = t.d3;
+    }
+    if (weight_out) {
+        // model/pointnet2_utils.py:97 + model/pointnet_util.py:206-208
+        float e1 = __fsqrt_rn(t.d1), e2 = __fsqrt_rn(t.d2), e3 = __fsqrt_rn(t.d3);
+        e1 = e1 < 1e-10f ? 1e-10f : e1;
+        e2 = e2 < 1e-10f ? 1e-10f : e2;
+        e3 = e3 < 1e-10f ? 1e-10f : e3;
+        const float w1 = __fdiv_rn(1.0f, e1), w2 = __fdiv_rn(1.0f, e2), w3 = __fdiv_rn(1.0f, e3);
+        const float s = __fadd_rn(__fadd_rn(w1, w2), w3);
+        weight_out[o] = __fdiv_rn(w1, s); weight_out[o + 1] = __fdiv_rn(w2, s); weight_out[o + 2] = __fdiv_rn(w3, s);
+    }
+}
+
+}  // namespace
+}  // namespace pn2
+
+extern "C" int pn2_grid_max_points(void) { return pn2::GRID_MAX_N; }
+extern "C" int pn2_grid_table_stride(void) { return pn2::GRID_MAX_CELLS + 1; }
+
+extern "C" int pn2_grid_build(int b, int n, const float *xyz, float cell, float *sorted, int32_t *cell_start, int32_t *order,
+                              float *meta, void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(b >= 0 && n >= 1, "grid_build: bad dims b=%d n=%d", b, n);
+    if (n > GRID_MAX_N) return set_error(PN2_ERR_UNSUPPORTED, "grid_build: at most %d points per cloud (got %d)", GRID_MAX_N, n);
+    PN2_REQUIRE(cell == cell, "grid_build: cell size is NaN (pass <= 0 for automatic)");
+    if (b == 0) return PN2_OK;
+    PN2_REQUIRE(xyz && sorted && cell_start && meta, "grid_build: null pointer");
+    PN2_REQUIRE((((uintptr_t)sorted) & 15) == 0, "grid_build: sorted must be 16-byte aligned");
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    const size_t smem = (size_t)np2 * sizeof(unsigned long long);
+    if (smem > 40 * 1024)
+        PN2_CUDA(cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    grid_build_kernel<<<b, 1024, smem, (cudaStream_t)stream>>>(n, cell, xyz, reinterpret_cast<float4 *>(sorted), cell_start, order,
+                                                              reinterpret_cast<GridMeta *>(meta));
+    PN2_LAUNCH_OK("grid_build");
+    return PN2_OK;
+}
+
+extern "C" int pn2_ball_query_grid(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
+                                   const float *sorted, const int32_t *cell_start, const float *meta, int32_t *idx,
+                                   void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(b >= 0 && n >= 1 && m >= 0 && nsample >= 0, "ball_query_grid: bad dims");
+    if (b == 0 || m == 0 || nsample == 0) return PN2_OK;
+    PN2_REQUIRE(new_xyz && xyz && sorted && cell_start && meta && idx, "ball_query_grid: null pointer");
+    PN2_REQUIRE(b <= 65535, "ball_query_grid: b exceeds the grid limit");
+    dim3 grid(ceil_div(m, BQG_WARPS), b);
+    ball_query_grid_kernel<<<grid, BQG_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        n, m, radius, nsample, new_xyz, xyz, reinterpret_cast<const float4 *>(sorted), cell_start,
+        reinterpret_cast<const GridMeta *>(meta), idx);
+    PN2_LAUNCH_OK("ball_query_grid");
+    return PN2_OK;
+}
+
+extern "C" int pn2_three_nn_grid(int b, int n, int m, const float *unknown, const float *known, const float *sorted,
+                                 const int32_t *cell_start, const float *meta, const int32_t *query_order, float *dist2,
+                                 int32_t *idx, float *weight, void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(b >= 0 && n >= 0 && m >= 1, "three_nn_grid: bad dims");
+    if (b == 0 || n == 0) return PN2_OK;
+    PN2_REQUIRE(unknown && known && sorted && cell_start && meta && idx, "three_nn_grid: null pointer");
+    PN2_REQUIRE(b <= 65535, "three_nn_grid: b exceeds the grid limit");
+    dim3 grid(ceil_div(n, 128), b);
+    three_nn_grid_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n, m, unknown, known, reinterpret_cast<const float4 *>(sorted),
+                                                                cell_start, reinterpret_cast<const GridMeta *>(meta), query_order,
+                                                                dist2, idx, weight);
+    PN2_LAUNCH_OK("three_nn_grid");
+    return PN2_OK;
+}

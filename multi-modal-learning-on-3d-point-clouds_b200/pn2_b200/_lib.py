@@ -47,6 +47,9 @@ _SIGNATURES = {
     "pn2_mlp_pack_bf16": [ctypes.POINTER(Pn2Mlp), _c_int, _vp, _vp],
     "pn2_sa_mlp_max_bf16": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp, _c_int, _c_int, _vp],
     "pn2_fp_mlp_bf16": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp, _vp],
+    "pn2_grid_build": [_c_int, _c_int, _vp, _c_float, _vp, _vp, _vp, _vp, _vp],
+    "pn2_ball_query_grid": [_c_int, _c_int, _c_int, _c_float, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pn2_three_nn_grid": [_c_int, _c_int, _c_int] + [_vp] * 10,
     "pn2_three_nn_weights": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "pn2_transpose": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
 }
@@ -55,6 +58,8 @@ _OTHER = {
     "pn2_abi_version": ([], _c_int),
     "pn2_launch_count": ([], ctypes.c_uint64),
     "pn2_mlp_bf16_supported": ([ctypes.POINTER(Pn2Mlp)], _c_int),
+    "pn2_grid_max_points": ([], _c_int),
+    "pn2_grid_table_stride": ([], _c_int),
     "pn2_debug_set_fps_mode": ([_c_int], None),
     "pn2_debug_set_tc_timestamps": ([_vp], None),
     "pn2_mlp_pack_bf16_size": ([ctypes.POINTER(Pn2Mlp)], ctypes.c_longlong),

@@ -13,8 +13,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import pointnet2_utils
-from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, _FoldCache, _fusable, fps_gather_cl,
-                            get_mlp_precision, three_nn_weights_cl,
+from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, SpatialGrid, _FoldCache, _fusable, fps_gather_cl,
+                            get_mlp_precision, grid_max_points, three_nn_weights_cl,
                             to_channel_last)
 
 
@@ -65,6 +65,17 @@ class PointNet2SemSeg(nn.Module):
         start.record(main)
         keep = []  # tensors produced on side streams and consumed on the main stream
 
+        def use_grid(npts):
+            return 2048 <= npts <= grid_max_points()
+
+        grids = {}
+        with torch.cuda.stream(s_bq):
+            s_bq.wait_event(start)
+            if use_grid(xyz_cl.shape[1]):
+                # level-0 cell list: independent of the sampling, so it is built while FPS runs
+                grids[0] = SpatialGrid(xyz_cl, 1.01 * sas[0].radius)
+            g0_done = torch.cuda.Event()
+            g0_done.record(s_bq)
         with torch.cuda.stream(s_fps):
             s_fps.wait_event(start)
             levels = [xyz_cl]
@@ -78,17 +89,32 @@ class PointNet2SemSeg(nn.Module):
             balls = []
             for i, sa in enumerate(sas):
                 s_bq.wait_event(fps_done[i])
-                balls.append(pointnet2_utils.ball_query(sa.radius, sa.nsample, levels[i], levels[i + 1]))
+                if i == 0 and 0 in grids:
+                    balls.append(grids[0].ball_query(sa.radius, sa.nsample, levels[1]))
+                else:
+                    balls.append(pointnet2_utils.BallQuery.brute_force(sa.radius, sa.nsample, levels[i], levels[i + 1]))
                 ev = torch.cuda.Event()
                 ev.record(s_bq)
                 bq_done.append(ev)
         with torch.cuda.stream(s_fps):
             nnw = []
+            s_fps.wait_event(g0_done)
             for lvl in (3, 2, 1, 0):  # fp4 .. fp1: fine level `lvl`, coarse level `lvl + 1`
-                nnw.append(three_nn_weights_cl(levels[lvl], levels[lvl + 1]) if levels[lvl + 1].shape[1] > 1 else None)
+                m_known = levels[lvl + 1].shape[1]
+                if m_known <= 1:
+                    nnw.append(None)
+                elif 512 <= m_known <= grid_max_points():
+                    # cell ~ half the next level's ball radius: a few sampled points per cell
+                    known_grid = SpatialGrid(levels[lvl + 1], 0.5 * sas[lvl + 1].radius if lvl + 1 < len(sas) else 0.0)
+                    grids["nn%d" % lvl] = known_grid
+                    nnw.append(known_grid.three_nn(levels[lvl], query_order=grids[lvl].order if lvl in grids else None))
+                else:
+                    nnw.append(three_nn_weights_cl(levels[lvl], levels[lvl + 1]))
                 ev = torch.cuda.Event()
                 ev.record(s_fps)
                 nn_done.append(ev)
+        for gr in grids.values():
+            keep += gr.tensors()
         keep += levels[1:] + balls + [t for pair in nnw if pair is not None for t in pair]
         if not torch.cuda.is_current_stream_capturing():
             for t in keep:
@@ -188,9 +214,12 @@ class GraphedForward:
                 model.forward_fused(self.xyz, self.points)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import _lib
         self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.out = model.forward_fused(self.xyz, self.points)
+        self.kernels_per_replay = _lib.launch_count() - n0  # our kernels captured in the graph
 
     def run(self, xyz, points):
         self.xyz.copy_(xyz, non_blocking=True)

@@ -20,6 +20,12 @@ from . import pointnet2_cuda as _ext
 from ._lib import Pn2Error, require_cuda
 
 
+def _grid_pays_off(n_points, n_queries):
+    """Cell-list search (one sort per cloud) instead of brute force: worthwhile for mid-sized clouds with many queries."""
+    from .pointnet_util import grid_max_points
+    return 512 <= n_points <= grid_max_points() and n_points * n_queries >= (1 << 20)
+
+
 def _need_contiguous(**tensors):
     for name, t in tensors.items():
         if not t.is_contiguous():
@@ -85,9 +91,13 @@ class ThreeNN(Function):
         _need_contiguous(unknown=unknown, known=known)
         B, n, _ = unknown.size()
         m = known.size(1)
-        dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=unknown.device)
-        idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknown.device)
-        _ext.three_nn_wrapper(B, n, m, unknown, known, dist2, idx)
+        if _grid_pays_off(m, n) and m >= 512:
+            from .pointnet_util import SpatialGrid
+            idx, dist2 = SpatialGrid(known, 0.0).three_nn(unknown, want_dist2=True, want_weight=False)
+        else:
+            dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=unknown.device)
+            idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknown.device)
+            _ext.three_nn_wrapper(B, n, m, unknown, known, dist2, idx)
         dist = torch.sqrt(dist2)  # the kernel returns squared distances (:97)
         ctx.mark_non_differentiable(dist, idx)
         return dist, idx
@@ -161,10 +171,21 @@ class BallQuery(Function):
         require_cuda(xyz, new_xyz)
         _need_contiguous(xyz=xyz, new_xyz=new_xyz)
         B, N, _ = xyz.size()
+        if _grid_pays_off(N, new_xyz.size(1)):
+            # exact same result through a cell list instead of the brute-force scan (csrc/grid.cu)
+            from .pointnet_util import SpatialGrid
+            idx = SpatialGrid(xyz, 1.01 * float(radius)).ball_query(radius, nsample, new_xyz)
+        else:
+            idx = BallQuery.brute_force(radius, nsample, xyz, new_xyz)
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def brute_force(radius, nsample, xyz, new_xyz):
+        B, N, _ = xyz.size()
         npoint = new_xyz.size(1)
         idx = torch.empty((B, npoint, nsample), dtype=torch.int32, device=xyz.device)  # kernel writes every slot
         _ext.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
-        ctx.mark_non_differentiable(idx)
         return idx
 
     @staticmethod

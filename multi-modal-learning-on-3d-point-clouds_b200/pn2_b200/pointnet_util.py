@@ -183,6 +183,63 @@ def fps_gather_cl(xyz_cl, npoint):
     return idx, new_xyz
 
 
+class SpatialGrid:
+    """A cloud batch sorted by uniform-grid cell (csrc/grid.cu): exact ball queries / 3-NN without the brute-force
+    scan, and a spatially coherent point order.  xyz (B, N, 3) with N <= grid_max_points(); cell <= 0 = automatic."""
+
+    def __init__(self, xyz_cl, cell):
+        B, N, _ = xyz_cl.shape
+        dev = xyz_cl.device
+        self.xyz, self.B, self.N = xyz_cl, B, N
+        self.sorted = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+        self.cell_start = torch.empty((B, grid_table_stride()), dtype=torch.int32, device=dev)
+        self.order = torch.empty((B, N), dtype=torch.int32, device=dev)
+        self.meta = torch.empty((B, 8), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("pn2_grid_build", B, N, ptr(xyz_cl), float(cell), ptr(self.sorted), ptr(self.cell_start), ptr(self.order),
+                      ptr(self.meta), _lib.stream_ptr(dev))
+
+    def tensors(self):
+        return [self.sorted, self.cell_start, self.order, self.meta]
+
+    def ball_query(self, radius, nsample, new_xyz_cl):
+        """Bit-identical to pointnet2_utils.ball_query(radius, nsample, xyz, new_xyz); build with cell >= 1.01 * radius."""
+        M = new_xyz_cl.shape[1]
+        idx = torch.empty((self.B, M, nsample), dtype=torch.int32, device=self.xyz.device)
+        with torch.cuda.device(self.xyz.device):
+            _lib.call("pn2_ball_query_grid", self.B, self.N, M, float(radius), nsample, ptr(new_xyz_cl), ptr(self.xyz),
+                      ptr(self.sorted), ptr(self.cell_start), ptr(self.meta), ptr(idx), _lib.stream_ptr(self.xyz.device))
+        return idx
+
+    def three_nn(self, unknown_cl, query_order=None, want_dist2=False, want_weight=True):
+        """3-NN of `unknown` (B, n, 3) in this (known) cloud -> (idx, weight) [or (idx, dist2)]; bit-identical to the
+        brute-force kernels."""
+        n = unknown_cl.shape[1]
+        dev = self.xyz.device
+        idx = torch.empty((self.B, n, 3), dtype=torch.int32, device=dev)
+        d2 = torch.empty((self.B, n, 3), dtype=torch.float32, device=dev) if want_dist2 else None
+        w = torch.empty((self.B, n, 3), dtype=torch.float32, device=dev) if want_weight else None
+        with torch.cuda.device(dev):
+            _lib.call("pn2_three_nn_grid", self.B, n, self.N, ptr(unknown_cl), ptr(self.xyz), ptr(self.sorted),
+                      ptr(self.cell_start), ptr(self.meta), ptr(query_order), ptr(d2), ptr(idx), ptr(w), _lib.stream_ptr(dev))
+        return (idx, d2) if want_dist2 and not want_weight else (idx, w)
+
+
+_GRID_LIMITS = {}
+
+
+def grid_max_points():
+    if "n" not in _GRID_LIMITS:
+        _GRID_LIMITS["n"] = int(_lib.load().pn2_grid_max_points())
+    return _GRID_LIMITS["n"]
+
+
+def grid_table_stride():
+    if "s" not in _GRID_LIMITS:
+        _GRID_LIMITS["s"] = int(_lib.load().pn2_grid_table_stride())
+    return _GRID_LIMITS["s"]
+
+
 def sa_mlp_max_cl(xyz_cl, feat_cl, new_xyz_cl, idx, order, mlp, out=None, out_offset=0):
     """Fused grouping + MLP + max.  Returns (B, M, cout) (or writes a channel slice of `out`)."""
     B, N, _ = xyz_cl.shape

@@ -221,3 +221,46 @@ def test_aliases_and_query_and_group(cuda):
     np.testing.assert_array_equal(qg[:, :3].cpu().numpy(), want_xyz)
     ga = pu.GroupAll()(x, None, feats)
     assert ga.shape == (2, 8, 1, 2048)
+
+
+# ---- uniform-grid neighbour search: bit-identical to the brute-force kernels (and hence to the reference) ------------
+
+GRID_BQ = [("scannet", 2, 8192, 1024, 0.1, 32, 1.01), ("scannet", 2, 8192, 1024, 0.2, 32, 1.01), ("dup", 2, 4096, 300, 0.1, 16, 1.5),
+           ("lattice", 1, 3000, 100, 0.25, 64, 1.01), ("uniform", 1, 2500, 40, 10.0, 128, 1.01), ("uniform", 2, 5000, 300, 0.05, 16, 1.01),
+           ("dup", 2, 1024, 256, 0.3, 32, 1.01), ("uniform", 1, 700, 64, 0.3, 200, 0.3), ("scannet", 1, 8192, 512, 0.8, 32, 1.01)]
+
+
+@pytest.mark.parametrize("kind,B,N,M,r,K,cellf", GRID_BQ)
+def test_grid_ball_query_bit_exact(cuda, kind, B, N, M, r, K, cellf):
+    from pn2_b200.pointnet_util import SpatialGrid
+    xyz = clouds(kind, B, N, 7 * N + M)
+    new_xyz = xyz[:, orc.furthest_point_sample(xyz, M)[0]].copy()
+    new_xyz[:, -1] += 100.0   # far outside the grid: empty ball
+    new_xyz[:, -2] -= 0.03    # off-grid-point query
+    grid = SpatialGrid(dev(xyz, cuda), cellf * r)
+    got = grid.ball_query(r, K, dev(new_xyz, cuda)).cpu().numpy()
+    np.testing.assert_array_equal(got, orc.ball_query(r, K, xyz, new_xyz))
+    order = grid.order.cpu().numpy()
+    for b in range(B):
+        assert sorted(order[b].tolist()) == list(range(N))  # a permutation
+
+
+GRID_NN = [("scannet", 2, 8192, 1024, 0.1), ("scannet", 2, 8192, 1024, 0.0), ("uniform", 2, 3000, 600, 0.0), ("lattice", 2, 900, 500, 0.3),
+           ("dup", 2, 2000, 700, 0.05), ("uniform", 1, 500, 2, 0.0), ("uniform", 1, 400, 5000, 0.02), ("scannet", 1, 4096, 64, 0.0)]
+
+
+@pytest.mark.parametrize("kind,B,n,m,cell", GRID_NN)
+def test_grid_three_nn_bit_exact(cuda, kind, B, n, m, cell):
+    from pn2_b200.pointnet_util import SpatialGrid
+    unknown = clouds(kind, B, n, 11 * n + m)
+    known = clouds(kind, B, m, 11 * n + m + 1) if kind != "scannet" else unknown[:, :m].copy()
+    unknown[:, 0] += 50.0  # a query far outside the known set's bounding box
+    grid = SpatialGrid(dev(known, cuda), cell)
+    idx, d2 = grid.three_nn(dev(unknown, cuda), want_dist2=True, want_weight=False)
+    wd2, widx = orc.three_nn_dist2(unknown, known)
+    np.testing.assert_array_equal(idx.cpu().numpy(), widx)
+    np.testing.assert_array_equal(d2.cpu().numpy(), wd2)
+    order = SpatialGrid(dev(unknown, cuda), 0.0).order
+    idx2, w = grid.three_nn(dev(unknown, cuda), query_order=order)
+    np.testing.assert_array_equal(idx2.cpu().numpy(), widx)
+    np.testing.assert_allclose(w.cpu().numpy(), orc.fp_weights(np.sqrt(wd2)), rtol=1e-5, atol=1e-7)
