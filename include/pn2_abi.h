@@ -147,8 +147,11 @@ int pn2_mlp_pack_bf16(const pn2_mlp *mlp, int first_layer_rotate, void *packed, 
 int pn2_sa_mlp_max_bf16(int b, int n, int m, int k, int d, const float *xyz, const float *feat, const float *new_xyz,
                         const int32_t *idx, const pn2_mlp *mlp, const void *packed, float *out, int out_stride,
                         int out_offset, void *stream);
+/* row_perm (B,n) int32 or NULL: processing order of the rows of each cloud (a permutation, e.g. the `order` of
+ * pn2_grid_build); the result is the same, a spatially coherent order makes the 3-row gather cache friendly. */
 int pn2_fp_mlp_bf16(int b, int n, int m, int d1, int d2, const float *feat1, const float *feat2, const int32_t *idx,
-                    const float *weight, const pn2_mlp *mlp, const void *packed, float *out, void *stream);
+                    const float *weight, const pn2_mlp *mlp, const void *packed, const int32_t *row_perm, float *out,
+                    void *stream);
 
 /* three_nn followed by the reference's weight computation (model/pointnet_util.py:205-208):
  * dist = sqrt(dist2); clamp 1e-10; w = 1/dist; w /= sum.  -> idx (B,n,3), weight (B,n,3) */

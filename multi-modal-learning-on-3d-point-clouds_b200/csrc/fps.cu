@@ -137,10 +137,6 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_
     return r;
 }
 
-__device__ long long *g_fps_dbg = nullptr;
-}  // namespace
-const void *g_fps_dbg_ref();
-namespace {
 
 template <int T, int P, int C>
 __global__ void __launch_bounds__(T, 1)
@@ -215,8 +211,6 @@ fps_cluster_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__r
         if (tl == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_base + (uint32_t)par * 8u), "r"(32 * 20)
                          : "memory");
-        long long *dbg = (g_fps_dbg && blockIdx.x == 0 && tl == 0 && j >= 100 && j < 110) ? g_fps_dbg + (j - 100) * 4 : nullptr;
-        if (dbg) dbg[0] = clock64();
         // update the running minima, then a pairwise (log-depth) in-thread arg-max; on ties the lower i wins
         float bv[P];
         int bi[P];
@@ -240,7 +234,6 @@ fps_cluster_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__r
         const uint32_t hi = __float_as_uint(best), lo = inv_base - ((uint32_t)besti << 5);
         uint32_t whi = hi, wlo = lo;
         warp_argmax(whi, wlo);
-        if (dbg) dbg[1] = clock64();
         if (hi == whi && lo == wlo) {
             // the warp's winning lane delivers (key, coordinates) to every CTA; completion is counted on that
             // CTA's barrier (st.async + complete_tx: no fences, no block barrier)
@@ -272,7 +265,6 @@ fps_cluster_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__r
                 "}" ::"r"(bar), "r"(parity)
                 : "memory");
         }
-        if (dbg) dbg[2] = clock64();
         const uint2 key = *reinterpret_cast<const uint2 *>(&rec[par][lane]);
         uint32_t ghi = key.x, glo = key.y;
         warp_argmax(ghi, glo);
@@ -282,7 +274,6 @@ fps_cluster_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__r
         x1 = __uint_as_float(win.z);
         y1 = __uint_as_float(win.w);
         z1 = rec_z[par][src];
-        if (dbg) dbg[3] = clock64() + (long long)(z1 != 12345.f ? 0 : 1);
         if (g == 0) {
             const int k = (int)((tie & QMASK) >> 5) * 1024 + (int)(__brev(tie >> QB) >> 22);
             idx[j] = k;
@@ -430,7 +421,6 @@ int launch_reg_small(int b, int n, int m, const float *xyz, int32_t *idx, float 
 // 0 = automatic, 1 = always one CTA per cloud, 2 = always the cluster kernel (tests / benchmarking)
 static int g_fps_mode = 0;
 extern "C" void pn2_debug_set_fps_mode(int mode) { g_fps_mode = mode; }
-extern "C" void pn2_debug_set_fps_stamps(long long *buf) { cudaMemcpyToSymbol(pn2::g_fps_dbg_ref(), &buf, sizeof(buf)); }
 
 namespace pn2 {
 namespace {
@@ -479,8 +469,6 @@ int fps_impl(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, f
 }
 }  // namespace
 }  // namespace pn2
-
-const void *pn2::g_fps_dbg_ref() { return (const void *)&pn2::g_fps_dbg; }
 
 extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int32_t *idx,
                                            void *stream) {

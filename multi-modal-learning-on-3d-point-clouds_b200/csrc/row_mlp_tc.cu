@@ -57,6 +57,8 @@ struct TcParams {
     int d1, d2, fp_m;
     const float *feat1, *feat2, *weight;
     int feat_aligned;  // gathered feature rows are 16-byte aligned (float4 loads allowed)
+    const int32_t *row_perm;  // FP: optional (B, n) processing order (index within the cloud)
+    int kchunk;        // k-blocks of the first layer's operand produced per pass (see gather_chunk_tc)
     long long *dbg;    // optional phase timestamps of CTA 0 / warp 0 (developer profiling; NULL in production)
 };
 
@@ -167,28 +169,71 @@ __device__ __forceinline__ void st_chunk(unsigned char *a, int r, int c8, const 
 // ---- layer-0 operand: one thread per row, layout [block0 | block1 | zero pad] ---------------------------
 // SA: block0 = grouped features (D), block1 = centred xyz (3).  FP: block0 = interpolated (D2), block1 = skip (D1).
 // (pn2_mlp_pack_bf16 permutes the first layer's weight columns to this order.)
-__device__ __forceinline__ void gather_rows_tc(const TcParams &p, unsigned char *a, long long tile, int r) {
-    const int kpad = p.layer[0].kpad;
+// The operand is produced in chunks of whole k-blocks [c8_begin, c8_end) (8-column units), written at the start of
+// the A buffer, so arbitrarily wide inputs stream through a small buffer while the MMAs accumulate in TMEM.
+struct RowCtx {
+    bool ok;
+    // SA
+    const float *f;
+    float dx, dy, dz;
+    // FP
+    const float *r0, *r1, *r2, *f1;
+    float w0, w1, w2;
+    long long out_row;  // FP: destination row (after the optional permutation)
+};
+
+__device__ __forceinline__ RowCtx row_setup(const TcParams &p, long long tile, int r) {
+    RowCtx c = {};
     if (p.mode == MODE_SA) {
         const int K = p.k, D = p.d;
         const long long g = tile * (TC_ROWS / K) + r / K;
-        const bool ok = g < p.groups;
-        const float *f = nullptr;
-        float dx = 0.f, dy = 0.f, dz = 0.f;
-        if (ok) {
+        c.ok = g < p.groups;
+        if (c.ok) {
             const int b = (int)(g / p.m);
             const int pt = __ldg(p.idx + g * K + (r % K));
             const size_t src = (size_t)b * p.n + pt;
-            f = p.feat + src * D;
-            dx = __fsub_rn(__ldg(p.xyz + src * 3 + 0), __ldg(p.new_xyz + g * 3 + 0));
-            dy = __fsub_rn(__ldg(p.xyz + src * 3 + 1), __ldg(p.new_xyz + g * 3 + 1));
-            dz = __fsub_rn(__ldg(p.xyz + src * 3 + 2), __ldg(p.new_xyz + g * 3 + 2));
+            c.f = p.feat + src * D;
+            c.dx = __fsub_rn(__ldg(p.xyz + src * 3 + 0), __ldg(p.new_xyz + g * 3 + 0));
+            c.dy = __fsub_rn(__ldg(p.xyz + src * 3 + 1), __ldg(p.new_xyz + g * 3 + 1));
+            c.dz = __fsub_rn(__ldg(p.xyz + src * 3 + 2), __ldg(p.new_xyz + g * 3 + 2));
         }
+    } else {
+        const int D1 = p.d1, D2 = p.d2;
+        long long row = tile * TC_ROWS + r;
+        c.ok = row < p.rows;
+        if (c.ok) {
+            const int b = (int)(row / p.n);
+            if (p.row_perm) row = (long long)b * p.n + __ldg(p.row_perm + row);  // spatially coherent processing order
+            const float *f2 = p.feat2 + (size_t)b * p.fp_m * D2;
+            if (p.fp_m == 1) {
+                c.r0 = c.r1 = c.r2 = f2;  // S == 1: the coarse row is repeated
+                c.w0 = 1.f;
+            } else {
+                const int32_t *id = p.idx + (size_t)row * 3;
+                const float *w = p.weight + (size_t)row * 3;
+                c.r0 = f2 + (size_t)__ldg(id) * D2;
+                c.r1 = f2 + (size_t)__ldg(id + 1) * D2;
+                c.r2 = f2 + (size_t)__ldg(id + 2) * D2;
+                c.w0 = __ldg(w); c.w1 = __ldg(w + 1); c.w2 = __ldg(w + 2);
+            }
+            c.f1 = p.feat1 + (size_t)row * D1;
+        }
+        c.out_row = row;
+    }
+    return c;
+}
+
+__device__ __forceinline__ void gather_chunk_tc(const TcParams &p, const RowCtx &x, unsigned char *a, int r, int c8_begin,
+                                                int c8_end) {
+    const bool ok = x.ok;
+    if (p.mode == MODE_SA) {
+        const int D = p.d;
+        const float *f = x.f;
         const bool vec = ok && (D % 4 == 0) && p.feat_aligned;
-        int c8 = 0;
+        int c8 = c8_begin;
         if (vec) {
             // 4 chunks (32 channels, 8 x LDG.128) in flight per thread before the first use
-            for (; (c8 + 4) * 8 <= D; c8 += 4) {
+            for (; c8 + 4 <= c8_end && (c8 + 4) * 8 <= D; c8 += 4) {
                 float4 u[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) u[q] = __ldg(reinterpret_cast<const float4 *>(f + c8 * 8 + 4 * q));
@@ -196,11 +241,11 @@ __device__ __forceinline__ void gather_rows_tc(const TcParams &p, unsigned char 
                 for (int q = 0; q < 4; ++q) {
                     const float v[8] = {u[2 * q].x, u[2 * q].y, u[2 * q].z, u[2 * q].w,
                                         u[2 * q + 1].x, u[2 * q + 1].y, u[2 * q + 1].z, u[2 * q + 1].w};
-                    st_chunk(a, r, c8 + q, v);
+                    st_chunk(a, r, c8 - c8_begin + q, v);
                 }
             }
         }
-        for (; c8 * 8 < kpad; ++c8) {
+        for (; c8 < c8_end; ++c8) {
             float v[8];
             const int c0 = c8 * 8;
             if (vec && c0 + 8 <= D) {
@@ -212,46 +257,28 @@ __device__ __forceinline__ void gather_rows_tc(const TcParams &p, unsigned char 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int c = c0 + j;
-                    float x = 0.f;
+                    float y = 0.f;
                     if (ok) {
-                        if (c < D) x = __ldg(f + c);
-                        else if (c == D) x = dx;
-                        else if (c == D + 1) x = dy;
-                        else if (c == D + 2) x = dz;
+                        if (c < D) y = __ldg(f + c);
+                        else if (c == D) y = x.dx;
+                        else if (c == D + 1) y = x.dy;
+                        else if (c == D + 2) y = x.dz;
                     }
-                    v[j] = x;
+                    v[j] = y;
                 }
             }
-            st_chunk(a, r, c8, v);
+            st_chunk(a, r, c8 - c8_begin, v);
         }
     } else {
         const int D1 = p.d1, D2 = p.d2;
-        const long long row = tile * TC_ROWS + r;
-        const bool ok = row < p.rows;
-        const float *r0 = nullptr, *r1 = nullptr, *r2 = nullptr, *f1 = nullptr;
-        float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-        if (ok) {
-            const int b = (int)(row / p.n);
-            const float *f2 = p.feat2 + (size_t)b * p.fp_m * D2;
-            if (p.fp_m == 1) {
-                r0 = r1 = r2 = f2;  // S == 1: the coarse row is repeated (weights 1, 0, 0)
-                w0 = 1.f;
-            } else {
-                const int32_t *id = p.idx + (size_t)row * 3;
-                const float *w = p.weight + (size_t)row * 3;
-                r0 = f2 + (size_t)__ldg(id) * D2;
-                r1 = f2 + (size_t)__ldg(id + 1) * D2;
-                r2 = f2 + (size_t)__ldg(id + 2) * D2;
-                w0 = __ldg(w); w1 = __ldg(w + 1); w2 = __ldg(w + 2);
-            }
-            f1 = p.feat1 + (size_t)row * D1;
-        }
+        const float *r0 = x.r0, *r1 = x.r1, *r2 = x.r2, *f1 = x.f1;
+        const float w0 = x.w0, w1 = x.w1, w2 = x.w2;
         const bool single = p.fp_m == 1;
         const bool vec = ok && (D2 % 4 == 0) && p.feat_aligned;
-        int c8 = 0;
+        int c8 = c8_begin;
         if (vec && !single) {
             // 2 chunks (16 channels) of the three neighbour rows: 12 x LDG.128 in flight per thread
-            for (; (c8 + 2) * 8 <= D2; c8 += 2) {
+            for (; c8 + 2 <= c8_end && (c8 + 2) * 8 <= D2; c8 += 2) {
                 float4 a0[4], a1[4], a2[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -270,11 +297,11 @@ __device__ __forceinline__ void gather_rows_tc(const TcParams &p, unsigned char 
                         v[4 * q + 2] = __fmaf_rn(w2, x2.z, __fmaf_rn(w0, x0.z, __fmul_rn(w1, x1.z)));
                         v[4 * q + 3] = __fmaf_rn(w2, x2.w, __fmaf_rn(w0, x0.w, __fmul_rn(w1, x1.w)));
                     }
-                    st_chunk(a, r, c8 + h, v);
+                    st_chunk(a, r, c8 - c8_begin + h, v);
                 }
             }
         }
-        for (; c8 * 8 < kpad; ++c8) {
+        for (; c8 < c8_end; ++c8) {
             float v[8];
             const int c0 = c8 * 8;
             if (vec && c0 + 8 <= D2) {
@@ -296,18 +323,18 @@ __device__ __forceinline__ void gather_rows_tc(const TcParams &p, unsigned char 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int c = c0 + j;
-                    float x = 0.f;
+                    float y = 0.f;
                     if (ok) {
                         if (c < D2)
-                            x = single ? __ldg(r0 + c)
+                            y = single ? __ldg(r0 + c)
                                        : __fmaf_rn(w2, __ldg(r2 + c), __fmaf_rn(w0, __ldg(r0 + c), __fmul_rn(w1, __ldg(r1 + c))));
                         else if (c < D2 + D1)
-                            x = __ldg(f1 + (c - D2));
+                            y = __ldg(f1 + (c - D2));
                     }
-                    v[j] = x;
+                    v[j] = y;
                 }
             }
-            st_chunk(a, r, c8, v);
+            st_chunk(a, r, c8 - c8_begin, v);
         }
     }
 }
@@ -319,15 +346,16 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
     unsigned char *a_buf = smem;
     unsigned char *w_ring = smem + p.a_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(w_ring + (size_t)p.stages * p.stage_bytes);
-    // bars: [0..4) full, [4..8) empty, [8] a_ready, [9] acc_ready; then the TMEM base slot, exchange, biases
+    // bars: [0..4) full, [4..8) empty, [8] a_ready, [9] acc_ready, [10] a_free; then the TMEM base slot, exchange, biases
     const int S = p.stages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 2);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
     float *xchg = reinterpret_cast<float *>(tmem_slot + 4);  // [4 warps][32] for nsample > 32
     float *sbias = xchg + 4 * 32;                            // all layers' biases, zero padded to npad
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
     const uint32_t bar_a = smem_u32(bars + 2 * MAX_STAGES), bar_acc = smem_u32(bars + 2 * MAX_STAGES + 1);
+    const uint32_t bar_afree = smem_u32(bars + 2 * MAX_STAGES + 2);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -336,6 +364,7 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
         }
         mbar_init(bar_a, TC_ROWS);
         mbar_init(bar_acc, 1);
+        mbar_init(bar_afree, 1);
         fence_mbar_init();
     }
     for (int l = 0; l < p.num_layers; ++l) {
@@ -362,16 +391,19 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
                     const int nnb = L.npad / L.nblk;
                     const uint32_t bytes = (uint32_t)L.nblk * 128u;
                     const unsigned char *src = p.packed + L.w_off;
-                    for (int t = 0; t < nnb * nkb; ++t) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                        mbar_expect_tx(bar_full + 8 * stage, bytes);
-                        bulk_g2s(smem_u32(w_ring + (size_t)stage * p.stage_bytes), src + (size_t)t * bytes, bytes,
-                                 bar_full + 8 * stage);
-                        if (++stage == S) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
+                    const int kch = l == 0 ? p.kchunk : nkb;  // same (chunk, n-block, k-block) order as the MMA issuer
+                    for (int k0 = 0; k0 < nkb; k0 += kch)
+                        for (int nb = 0; nb < nnb; ++nb)
+                            for (int kb = k0; kb < min(k0 + kch, nkb); ++kb) {
+                                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                                mbar_expect_tx(bar_full + 8 * stage, bytes);
+                                bulk_g2s(smem_u32(w_ring + (size_t)stage * p.stage_bytes), src + (size_t)(nb * nkb + kb) * bytes,
+                                         bytes, bar_full + 8 * stage);
+                                if (++stage == S) {
+                                    stage = 0;
+                                    phase ^= 1;
+                                }
+                            }
                 }
             }
         }
@@ -382,32 +414,37 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
             uint32_t phase = 0, it = 0;
             const uint32_t a_addr = smem_u32(a_buf);
             for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-                for (int l = 0; l < p.num_layers; ++l, ++it) {
+                for (int l = 0; l < p.num_layers; ++l) {
                     const TcLayer &L = p.layer[l];
                     const int nkb = (L.kpad + KBLK - 1) / KBLK;
                     const int nnb = L.npad / L.nblk;
                     const uint32_t idesc = umma_idesc(L.nblk);
-                    mbar_wait(bar_a, it & 1);  // A of this layer is in shared memory
-                    tc_fence_after();
-                    for (int nb = 0; nb < nnb; ++nb) {
-                        for (int kb = 0; kb < nkb; ++kb) {
-                            mbar_wait(bar_full + 8 * stage, phase);
-                            tc_fence_after();
-                            const uint32_t w_addr = smem_u32(w_ring + (size_t)stage * p.stage_bytes);
-                            const int k16n = min(KBLK, L.kpad - kb * KBLK) / 16;
-                            for (int k = 0; k < k16n; ++k) {
-                                const uint64_t ad = umma_desc(a_addr + kb * A_BLOCK_BYTES + k * 32);
-                                const uint64_t bd = umma_desc(w_addr + k * 32);
-                                tc_mma(tmem_base + (uint32_t)(nb * L.nblk), ad, bd, idesc, (uint32_t)((kb | k) != 0));
-                            }
-                            tc_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
-                            if (++stage == S) {
-                                stage = 0;
-                                phase ^= 1;
+                    const int kch = l == 0 ? p.kchunk : nkb;
+                    for (int k0 = 0; k0 < nkb; k0 += kch, ++it) {
+                        mbar_wait(bar_a, it & 1);  // this chunk of the operand is in shared memory
+                        tc_fence_after();
+                        const int k1 = min(k0 + kch, nkb);
+                        for (int nb = 0; nb < nnb; ++nb) {
+                            for (int kb = k0; kb < k1; ++kb) {
+                                mbar_wait(bar_full + 8 * stage, phase);
+                                tc_fence_after();
+                                const uint32_t w_addr = smem_u32(w_ring + (size_t)stage * p.stage_bytes);
+                                const int k16n = min(KBLK, L.kpad - kb * KBLK) / 16;
+                                for (int k = 0; k < k16n; ++k) {
+                                    const uint64_t ad = umma_desc(a_addr + (kb - k0) * A_BLOCK_BYTES + k * 32);
+                                    const uint64_t bd = umma_desc(w_addr + k * 32);
+                                    tc_mma(tmem_base + (uint32_t)(nb * L.nblk), ad, bd, idesc, (uint32_t)((kb | k) != 0));
+                                }
+                                tc_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
+                                if (++stage == S) {
+                                    stage = 0;
+                                    phase ^= 1;
+                                }
                             }
                         }
+                        // accumulators complete (last chunk) / operand buffer reusable (earlier chunks)
+                        tc_commit(k1 == nkb ? bar_acc : bar_afree);
                     }
-                    tc_commit(bar_acc);  // accumulators of layer l complete
                 }
             }
         }
@@ -416,13 +453,27 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
         const int r = threadIdx.x;  // 0..127
         const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
         uint32_t it = 0;
+        long long out_row = 0;
         long long *dbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg : nullptr;
         int di = 0;
+        uint32_t afree_it = 0;
         for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             if (dbg && di < 240) dbg[di++] = clock64();
-            gather_rows_tc(p, a_buf, tile, r);
-            fence_proxy_async();
-            mbar_arrive(bar_a);
+            {
+                const RowCtx ctx = row_setup(p, tile, r);
+                out_row = ctx.out_row;
+                const int nkb0 = (p.layer[0].kpad + KBLK - 1) / KBLK;
+                const int c8_total = p.layer[0].kpad / 8;
+                for (int k0 = 0; k0 < nkb0; k0 += p.kchunk) {
+                    if (k0 > 0) {
+                        mbar_wait(bar_afree, afree_it & 1);  // the MMAs of the previous chunk have consumed the buffer
+                        ++afree_it;
+                    }
+                    gather_chunk_tc(p, ctx, a_buf, r, k0 * 8, min((k0 + p.kchunk) * 8, c8_total));
+                    fence_proxy_async();
+                    mbar_arrive(bar_a);
+                }
+            }
             if (dbg && di < 240) dbg[di++] = clock64();
             for (int l = 0; l < p.num_layers; ++l, ++it) {
                 const TcLayer &L = p.layer[l];
@@ -511,8 +562,8 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
                         const long long row0 = tile * TC_ROWS + warp * 32;
                         const int col = c0 + lane;
                         for (int rr = 0; rr < 32; ++rr) {
-                            const long long row = row0 + rr;
-                            if (row < p.rows && col < cout) p.out[(size_t)row * cout + col] = stg[rr * 33 + lane];
+                            const long long dst = __shfl_sync(0xffffffffu, out_row, rr);  // lane rr's (permuted) output row
+                            if (row0 + rr < p.rows && col < cout) p.out[(size_t)dst * cout + col] = stg[rr * 33 + lane];
                         }
                         __syncwarp();
                     }
@@ -566,13 +617,13 @@ struct Plan {
     TcLayer layer[PN2_MAX_LAYERS];
     int num_layers;
     long long packed_bytes;
-    int a_bytes, stage_bytes, stages, tmem_cols, bias_floats;
+    int a_bytes, stage_bytes, stages, tmem_cols, bias_floats, kchunk;
     size_t smem_bytes;
     bool fits;
 };
 
 constexpr size_t TC_SMEM_LIMIT = 227 * 1024;
-constexpr int TC_TAIL_BYTES = (2 * MAX_STAGES + 2) * 8 + 16 + 4 * 32 * 4;  // barriers, TMEM slot, exchange (+ biases)
+constexpr int TC_TAIL_BYTES = (2 * MAX_STAGES + 4) * 8 + 16 + 4 * 32 * 4;  // barriers, TMEM slot, exchange (+ biases)
 
 Plan make_plan(const pn2_mlp *mlp) {
     Plan P = {};
@@ -594,7 +645,7 @@ Plan make_plan(const pn2_mlp *mlp) {
         boff += L.npad;
         const int nkb = (L.kpad + KBLK - 1) / KBLK;
         off += (long long)L.npad * nkb * 128;
-        amax = amax > nkb ? amax : nkb;                                   // operand of this layer
+        if (l > 0) amax = amax > nkb ? amax : nkb;                        // operand of this layer (layer 0 is chunked)
         if (l + 1 < mlp->num_layers) {
             const int okb = (L.npad + KBLK - 1) / KBLK;                    // its epilogue writes npad columns
             amax = amax > okb ? amax : okb;
@@ -603,6 +654,14 @@ Plan make_plan(const pn2_mlp *mlp) {
         nmax = nmax > L.npad ? nmax : L.npad;
     }
     P.packed_bytes = off;
+    // first-layer operand: produced in passes of `kchunk` k-blocks; at least 2, at most what the hidden layers need anyway
+    {
+        const int nkb0 = (P.layer[0].kpad + KBLK - 1) / KBLK;
+        int kc = amax > 2 ? amax : 2;
+        if (kc > nkb0) kc = nkb0;
+        P.kchunk = kc;
+        amax = amax > kc ? amax : kc;
+    }
     P.a_bytes = amax * A_BLOCK_BYTES;
     if (P.a_bytes < 4 * 32 * 33 * 4) P.a_bytes = ((4 * 32 * 33 * 4) + 1023) / 1024 * 1024;  // FP store staging
     P.stage_bytes = smax;
@@ -655,6 +714,7 @@ int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, c
     p.a_bytes = P.a_bytes;
     p.tmem_cols = P.tmem_cols;
     p.bias_floats = P.bias_floats;
+    p.kchunk = P.kchunk;
     p.tiles = tiles;
     PN2_CUDA(cudaFuncSetAttribute(row_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
     // persistent grid: as many CTAs as can be resident (shared memory, 512 TMEM columns, threads), at most one per tile
@@ -729,8 +789,8 @@ extern "C" int pn2_sa_mlp_max_bf16(int b, int n, int m, int k, int d, const floa
 }
 
 extern "C" int pn2_fp_mlp_bf16(int b, int n, int m, int d1, int d2, const float *feat1, const float *feat2,
-                               const int32_t *idx, const float *weight, const pn2_mlp *mlp, const void *packed, float *out,
-                               void *stream) {
+                               const int32_t *idx, const float *weight, const pn2_mlp *mlp, const void *packed,
+                               const int32_t *row_perm, float *out, void *stream) {
     using namespace pn2;
     PN2_REQUIRE(b >= 0 && n >= 0 && m >= 1 && d1 >= 0 && d2 >= 1, "fp_mlp_bf16: bad dims b=%d n=%d m=%d d1=%d d2=%d", b, n, m, d1, d2);
     if (int st = check_mlp_tc("fp_mlp_bf16", mlp, d1 + d2)) return st;
@@ -745,6 +805,7 @@ extern "C" int pn2_fp_mlp_bf16(int b, int n, int m, int d1, int d2, const float 
     p.feat1 = feat1; p.feat2 = feat2; p.idx = idx; p.weight = weight;
     p.out = out;
     p.feat_aligned = (((uintptr_t)feat2) & 15) == 0;
+    p.row_perm = row_perm;
     const long long tiles = (p.rows + TC_ROWS - 1) / TC_ROWS;
     return launch_tc(p, P, packed, tiles, (cudaStream_t)stream);
 }

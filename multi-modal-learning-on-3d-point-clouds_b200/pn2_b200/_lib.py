@@ -46,7 +46,7 @@ _SIGNATURES = {
     "pn2_fp_mlp": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp],
     "pn2_mlp_pack_bf16": [ctypes.POINTER(Pn2Mlp), _c_int, _vp, _vp],
     "pn2_sa_mlp_max_bf16": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp, _c_int, _c_int, _vp],
-    "pn2_fp_mlp_bf16": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp, _vp],
+    "pn2_fp_mlp_bf16": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp, _vp, _vp],
     "pn2_grid_build": [_c_int, _c_int, _vp, _c_float, _vp, _vp, _vp, _vp, _vp],
     "pn2_ball_query_grid": [_c_int, _c_int, _c_int, _c_float, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_three_nn_grid": [_c_int, _c_int, _c_int] + [_vp] * 10,

@@ -104,8 +104,7 @@ class PointNet2SemSeg(nn.Module):
                 if m_known <= 1:
                     nnw.append(None)
                 elif 512 <= m_known <= grid_max_points():
-                    # cell ~ half the next level's ball radius: a few sampled points per cell
-                    known_grid = SpatialGrid(levels[lvl + 1], 0.5 * sas[lvl + 1].radius if lvl + 1 < len(sas) else 0.0)
+                    known_grid = SpatialGrid(levels[lvl + 1], 0.0)  # automatic cell: about one point per cell
                     grids["nn%d" % lvl] = known_grid
                     nnw.append(known_grid.three_nn(levels[lvl], query_order=grids[lvl].order if lvl in grids else None))
                 else:
@@ -133,11 +132,14 @@ class PointNet2SemSeg(nn.Module):
         main.wait_event(nn_done[2])
         l1 = self.fp2.forward_cl(levels[1], levels[2], l1, l2, nn_weights=nnw[2])
         main.wait_event(nn_done[3])
+        order0 = grids[0].order if 0 in grids else None
         if self.timers is None:
-            return self.fp1.forward_cl(xyz_cl, levels[1], feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw[3])
+            return self.fp1.forward_cl(xyz_cl, levels[1], feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw[3],
+                                       row_order=order0)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
-        out = self.fp1.forward_cl(xyz_cl, levels[1], feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw[3])
+        out = self.fp1.forward_cl(xyz_cl, levels[1], feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw[3],
+                                  row_order=order0)
         t1.record()
         self.timers.setdefault("fp1_head", []).append((t0, t1))
         return out

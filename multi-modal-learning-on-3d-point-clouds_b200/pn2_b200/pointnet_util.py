@@ -271,14 +271,14 @@ def three_nn_weights_cl(xyz1_cl, xyz2_cl):
     return idx, w
 
 
-def fp_mlp_cl(feat1_cl, feat2_cl, idx, weight, mlp, n):
+def fp_mlp_cl(feat1_cl, feat2_cl, idx, weight, mlp, n, row_order=None):
     B, m, D2 = feat2_cl.shape
     D1 = 0 if feat1_cl is None else feat1_cl.shape[2]
     out = torch.empty((B, n, mlp.cout), dtype=torch.float32, device=feat2_cl.device)
     with torch.cuda.device(feat2_cl.device):
         if _PRECISION == "bf16" and mlp.bf16_ok():
             _lib.call("pn2_fp_mlp_bf16", B, n, m, D1, D2, ptr(feat1_cl), ptr(feat2_cl), ptr(idx), ptr(weight), mlp.desc,
-                      ptr(mlp.packed(D1)), ptr(out), _lib.stream_ptr(feat2_cl.device))
+                      ptr(mlp.packed(D1)), ptr(row_order), ptr(out), _lib.stream_ptr(feat2_cl.device))
         else:
             _lib.call("pn2_fp_mlp", B, n, m, D1, D2, ptr(feat1_cl), ptr(feat2_cl), ptr(idx), ptr(weight), mlp.desc, ptr(out),
                       _lib.stream_ptr(feat2_cl.device))
@@ -449,10 +449,11 @@ class PointNetFeaturePropagation(nn.Module):
     def folded(self):
         return self._fold.get(self.mlp_convs, self.mlp_bns, [True] * len(self.mlp_convs))
 
-    def forward_cl(self, xyz1_cl, xyz2_cl, feat1_cl, feat2_cl, mlp=None, nn_weights=None):
+    def forward_cl(self, xyz1_cl, xyz2_cl, feat1_cl, feat2_cl, mlp=None, nn_weights=None, row_order=None):
         """xyz1 (B, N, 3), xyz2 (B, S, 3), feat1 (B, N, D1) or None, feat2 (B, S, D2) -> (B, N, D').
         `mlp` overrides the folded stack (a network appends its head to the last block);
-        `nn_weights` = (idx, weight) computed elsewhere (e.g. on a side stream)."""
+        `nn_weights` = (idx, weight) computed elsewhere (e.g. on a side stream); `row_order` (B, N) int32 = a
+        spatially coherent processing order of the fine points (SpatialGrid.order), same result, cache-friendly gather."""
         mlp = mlp if mlp is not None else self.folded()
         n, m = xyz1_cl.shape[1], xyz2_cl.shape[1]
         if m == 1:
@@ -461,7 +462,7 @@ class PointNetFeaturePropagation(nn.Module):
             idx, w = nn_weights
         else:
             idx, w = three_nn_weights_cl(xyz1_cl, xyz2_cl)
-        return fp_mlp_cl(feat1_cl, feat2_cl, idx, w, mlp, n)
+        return fp_mlp_cl(feat1_cl, feat2_cl, idx, w, mlp, n, row_order=row_order)
 
     def forward(self, xyz1, xyz2, points1, points2):
         """xyz1 (B, 3, N), xyz2 (B, 3, S), points1 (B, D1, N) or None, points2 (B, D2, S) -> (B, D', N)"""
