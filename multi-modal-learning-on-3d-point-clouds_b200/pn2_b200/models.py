@@ -228,3 +228,40 @@ class GraphedForward:
         self.points.copy_(points, non_blocking=True)
         self.graph.replay()
         return self.out
+
+
+class PipelinedForward:
+    """`depth` graph instances on `depth` streams: consecutive batches overlap on the GPU (the FPS of batch i+1 runs
+    on SMs that the latency-bound sampling of a single batch leaves idle).  submit() returns the static output of the
+    slot it used together with an event; the output stays valid until that slot is submitted again."""
+
+    def __init__(self, model, example_xyz, example_points, depth=2):
+        self.depth = depth
+        self.streams = [torch.cuda.Stream(example_xyz.device) for _ in range(depth)]
+        self.slots = []
+        for st in self.streams:
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                self.slots.append(GraphedForward(model, example_xyz, example_points))
+            torch.cuda.current_stream().wait_stream(st)
+        self.kernels_per_replay = self.slots[0].kernels_per_replay
+        self.i = 0
+
+    def submit(self, xyz, points, after=None):
+        """Enqueue one forward; `after` = optional event the slot's stream waits for first (e.g. the H2D copy)."""
+        k = self.i % self.depth
+        self.i += 1
+        st = self.streams[k]
+        if after is not None:
+            st.wait_event(after)
+        else:
+            st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            out = self.slots[k].run(xyz, points)
+            done = torch.cuda.Event()
+            done.record(st)
+        return out, done, st
+
+    def join(self):
+        for st in self.streams:
+            torch.cuda.current_stream().wait_stream(st)
