@@ -129,8 +129,6 @@ def run_reference(args):
     if rank != 0:
         return
     sample = 4
-    args.steps = min(args.steps, 40)     # bounded: ~0.1 s per step of 4 scenes on 16 cores
-    args.warmup = min(args.warmup, 3)
     value, ms, cores = cpu_reference_scenes_per_sec(args.steps, args.warmup, sample)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": args.gpus, "steps": args.steps,
