@@ -224,6 +224,7 @@ fps_cluster_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__r
         for (int s2 = 1; s2 < P; s2 *= 2) {
 #pragma unroll
             for (int i = 0; i + s2 < P; i += 2 * s2) {
+                // ties keep the lower i: within a pair the left operand always covers the lower indices
                 const bool take = bv[i + s2] > bv[i];
                 bv[i] = take ? bv[i + s2] : bv[i];
                 bi[i] = take ? bi[i + s2] : bi[i];
@@ -456,6 +457,9 @@ int fps_impl(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, f
         if (n <= 4096) return launch_cluster<4>(b, n, m, xyz, idx, new_xyz, s);
         if (n <= 8192) return launch_cluster<8>(b, n, m, xyz, idx, new_xyz, s);
         if (n <= 16384) return launch_cluster<16>(b, n, m, xyz, idx, new_xyz, s);
+        if (n <= 24576) return launch_cluster<24>(b, n, m, xyz, idx, new_xyz, s);
+        if (n <= 32768) return launch_cluster<32>(b, n, m, xyz, idx, new_xyz, s);
+        if (n <= 49152) return launch_cluster<48>(b, n, m, xyz, idx, new_xyz, s);  // e.g. a raw 35k-point lidar sweep
     }
     if (n <= 2048) return launch_reg<1024, 2>(b, n, m, xyz, idx, new_xyz, s);
     if (n <= 4096) return launch_reg<1024, 4>(b, n, m, xyz, idx, new_xyz, s);

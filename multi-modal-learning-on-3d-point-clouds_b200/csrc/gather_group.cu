@@ -36,6 +36,60 @@ gather_rows_kernel(int c, int n, long long J, const float *__restrict__ points, 
         if (i < cc) __stcs(dst + (size_t)i * J, v[i]);
 }
 
+// Shared-memory variant for long index lists (grouping: J = npoints*nsample >> N).  A CTA stages CC whole source
+// rows (CC * N floats, coalesced float4 copies) and then streams the index list once: every random access is an
+// LDS, HBM sees only the compulsory bytes (source rows once, indices, coalesced output).
+constexpr int GS_THREADS = 512;
+
+__global__ void __launch_bounds__(GS_THREADS, 1)
+gather_rows_smem_kernel(int c, int n, long long J, int cc, const float *__restrict__ points, const int32_t *__restrict__ idx,
+                        float *__restrict__ out) {
+    extern __shared__ __align__(16) float rows[];  // [cc][n]
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * cc;
+    const int nc = min(cc, c - c0);
+    const float *src = points + ((size_t)b * c + c0) * n;
+    const long long total = (long long)nc * n;
+    if (((uintptr_t)src & 15) == 0 && (total & 3) == 0) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        float4 *d4 = reinterpret_cast<float4 *>(rows);
+        for (long long e = threadIdx.x; e < total / 4; e += GS_THREADS) d4[e] = __ldcs(s4 + e);
+    } else {
+        for (long long e = threadIdx.x; e < total; e += GS_THREADS) rows[e] = __ldcs(src + e);
+    }
+    __syncthreads();
+    const int32_t *ib = idx + (size_t)b * J;
+    float *ob = out + ((size_t)b * c + c0) * J;
+    if ((J & 3) == 0 && ((uintptr_t)ib & 15) == 0 && ((uintptr_t)ob & 15) == 0) {
+        // four consecutive outputs per thread: one 128-bit index load, nc x (4 LDS + one 128-bit streaming store),
+        // two such groups in flight per iteration
+        const long long J4 = J / 4;
+        const long long per = (J4 + gridDim.x - 1) / gridDim.x;
+        const long long q0 = (long long)blockIdx.x * per, q1 = min(J4, q0 + per);
+        const int4 *ib4 = reinterpret_cast<const int4 *>(ib);
+        for (long long q = q0 + threadIdx.x; q < q1; q += 2 * GS_THREADS) {
+            const long long qb = q + GS_THREADS;
+            const bool two = qb < q1;
+            const int4 ka = __ldcs(ib4 + q);
+            int4 kb = ka;
+            if (two) kb = __ldcs(ib4 + qb);
+            for (int i = 0; i < nc; ++i) {
+                const float *r = rows + (size_t)i * n;
+                float4 *dst = reinterpret_cast<float4 *>(ob + (size_t)i * J);
+                __stcs(dst + q, make_float4(r[ka.x], r[ka.y], r[ka.z], r[ka.w]));
+                if (two) __stcs(dst + qb, make_float4(r[kb.x], r[kb.y], r[kb.z], r[kb.w]));
+            }
+        }
+        return;
+    }
+    const long long per = (J + gridDim.x - 1) / gridDim.x;
+    const long long j0 = (long long)blockIdx.x * per, j1 = min(J, j0 + per);
+    for (long long j = j0 + threadIdx.x; j < j1; j += GS_THREADS) {
+        const int k = __ldcs(ib + j);
+        for (int i = 0; i < nc; ++i) __stcs(ob + (size_t)i * J + j, rows[(size_t)i * n + k]);
+    }
+}
+
 // grad_points[b, c, idx[b, j]] += grad_out[b, c, j]   (accumulation order unspecified, as in the reference)
 __global__ void __launch_bounds__(GG_THREADS)
 scatter_add_rows_kernel(int c, int n, long long J, const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
@@ -91,6 +145,23 @@ int gather_rows(const char *op, int b, int c, int n, long long J, const float *p
     if (int st = check_common(op, b, c, n, J)) return st;
     if (b == 0 || c == 0 || J == 0) return PN2_OK;
     PN2_REQUIRE(points && idx && out, "%s: null pointer", op);
+    // long index lists over rows that fit in shared memory: stage the rows (see gather_rows_smem_kernel)
+    const long long smem_floats = 50 * 1024;  // 200 KB
+    if (J >= 2ll * n && n <= smem_floats && (long long)b * c >= 32) {
+        int cc = (int)(smem_floats / n);
+        if (cc > 8) cc = 8;
+        if (cc > c) cc = c;
+        const int chunks = ceil_div(c, cc);
+        // enough CTAs for two waves; each CTA still streams a long slice of the index list
+        int jsplit = 1;
+        while ((long long)jsplit * chunks * b < 2ll * sm_count() && J / (jsplit * 2) >= 8 * n) jsplit *= 2;
+        const size_t smem = (size_t)cc * n * sizeof(float);
+        PN2_CUDA(cudaFuncSetAttribute(gather_rows_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(jsplit, chunks, b);
+        gather_rows_smem_kernel<<<grid, GS_THREADS, smem, (cudaStream_t)stream>>>(c, n, J, cc, points, idx, out);
+        PN2_LAUNCH_OK(op);
+        return PN2_OK;
+    }
     dim3 grid((unsigned)((J + GG_THREADS - 1) / GG_THREADS), ceil_div(c, GG_CH), b);
     gather_rows_kernel<<<grid, GG_THREADS, 0, (cudaStream_t)stream>>>(c, n, J, points, idx, out);
     PN2_LAUNCH_OK(op);

@@ -16,7 +16,7 @@
 namespace pn2 {
 namespace {
 
-constexpr int GRID_MAX_N = 8192;        // points per cloud the single-CTA sort handles
+constexpr int GRID_MAX_N = 16384;       // points per cloud the single-CTA sort handles (128 KB of keys)
 constexpr int GRID_MAX_CELLS = 1 << 16; // cells per cloud (dense start table)
 constexpr int GRID_MAX_DIM = 1024;
 

@@ -144,6 +144,118 @@ three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points, 
         if (k < cc) __stcs(o + (size_t)k * n, __fmaf_rn(w2, a2[k], __fmaf_rn(w0, a0[k], __fmul_rn(w1, a1[k]))));
 }
 
+// Shared-memory variant: a CTA stages the coarse features of CC channels TRANSPOSED ([m][CC], so a neighbour's CC
+// channels are contiguous: one LDS.128 per 4 channels), then every thread streams output points: lane <-> point keeps
+// the stores of a warp coalesced along n.  HBM sees the coarse features once per CTA slice, idx/weight once per channel
+// chunk, and the output once.
+constexpr int TS_THREADS = 256;
+
+template <int CC>
+__global__ void __launch_bounds__(TS_THREADS, 3)
+three_interpolate_smem_kernel(int c, int m, int n, const float *__restrict__ points, const int32_t *__restrict__ idx,
+                              const float *__restrict__ weight, float *__restrict__ out) {
+    constexpr int CCP = CC + 4;  // row stride (floats): 16-byte aligned, rows spread over the banks
+    extern __shared__ __align__(16) float tile[];  // [m][CCP]
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * CC;
+    const int nc = min(CC, c - c0);
+    const float *f = points + ((size_t)b * c + c0) * m;
+    // transposing stage: lanes run along m (coalesced 128-byte reads of four channel rows), each thread writes the four
+    // channels of its point as ONE 16-byte store; row stride CCP = CC + 4 puts consecutive points 4 banks apart, so a
+    // quarter warp covers all 32 banks (conflict free)
+    for (int cq = 0; cq < CC / 4; ++cq)
+        for (int k = threadIdx.x; k < m; k += TS_THREADS) {
+            float4 v;
+            v.x = 4 * cq + 0 < nc ? __ldg(f + (size_t)(4 * cq + 0) * m + k) : 0.f;
+            v.y = 4 * cq + 1 < nc ? __ldg(f + (size_t)(4 * cq + 1) * m + k) : 0.f;
+            v.z = 4 * cq + 2 < nc ? __ldg(f + (size_t)(4 * cq + 2) * m + k) : 0.f;
+            v.w = 4 * cq + 3 < nc ? __ldg(f + (size_t)(4 * cq + 3) * m + k) : 0.f;
+            *reinterpret_cast<float4 *>(tile + (size_t)k * CCP + 4 * cq) = v;
+        }
+    __syncthreads();
+    float *ob = out + ((size_t)b * c + c0) * n;
+    const int32_t *idb = idx + (size_t)b * n * 3;
+    const float *wb = weight + (size_t)b * n * 3;
+    if ((n & 3) == 0 && ((uintptr_t)idb & 15) == 0 && ((uintptr_t)wb & 15) == 0 && ((uintptr_t)ob & 15) == 0) {
+        // four consecutive points per thread: their 12 indices / 12 weights are three 128-bit loads each, and every
+        // channel's four results leave as one 128-bit streaming store
+        const int n4 = n / 4;
+        const int per = (n4 + gridDim.x - 1) / gridDim.x;
+        const int q0 = blockIdx.x * per, q1 = min(n4, q0 + per);
+        for (int q = q0 + threadIdx.x; q < q1; q += TS_THREADS) {
+            int k[12];
+            float w[12];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int4 kv = __ldcs(reinterpret_cast<const int4 *>(idb) + (size_t)q * 3 + u);
+                const float4 wv = __ldcs(reinterpret_cast<const float4 *>(wb) + (size_t)q * 3 + u);
+                k[4 * u] = kv.x; k[4 * u + 1] = kv.y; k[4 * u + 2] = kv.z; k[4 * u + 3] = kv.w;
+                w[4 * u] = wv.x; w[4 * u + 1] = wv.y; w[4 * u + 2] = wv.z; w[4 * u + 3] = wv.w;
+            }
+#pragma unroll
+            for (int cq = 0; cq < CC / 4; ++cq) {
+                float r[4][4];  // [point][channel]
+#pragma unroll
+                for (int pt = 0; pt < 4; ++pt) {
+                    const float4 a0 = *reinterpret_cast<const float4 *>(tile + (size_t)k[3 * pt] * CCP + 4 * cq);
+                    const float4 a1 = *reinterpret_cast<const float4 *>(tile + (size_t)k[3 * pt + 1] * CCP + 4 * cq);
+                    const float4 a2 = *reinterpret_cast<const float4 *>(tile + (size_t)k[3 * pt + 2] * CCP + 4 * cq);
+                    const float w0 = w[3 * pt], w1 = w[3 * pt + 1], w2 = w[3 * pt + 2];
+                    r[pt][0] = __fmaf_rn(w2, a2.x, __fmaf_rn(w0, a0.x, __fmul_rn(w1, a1.x)));
+                    r[pt][1] = __fmaf_rn(w2, a2.y, __fmaf_rn(w0, a0.y, __fmul_rn(w1, a1.y)));
+                    r[pt][2] = __fmaf_rn(w2, a2.z, __fmaf_rn(w0, a0.z, __fmul_rn(w1, a1.z)));
+                    r[pt][3] = __fmaf_rn(w2, a2.w, __fmaf_rn(w0, a0.w, __fmul_rn(w1, a1.w)));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (4 * cq + u < nc)
+                        __stcs(reinterpret_cast<float4 *>(ob + (size_t)(4 * cq + u) * n) + q,
+                               make_float4(r[0][u], r[1][u], r[2][u], r[3][u]));
+            }
+        }
+        return;
+    }
+    const int per = (n + gridDim.x - 1) / gridDim.x;
+    const int i0 = blockIdx.x * per, i1 = min(n, i0 + per);
+    for (int i = i0 + threadIdx.x; i < i1; i += TS_THREADS) {
+        const int32_t *id = idb + (size_t)i * 3;
+        const float *w = wb + (size_t)i * 3;
+        const int k0 = __ldcs(id), k1 = __ldcs(id + 1), k2 = __ldcs(id + 2);
+        const float w0 = __ldcs(w), w1 = __ldcs(w + 1), w2 = __ldcs(w + 2);
+        const float *r0 = tile + (size_t)k0 * CCP, *r1 = tile + (size_t)k1 * CCP, *r2 = tile + (size_t)k2 * CCP;
+#pragma unroll
+        for (int q = 0; q < CC / 4; ++q) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(r0 + 4 * q);
+            const float4 a1 = *reinterpret_cast<const float4 *>(r1 + 4 * q);
+            const float4 a2 = *reinterpret_cast<const float4 *>(r2 + 4 * q);
+            const float v[4] = {__fmaf_rn(w2, a2.x, __fmaf_rn(w0, a0.x, __fmul_rn(w1, a1.x))),
+                                __fmaf_rn(w2, a2.y, __fmaf_rn(w0, a0.y, __fmul_rn(w1, a1.y))),
+                                __fmaf_rn(w2, a2.z, __fmaf_rn(w0, a0.z, __fmul_rn(w1, a1.z))),
+                                __fmaf_rn(w2, a2.w, __fmaf_rn(w0, a0.w, __fmul_rn(w1, a1.w)))};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (4 * q + u < nc) __stcs(ob + (size_t)(4 * q + u) * n + i, v[u]);
+        }
+    }
+}
+
+template <int CC>
+int launch_interp_smem(int b, int c, int m, int n, const float *points, const int32_t *idx, const float *weight, float *out,
+                       cudaStream_t s) {
+    const int chunks = ceil_div(c, CC);
+    const size_t smem = (size_t)m * (CC + 4) * sizeof(float);
+    const int per_sm = smem <= 72 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1);
+    // split the points of a (cloud, channel chunk) until the grid gives two full waves, but keep at least 2*m points
+    // per CTA so the staging stays a small part of its work
+    int nsplit = 1;
+    while ((long long)nsplit * chunks * b < 2ll * per_sm * sm_count() && n / (nsplit + 1) >= 2 * m) ++nsplit;
+    PN2_CUDA(cudaFuncSetAttribute(three_interpolate_smem_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(nsplit, chunks, b);
+    three_interpolate_smem_kernel<CC><<<grid, TS_THREADS, smem, s>>>(c, m, n, points, idx, weight, out);
+    PN2_LAUNCH_OK("three_interpolate");
+    return PN2_OK;
+}
+
 // grad_points[b,c,idx_j] += grad_out[b,c,i] * w_j   (interpolate_gpu.cu:120-142)
 __global__ void __launch_bounds__(TI_THREADS)
 three_interpolate_grad_kernel(int c, int n, int m, const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
@@ -205,6 +317,20 @@ extern "C" int pn2_three_interpolate(int b, int c, int m, int n, const float *po
     if (b == 0 || c == 0 || n == 0) return PN2_OK;
     PN2_REQUIRE(points && idx && weight && out, "three_interpolate: null pointer");
     PN2_REQUIRE(b <= 65535 && ceil_div(c, TI_CH) <= 65535, "three_interpolate: b or c exceeds the grid limits");
+    // upsampling (n >> m) with a coarse set that fits in shared memory: stage it (three_interpolate_smem_kernel)
+    if (n >= 2 * m && (long long)b * c >= 64) {
+        // prefer a tile that lets two CTAs share an SM (one stages while the other streams), else the widest that fits
+        const long long three = 72 * 1024 / 4, two = 110 * 1024 / 4, one = 200 * 1024 / 4;  // floats
+        cudaStream_t st = (cudaStream_t)stream;
+        if ((long long)m * 20 <= three && c >= 16) return launch_interp_smem<16>(b, c, m, n, points, idx, weight, out, st);
+        if ((long long)m * 12 <= three) return launch_interp_smem<8>(b, c, m, n, points, idx, weight, out, st);
+        if ((long long)m * 36 <= two && c >= 32) return launch_interp_smem<32>(b, c, m, n, points, idx, weight, out, st);
+        if ((long long)m * 20 <= two && c >= 16) return launch_interp_smem<16>(b, c, m, n, points, idx, weight, out, st);
+        if ((long long)m * 12 <= two) return launch_interp_smem<8>(b, c, m, n, points, idx, weight, out, st);
+        if ((long long)m * 36 <= one && c >= 32) return launch_interp_smem<32>(b, c, m, n, points, idx, weight, out, st);
+        if ((long long)m * 20 <= one && c >= 16) return launch_interp_smem<16>(b, c, m, n, points, idx, weight, out, st);
+        if ((long long)m * 12 <= one) return launch_interp_smem<8>(b, c, m, n, points, idx, weight, out, st);
+    }
     dim3 grid(ceil_div(n, TI_THREADS), ceil_div(c, TI_CH), b);
     three_interpolate_kernel<<<grid, TI_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, points, idx, weight, out);
     PN2_LAUNCH_OK("three_interpolate");

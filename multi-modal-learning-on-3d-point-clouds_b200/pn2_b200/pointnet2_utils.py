@@ -42,7 +42,7 @@ class FurthestPointSampling(Function):
         out = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
         # the reference allocates a (B, N) scratch of 1e10 here (:26); running minima live on chip
         # in our kernels, so the scratch is only materialised for clouds beyond their capacity.
-        temp = torch.empty((B, N), dtype=torch.float32, device=xyz.device) if N > 8192 else None
+        temp = torch.empty((B, N), dtype=torch.float32, device=xyz.device) if N > 49152 else None  # beyond the on-chip kernels
         _ext.furthest_point_sampling_wrapper(B, N, npoint, xyz, temp, out)
         ctx.mark_non_differentiable(out)
         return out

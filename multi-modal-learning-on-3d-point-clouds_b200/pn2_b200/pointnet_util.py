@@ -176,7 +176,7 @@ def fps_gather_cl(xyz_cl, npoint):
     B, N, _ = xyz_cl.shape
     idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz_cl.device)
     new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz_cl.device)
-    temp = torch.empty((B, N), dtype=torch.float32, device=xyz_cl.device) if N > 8192 else None
+    temp = torch.empty((B, N), dtype=torch.float32, device=xyz_cl.device) if N > 49152 else None  # beyond the on-chip kernels
     with torch.cuda.device(xyz_cl.device):
         _lib.call("pn2_fps_gather", B, N, npoint, ptr(xyz_cl), ptr(temp), ptr(idx), ptr(new_xyz),
                   _lib.stream_ptr(xyz_cl.device))

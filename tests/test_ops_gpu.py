@@ -54,7 +54,8 @@ def test_fps_bit_exact(cuda, kind, B, N, M):
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("kind,B,N,M", [("scannet", 3, 8192, 1024), ("dup", 2, 8192, 700), ("lattice", 2, 4096, 300),
                                         ("dup", 2, 3000, 200), ("uniform", 2, 1025, 64), ("dup", 1, 16384, 300),
-                                        ("uniform", 1, 12000, 150), ("dup", 2, 2048, 2100)])
+                                        ("uniform", 1, 12000, 150), ("dup", 2, 2048, 2100), ("uniform", 1, 20000, 120),
+                                        ("dup", 1, 30000, 100), ("uniform", 1, 35000, 200), ("uniform", 1, 50000, 40)])
 def test_fps_single_cta_and_cluster_kernels_agree_with_reference(cuda, mode, kind, B, N, M):
     """Both on-chip FPS kernels (one CTA per cloud / four-CTA cluster with DSMEM exchange) are bit-exact."""
     from pn2_b200 import _lib
@@ -225,7 +226,7 @@ def test_aliases_and_query_and_group(cuda):
 
 # ---- uniform-grid neighbour search: bit-identical to the brute-force kernels (and hence to the reference) ------------
 
-GRID_BQ = [("scannet", 2, 8192, 1024, 0.1, 32, 1.01), ("scannet", 2, 8192, 1024, 0.2, 32, 1.01), ("dup", 2, 4096, 300, 0.1, 16, 1.5),
+GRID_BQ = [("uniform", 1, 16384, 512, 0.04, 32, 1.01), ("scannet", 2, 8192, 1024, 0.1, 32, 1.01), ("scannet", 2, 8192, 1024, 0.2, 32, 1.01), ("dup", 2, 4096, 300, 0.1, 16, 1.5),
            ("lattice", 1, 3000, 100, 0.25, 64, 1.01), ("uniform", 1, 2500, 40, 10.0, 128, 1.01), ("uniform", 2, 5000, 300, 0.05, 16, 1.01),
            ("dup", 2, 1024, 256, 0.3, 32, 1.01), ("uniform", 1, 700, 64, 0.3, 200, 0.3), ("scannet", 1, 8192, 512, 0.8, 32, 1.01)]
 
