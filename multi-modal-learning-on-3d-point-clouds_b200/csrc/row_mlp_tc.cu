@@ -74,16 +74,19 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Blocking wait.  The suspend-time hint lets the hardware park the thread until the phase completes (or the hint
+// expires) instead of spinning: without it the polling loops of the producer / MMA lanes and of the epilogue warps
+// were ~40 % of all issued instructions (ncu, profiles/r1_tc_mlp_v2_*), stealing issue slots from the working warps.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity)
+        "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -173,6 +176,7 @@ __device__ __forceinline__ void st_chunk(unsigned char *a, int r, int c8, const 
 // the A buffer, so arbitrarily wide inputs stream through a small buffer while the MMAs accumulate in TMEM.
 struct RowCtx {
     bool ok;
+    long long src0, src1, src2;  // element offsets of the gathered feature row(s): SA uses src0, FP all three
     // SA
     const float *f;
     float dx, dy, dz;
@@ -193,6 +197,7 @@ __device__ __forceinline__ RowCtx row_setup(const TcParams &p, long long tile, i
             const int pt = __ldg(p.idx + g * K + (r % K));
             const size_t src = (size_t)b * p.n + pt;
             c.f = p.feat + src * D;
+            c.src0 = (long long)(src * D);
             c.dx = __fsub_rn(__ldg(p.xyz + src * 3 + 0), __ldg(p.new_xyz + g * 3 + 0));
             c.dy = __fsub_rn(__ldg(p.xyz + src * 3 + 1), __ldg(p.new_xyz + g * 3 + 1));
             c.dz = __fsub_rn(__ldg(p.xyz + src * 3 + 2), __ldg(p.new_xyz + g * 3 + 2));
@@ -205,9 +210,11 @@ __device__ __forceinline__ RowCtx row_setup(const TcParams &p, long long tile, i
             const int b = (int)(row / p.n);
             if (p.row_perm) row = (long long)b * p.n + __ldg(p.row_perm + row);  // spatially coherent processing order
             const float *f2 = p.feat2 + (size_t)b * p.fp_m * D2;
+            const long long base2 = (long long)b * p.fp_m * D2;
             if (p.fp_m == 1) {
                 c.r0 = c.r1 = c.r2 = f2;  // S == 1: the coarse row is repeated
                 c.w0 = 1.f;
+                c.src0 = c.src1 = c.src2 = base2;
             } else {
                 const int32_t *id = p.idx + (size_t)row * 3;
                 const float *w = p.weight + (size_t)row * 3;
@@ -215,6 +222,7 @@ __device__ __forceinline__ RowCtx row_setup(const TcParams &p, long long tile, i
                 c.r1 = f2 + (size_t)__ldg(id + 1) * D2;
                 c.r2 = f2 + (size_t)__ldg(id + 2) * D2;
                 c.w0 = __ldg(w); c.w1 = __ldg(w + 1); c.w2 = __ldg(w + 2);
+                c.src0 = base2 + (c.r0 - f2); c.src1 = base2 + (c.r1 - f2); c.src2 = base2 + (c.r2 - f2);
             }
             c.f1 = p.feat1 + (size_t)row * D1;
         }
@@ -223,14 +231,14 @@ __device__ __forceinline__ RowCtx row_setup(const TcParams &p, long long tile, i
     return c;
 }
 
-__device__ __forceinline__ void gather_chunk_tc(const TcParams &p, const RowCtx &x, unsigned char *a, int r, int c8_begin,
-                                                int c8_end) {
+__device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &x, unsigned char *a, int r, int c8_begin,
+                                               int c8_from, int c8_end) {
     const bool ok = x.ok;
     if (p.mode == MODE_SA) {
         const int D = p.d;
         const float *f = x.f;
         const bool vec = ok && (D % 4 == 0) && p.feat_aligned;
-        int c8 = c8_begin;
+        int c8 = c8_from;
         if (vec) {
             // 4 chunks (32 channels, 8 x LDG.128) in flight per thread before the first use
             for (; c8 + 4 <= c8_end && (c8 + 4) * 8 <= D; c8 += 4) {
@@ -275,7 +283,8 @@ __device__ __forceinline__ void gather_chunk_tc(const TcParams &p, const RowCtx 
         const float w0 = x.w0, w1 = x.w1, w2 = x.w2;
         const bool single = p.fp_m == 1;
         const bool vec = ok && (D2 % 4 == 0) && p.feat_aligned;
-        int c8 = c8_begin;
+        const float2 ww0 = make_float2(w0, w0), ww1 = make_float2(w1, w1), ww2 = make_float2(w2, w2);
+        int c8 = c8_from;
         if (vec && !single) {
             // 2 chunks (16 channels) of the three neighbour rows: 12 x LDG.128 in flight per thread
             for (; c8 + 2 <= c8_end && (c8 + 2) * 8 <= D2; c8 += 2) {
@@ -291,11 +300,13 @@ __device__ __forceinline__ void gather_chunk_tc(const TcParams &p, const RowCtx 
                     float v[8];
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
+                        // packed f32x2: per-lane IEEE results identical to the scalar rn sequence
                         const float4 x0 = a0[2 * h + q], x1 = a1[2 * h + q], x2 = a2[2 * h + q];
-                        v[4 * q + 0] = __fmaf_rn(w2, x2.x, __fmaf_rn(w0, x0.x, __fmul_rn(w1, x1.x)));
-                        v[4 * q + 1] = __fmaf_rn(w2, x2.y, __fmaf_rn(w0, x0.y, __fmul_rn(w1, x1.y)));
-                        v[4 * q + 2] = __fmaf_rn(w2, x2.z, __fmaf_rn(w0, x0.z, __fmul_rn(w1, x1.z)));
-                        v[4 * q + 3] = __fmaf_rn(w2, x2.w, __fmaf_rn(w0, x0.w, __fmul_rn(w1, x1.w)));
+                        const float2 lo = __ffma2_rn(ww2, make_float2(x2.x, x2.y),
+                                                     __ffma2_rn(ww0, make_float2(x0.x, x0.y), __fmul2_rn(ww1, make_float2(x1.x, x1.y))));
+                        const float2 hi = __ffma2_rn(ww2, make_float2(x2.z, x2.w),
+                                                     __ffma2_rn(ww0, make_float2(x0.z, x0.w), __fmul2_rn(ww1, make_float2(x1.z, x1.w))));
+                        v[4 * q + 0] = lo.x; v[4 * q + 1] = lo.y; v[4 * q + 2] = hi.x; v[4 * q + 3] = hi.y;
                     }
                     st_chunk(a, r, c8 - c8_begin + h, v);
                 }
@@ -469,7 +480,11 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
                         mbar_wait(bar_afree, afree_it & 1);  // the MMAs of the previous chunk have consumed the buffer
                         ++afree_it;
                     }
-                    gather_chunk_tc(p, ctx, a_buf, r, k0 * 8, min((k0 + p.kchunk) * 8, c8_total));
+                    const int cb = k0 * 8, ce = min((k0 + p.kchunk) * 8, c8_total);
+                    // one thread per row, several 128-bit loads in flight per thread.  (A warp-cooperative variant -- one
+                    // coalesced row per instruction, 8x fewer L1 wavefronts -- measured 10-25 % SLOWER: it serialises the
+                    // rows of a warp and leaves too few loads in flight; see profiles/README.md.)
+                    gather_tail_tc(p, ctx, a_buf, r, cb, cb, ce);
                     fence_proxy_async();
                     mbar_arrive(bar_a);
                 }
@@ -486,6 +501,31 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
                 for (int c0 = 0; c0 < npad; c0 += 32) {
                     uint32_t acc[32];
                     tmem_ld32(lane_base + (uint32_t)c0, acc);
+                    if (!last) {
+                        // bias add as packed f32x2, conversion to bf16x2, ReLU on the packed pair (max(bf16(x), 0) ==
+                        // bf16(max(x, 0))): ~70 instructions per 32 columns instead of ~130
+                        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b0 = *reinterpret_cast<const float4 *>(bl + c0 + 8 * q);
+                            const float4 b1 = *reinterpret_cast<const float4 *>(bl + c0 + 8 * q + 4);
+                            const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 0]), __uint_as_float(acc[8 * q + 1])), make_float2(b0.x, b0.y));
+                            const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 2]), __uint_as_float(acc[8 * q + 3])), make_float2(b0.z, b0.w));
+                            const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 4]), __uint_as_float(acc[8 * q + 5])), make_float2(b1.x, b1.y));
+                            const float2 s3 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 6]), __uint_as_float(acc[8 * q + 7])), make_float2(b1.z, b1.w));
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(s0.x, s0.y), h1 = __floats2bfloat162_rn(s1.x, s1.y);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(s2.x, s2.y), h3 = __floats2bfloat162_rn(s3.x, s3.y);
+                            if (relu) {
+                                h0 = __hmax2(h0, zero2); h1 = __hmax2(h1, zero2);
+                                h2 = __hmax2(h2, zero2); h3 = __hmax2(h3, zero2);
+                            }
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                            *reinterpret_cast<uint4 *>(a_buf + swz_chunk(r, (c0 >> 3) + q, TC_ROWS)) = pk;
+                        }
+                        continue;
+                    }
                     float v[32];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -499,15 +539,7 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
-                    if (!last) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float w8[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) w8[j] = v[8 * q + j];
-                            st_chunk(a_buf, r, (c0 >> 3) + q, w8);
-                        }
-                    } else if (p.mode == MODE_SA) {
+                    if (p.mode == MODE_SA) {
                         // max over the nsample rows of each group (rows of a group are consecutive TMEM lanes)
                         const int K = p.k;
                         float keep = 0.f;
@@ -625,7 +657,7 @@ struct Plan {
 constexpr size_t TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_TAIL_BYTES = (2 * MAX_STAGES + 4) * 8 + 16 + 4 * 32 * 4;  // barriers, TMEM slot, exchange (+ biases)
 
-Plan make_plan(const pn2_mlp *mlp) {
+Plan make_plan_capped(const pn2_mlp *mlp, int nblk_cap) {
     Plan P = {};
     P.num_layers = mlp->num_layers;
     long long off = 0;
@@ -636,7 +668,7 @@ Plan make_plan(const pn2_mlp *mlp) {
         L.cout = mlp->cout[l];
         L.kpad = (L.cin + 15) / 16 * 16;
         L.npad = (L.cout + 31) / 32 * 32;
-        L.nblk = L.npad < 256 ? L.npad : 256;
+        L.nblk = L.npad < nblk_cap ? L.npad : nblk_cap;
         if (L.npad % L.nblk) L.npad = (L.npad + L.nblk - 1) / L.nblk * L.nblk;
         L.relu = mlp->relu[l];
         L.bias = mlp->bias[l];
@@ -685,6 +717,25 @@ Plan make_plan(const pn2_mlp *mlp) {
     return P;
 }
 
+int ctas_per_sm(const Plan &P) {
+    int per_sm = (int)((TC_SMEM_LIMIT + 1024) / P.smem_bytes);
+    if (per_sm > 512 / P.tmem_cols) per_sm = 512 / P.tmem_cols;
+    if (per_sm > 8) per_sm = 8;
+    return per_sm < 1 ? 1 : per_sm;
+}
+
+// Weight tiles of 256, 128 or 64 rows: smaller tiles shrink the ring and let more CTAs share an SM (their
+// gather / MMA / epilogue phases overlap); the packed image depends on the choice, so it is a pure function of the MLP.
+Plan make_plan(const pn2_mlp *mlp) {
+    Plan best = make_plan_capped(mlp, 256);
+    const int caps[2] = {128, 64};
+    for (int i = 0; i < 2; ++i) {
+        const Plan q = make_plan_capped(mlp, caps[i]);
+        if (q.fits && (!best.fits || ctas_per_sm(q) > ctas_per_sm(best))) best = q;
+    }
+    return best;
+}
+
 int check_mlp_tc(const char *op, const pn2_mlp *mlp, int c0) {
     PN2_REQUIRE(mlp, "%s: null mlp", op);
     PN2_REQUIRE(mlp->num_layers >= 1 && mlp->num_layers <= PN2_MAX_LAYERS, "%s: num_layers %d outside 1..%d", op,
@@ -718,10 +769,7 @@ int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, c
     p.tiles = tiles;
     PN2_CUDA(cudaFuncSetAttribute(row_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
     // persistent grid: as many CTAs as can be resident (shared memory, 512 TMEM columns, threads), at most one per tile
-    int per_sm = (int)((TC_SMEM_LIMIT + 1024) / P.smem_bytes);
-    if (per_sm > 512 / P.tmem_cols) per_sm = 512 / P.tmem_cols;
-    if (per_sm > 8) per_sm = 8;
-    if (per_sm < 1) per_sm = 1;
+    const int per_sm = ctas_per_sm(P);
     long long grid = (long long)per_sm * sm_count();
     if (grid > tiles) grid = tiles;
     row_mlp_tc_kernel<<<(unsigned)grid, TC_THREADS, P.smem_bytes, s>>>(p);

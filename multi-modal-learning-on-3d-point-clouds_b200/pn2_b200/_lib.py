@@ -109,10 +109,20 @@ def require_cuda(*tensors):
             raise Pn2Error("pn2_b200 operators need CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
 
 
+PROFILE = None  # developer profiling: list of (name, start_event, end_event) when enabled
+
+
 def call(name, *args):
     """Invokes an ABI entry point and raises Pn2Error on a non-zero status."""
     lib = load()
-    status = getattr(lib, name)(*args)
+    if PROFILE is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        status = getattr(lib, name)(*args)
+        b.record()
+        PROFILE.append((name, a, b))
+    else:
+        status = getattr(lib, name)(*args)
     if status != 0:
         msg = lib.pn2_last_error().decode("utf-8", "replace")
         raise Pn2Error("%s failed with status %d: %s" % (name, status, msg))

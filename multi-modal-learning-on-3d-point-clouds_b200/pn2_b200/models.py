@@ -36,6 +36,7 @@ class PointNet2SemSeg(nn.Module):
         self._head_fold = _FoldCache()
         self.timers = None  # bench.py: dict name -> [(start_event, end_event)] recorded on the current stream
         self._streams = None
+        self.single_stream = False
 
     @property
     def compute_dtype(self):
@@ -58,6 +59,8 @@ class PointNet2SemSeg(nn.Module):
         if self._streams is None or self._streams[0].device != xyz.device:
             self._streams = (torch.cuda.Stream(xyz.device), torch.cuda.Stream(xyz.device))
         s_fps, s_bq = self._streams
+        if self.single_stream:  # developer profiling: everything on the caller's stream
+            s_fps = s_bq = main
         xyz_cl, feat_cl = to_channel_last(xyz), to_channel_last(points)
         sas = [self.sa1, self.sa2, self.sa3, self.sa4]
         fps_done, bq_done, nn_done = [], [], []
