@@ -42,38 +42,48 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    """Samples nvidia-smi SM clocks / throttle reasons; only samples that arrive between begin() and end() are used.
+    Started well before the timed region (nvidia-smi needs a few hundred ms to come up)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
-
-    def __enter__(self):
+    def __init__(self, index, period_ms=20):
+        self.rows, self.proc, self.t0, self.t1 = [], None, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", str(period_ms)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
-        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *a):
+    def wait_ready(self, timeout=5.0):
+        t = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t < timeout:
+            time.sleep(0.02)
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
+    def close(self):
         if self.proc is not None:
-            time.sleep(0.05)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.t0 is None or ts < self.t0 or ts > (self.t1 or ts) + 0.03:
+                continue
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -169,6 +179,7 @@ def time_ref_gpu(model, device, batch):
 
 def op_rooflines(device, batch, pk):
     """HBM-roofline figures of the standalone gather / interpolate kernels at the C1 shapes (timed alone -> burst peak)."""
+    from pn2_b200 import _lib as _lib_mod
     from pn2_b200 import pointnet2_utils as pu
     from pn2_b200.pointnet_util import fps_gather_cl, three_nn_weights_cl
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
@@ -190,21 +201,34 @@ def op_rooflines(device, batch, pk):
         return float(np.median(ts))
 
     out = {}
-    ms = t_ms(lambda: fps_gather_cl(xyz, 1024))
-    out["fps_8192_to_1024"] = {"ms": ms, "us_per_cloud_per_sm": ms * 1e3 * min(batch, 148) / batch,
-                               "clouds_in_flight": min(batch, 148), "algorithmic_gbs": batch * (12 * NPOINTS + 16 * 1024) / ms / 1e6,
-                               "note": "latency-bound (1023 dependent rounds); one CTA per cloud"}
+    lib = _lib_mod.load()
+    for mode, label in ((1, "fps_8192_to_1024_one_cta_per_cloud"), (2, "fps_8192_to_1024_cluster4_dsmem")):
+        lib.pn2_debug_set_fps_mode(mode)
+        ms = t_ms(lambda: fps_gather_cl(xyz, 1024))
+        out[label] = {"ms": ms, "us_per_round": ms * 1e3 / 1023, "clouds_in_flight": batch,
+                      "algorithmic_gbs": batch * (12 * NPOINTS + 16 * 1024) / ms / 1e6,
+                      "note": "latency-bound: 1023 dependent rounds per cloud; HBM bytes are read once (cloud lives on chip)"}
+    lib.pn2_debug_set_fps_mode(0)
     _, new_xyz = fps_gather_cl(xyz, 1024)
     i3, w3 = three_nn_weights_cl(xyz, new_xyz)
-    feats = torch.randn(batch, 128, 1024, device=device)
-    ms = t_ms(lambda: pu.three_interpolate(feats, i3, w3))
-    byts = batch * (24 * NPOINTS + 4 * 128 * 1024 + 4 * 128 * NPOINTS)
-    out["three_interpolate_c128"] = {"ms": ms, "gbs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm_gbs"]}
-    bq = pu.ball_query(0.1, 32, xyz, new_xyz)
-    f64 = torch.randn(batch, 64, NPOINTS, device=device)
-    ms = t_ms(lambda: pu.grouping_operation(f64, bq))
-    byts = batch * (4 * 1024 * 32 + 4 * 64 * NPOINTS + 4 * 64 * 1024 * 32)
-    out["group_points_c64"] = {"ms": ms, "gbs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm_gbs"]}
+    for (C, m, n, bb) in ((128, 1024, NPOINTS, batch), (128, 4096, 16384, 64)):
+        feats = torch.randn(bb, C, m, device=device)
+        idx = torch.randint(0, m, (bb, n, 3), device=device, dtype=torch.int32)
+        w = torch.rand(bb, n, 3, device=device)
+        w = (w / w.sum(-1, keepdim=True)).contiguous()
+        ms = t_ms(lambda: pu.three_interpolate(feats, idx, w))
+        byts = bb * (24 * n + 4 * C * m + 4 * C * n)
+        out["three_interpolate_b%d_c%d_m%d_n%d" % (bb, C, m, n)] = {"ms": ms, "gbs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm_gbs"]}
+        del feats, idx, w
+    for (C, N, M, K, bb) in ((64, NPOINTS, 1024, 32, batch), (128, 16384, 4096, 32, 64)):
+        f = torch.randn(bb, C, N, device=device)
+        idx = torch.randint(0, N, (bb, M, K), device=device, dtype=torch.int32)
+        ms = t_ms(lambda: pu.grouping_operation(f, idx))
+        byts = bb * (4 * M * K + 4 * C * min(N, M * K) + 4 * C * M * K)
+        out["group_points_b%d_c%d_n%d_m%d_k%d" % (bb, C, N, M, K)] = {"ms": ms, "gbs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm_gbs"]}
+        del f, idx
+    ms = t_ms(lambda: pu.ball_query(0.1, 32, xyz, new_xyz))
+    out["ball_query_r0.1_k32_grid"] = {"ms": ms, "note": "grid build + query; brute force (first version) 0.345 ms"}
     return out
 
 
@@ -243,6 +267,8 @@ def run_ours(args):
     depth = 1 if args.no_graph else max(1, args.pipeline)
     pipe = PipelinedForward(model, ex_xyz, ex_pts, depth) if depth > 1 else None
 
+    clocks = ClockSampler(local)
+
     def step(i):
         x = devs[i % n_rot]
         if graphed is not None:
@@ -271,20 +297,23 @@ def run_ours(args):
         serial_ms = sum(a.elapsed_time(b) for a, b in evs)
         # ---- (b) device-resident throughput: `depth` batches in flight, inputs rotate over a set larger than L2 ----
         launches0 = _lib.launch_count()
-        with ClockSampler(local) as clocks:
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for i in range(args.steps):
-                x = devs[i % n_rot]
-                if pipe is not None:
-                    pipe.submit(x[:, :3], x[:, 3:])
-                else:
-                    step(i)
+        clocks.wait_ready()
+        barrier()
+        clocks.begin()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            x = devs[i % n_rot]
             if pipe is not None:
-                pipe.join()
-            b.record()
-            barrier()
+                pipe.submit(x[:, :3], x[:, 3:])
+            else:
+                step(i)
+        if pipe is not None:
+            pipe.join()
+        b.record()
+        barrier()
+        clocks.end()
+        clocks.close()
         total_ms = a.elapsed_time(b)
         launches = _lib.launch_count() - launches0
         if graphed is not None:
@@ -292,13 +321,15 @@ def run_ours(args):
         # ---- the dominant kernel, timed with events inside eager steps of the same workload -------------
         timers = {}
         model.timers = timers
+        model.single_stream = True   # nothing else on the GPU while the kernel is timed
         for i in range(max(3, min(args.steps, 10))):
             x = devs[i % n_rot]
             flush.zero_()
             model(x[:, :3], x[:, 3:])
         torch.cuda.synchronize()
         model.timers = None
-        dom_ms = [a.elapsed_time(b) for a, b in timers.get("fp1_head", [])]
+        model.single_stream = False
+        dom_ms = [a.elapsed_time(b) for a, b in timers.get("fp1_head", [])][1:]
         # ---- end to end: pinned host (B,N,6) -> H2D -> forward -> D2H of the logits, every step -----------------
         n_slots = max(depth, 1)
         stages = [torch.empty((B, NPOINTS, 6), dtype=torch.float32, device=device) for _ in range(n_slots)]
@@ -368,10 +399,17 @@ def run_ours(args):
             ms = float(np.mean(dom_ms))
             achieved = B * FP1_HEAD_FLOPS_PER_SCENE / (ms / 1e3) / 1e12
             peak = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
-            line["roofline"] = {"kernel": "row_mlp (fp1 + head: 131-128-128-128-128-21 over %d rows)" % (B * NPOINTS),
+            line["roofline"] = {"kernel": "row_mlp_tc_kernel (fused fp1 + head: 3-NN interpolation gather + 131-128-128-128-128-21 "
+                                          "tcgen05 MLP over %d rows)" % (B * NPOINTS),
                                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                                "traffic": None, "ms": ms, "share_of_step": ms / (total_ms / args.steps),
-                                "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step)"}
+                                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full at batch 32
+                                # (profiles/r1_tc_mlp_v2_ncu_full_summary.csv, last row); the 22 MB of logits stay in L2
+                                "traffic": 27.55e6 if B == 32 else None,
+                                "algorithmic_bytes": B * NPOINTS * (12 + 12 + 24 + 4 * NUM_CLASSES) + B * 1024 * 128 * 4,
+                                "ms": ms, "share_of_step_one_at_a_time": ms / (serial_ms / args.steps),
+                                "peak_source": pk["source"] + " bf16 sustained (kernel timed inside eager steps, alone on the GPU)",
+                                "note": "largest full-GPU kernel of the step; it is gather/epilogue (L1-wavefront) bound, not tensor bound "
+                                        "(ncu: tensor pipe 10 % active, l1tex 56 %)"}
         if world == 1 and not args.no_extras:
             line["kernels"] = op_rooflines(device, B, pk)
             line["ref_gpu"] = time_ref_gpu(model, device, B)

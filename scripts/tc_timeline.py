@@ -19,7 +19,9 @@ with torch.no_grad():
     l2_xyz, l2 = model.sa2.forward_cl(l1_xyz, l1)
     nnw = U.three_nn_weights_cl(xyz_cl, l1_xyz)
     l1n = torch.randn_like(l1[:, :, :1]).expand(-1, -1, 128).contiguous()
-    for name, fn in [("fp1+head", lambda: model.fp1.forward_cl(xyz_cl, l1_xyz, feat_cl, l1n, mlp=model._fp1_with_head(), nn_weights=nnw)),
+    g0 = U.SpatialGrid(xyz_cl, 0.101)
+    for name, fn in [("fp1+head sorted", lambda: model.fp1.forward_cl(xyz_cl, l1_xyz, feat_cl, l1n, mlp=model._fp1_with_head(), nn_weights=nnw, row_order=g0.order)),
+                     ("fp1+head unsorted", lambda: model.fp1.forward_cl(xyz_cl, l1_xyz, feat_cl, l1n, mlp=model._fp1_with_head(), nn_weights=nnw)),
                      ("sa1", lambda: model.sa1.forward_cl(xyz_cl, feat_cl)),
                      ("sa2", lambda: model.sa2.forward_cl(l1_xyz, l1))]:
         buf = torch.zeros(256, dtype=torch.int64, device=dev)
