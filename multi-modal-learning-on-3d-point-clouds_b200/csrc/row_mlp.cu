@@ -49,7 +49,8 @@ struct RowMlpParams {
     const float *feat1, *feat2, *weight;
 };
 
-__host__ __device__ inline int pick_nt(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : 128); }
+// n-tile width of a layer; the 16-row tile has 64 thread columns, so its tiles are at least 64 wide
+__host__ __device__ inline int pick_nt(int cout, int tr) { return cout <= 32 ? (tr == 16 ? 64 : 32) : (cout <= 64 ? 64 : 128); }
 __host__ __device__ inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // One n-tile of one layer: acc = X_in[.,rows] * W[n0 + cols, .]^T, then bias/ReLU and a k-major store.
@@ -263,14 +264,14 @@ __global__ void __launch_bounds__(RM_THREADS, 1) row_mlp_kernel(const __grid_con
         float *xout = buf[(l + 1) & 1];
         const bool last = (l == p.num_layers - 1);
         const int cin = p.cin[l], cout = p.cout[l];
-        const int nt = pick_nt(cout);
+        const int nt = pick_nt(cout, TR);
         for (int n0 = 0; n0 < cout; n0 += nt) {
             const int ch0 = last ? 0 : n0;
             if (nt == 128)
                 layer_tile<TR, 128>(xin, xout, ch0, p.w[l], p.bias[l], cin, cout, n0, p.relu[l], ws);
             else if (nt == 64)
                 layer_tile<TR, 64>(xin, xout, ch0, p.w[l], p.bias[l], cin, cout, n0, p.relu[l], ws);
-            else
+            else if constexpr (TR != 16)
                 layer_tile<TR, 32>(xin, xout, ch0, p.w[l], p.bias[l], cin, cout, n0, p.relu[l], ws);
             if (!last) continue;
             __syncthreads();
@@ -312,7 +313,7 @@ Layout make_layout(int tr, int c0, const pn2_mlp *mlp) {
     const int trp = tr + 4;
     int a = round_up(c0, KC) * trp, b = 0;
     for (int l = 0; l < mlp->num_layers; ++l) {
-        const int nt = pick_nt(mlp->cout[l]);
+        const int nt = pick_nt(mlp->cout[l], tr);
         const int ch = (l == mlp->num_layers - 1) ? nt : round_up(mlp->cout[l], nt);
         if (((l + 1) & 1) == 1)
             b = b > ch * trp ? b : ch * trp;
@@ -355,15 +356,15 @@ int launch(const RowMlpParams &p, const Layout &L, long long tiles, cudaStream_t
 // Picks the largest row tile whose buffers fit in shared memory, then shrinks it while the grid
 // would leave SMs idle.
 int dispatch(RowMlpParams &p, const pn2_mlp *mlp, int c0, long long total_rows, int min_tr, cudaStream_t s) {
-    const int cands[3] = {128, 64, 32};
+    const int cands[4] = {128, 64, 32, 16};
     int chosen = -1;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
         const int tr = cands[i];
         if (tr < min_tr || tr % min_tr) continue;
         if (make_layout(tr, c0, mlp).bytes > SMEM_LIMIT) continue;
         chosen = tr;
         const long long tiles = (total_rows + tr - 1) / tr;
-        if (tiles >= 2ll * sm_count()) break;  // enough CTAs; otherwise try a smaller tile
+        if (tiles >= 2ll * sm_count() || tr <= 32) break;  // enough CTAs; otherwise try a smaller tile (16 only if nothing else fits)
     }
     if (chosen < 0)
         return set_error(PN2_ERR_UNSUPPORTED, "row_mlp: channel widths need more than %zu bytes of shared memory", SMEM_LIMIT);
@@ -374,7 +375,8 @@ int dispatch(RowMlpParams &p, const pn2_mlp *mlp, int c0, long long total_rows, 
     switch (chosen) {
         case 128: return launch<128>(p, L, tiles, s);
         case 64: return launch<64>(p, L, tiles, s);
-        default: return launch<32>(p, L, tiles, s);
+        case 32: return launch<32>(p, L, tiles, s);
+        default: return launch<16>(p, L, tiles, s);
     }
 }
 
@@ -412,7 +414,7 @@ extern "C" int pn2_sa_mlp_max(int b, int n, int m, int k, int d, const float *xy
     p.groups = (long long)b * m;
     p.xyz = xyz; p.feat = feat; p.new_xyz = new_xyz; p.idx = idx;
     p.out = out; p.out_stride = out_stride; p.out_offset = out_offset;
-    return dispatch(p, mlp, 3 + d, p.groups * k, k < 32 ? 32 : k, (cudaStream_t)stream);
+    return dispatch(p, mlp, 3 + d, p.groups * k, k < 16 ? 16 : k, (cudaStream_t)stream);
 }
 
 extern "C" int pn2_fp_mlp(int b, int n, int m, int d1, int d2, const float *feat1, const float *feat2, const int32_t *idx,
@@ -429,5 +431,5 @@ extern "C" int pn2_fp_mlp(int b, int n, int m, int d1, int d2, const float *feat
     p.rows = (long long)b * n;
     p.feat1 = feat1; p.feat2 = feat2; p.idx = idx; p.weight = weight;
     p.out = out;
-    return dispatch(p, mlp, d1 + d2, p.rows, 32, (cudaStream_t)stream);
+    return dispatch(p, mlp, d1 + d2, p.rows, 16, (cudaStream_t)stream);
 }

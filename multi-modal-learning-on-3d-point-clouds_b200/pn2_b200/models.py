@@ -1,7 +1,9 @@
 """Networks on the hot path, mirroring the reference's callers of the SA/FP modules.
 
-PointNet2SemSeg      model/pointnet2.py:131-162          (ScanNet SSG semseg -- the benchmark model)
-PointNet2Backbone    model/pointmaskrcnn.py:8-32         (nuScenes backbone `PointNet2`)
+PointNet2SemSeg         model/pointnet2.py:131-162              (ScanNet SSG semseg -- the benchmark model)
+PointNet2Backbone       model/pointmaskrcnn.py:8-32             (nuScenes backbone `PointNet2`)
+PointNet2Multiview2     model/pointnet2multiview.py:61-121      (multi-view semseg, point branch; ENet is out of scope)
+PointNet2Multiview2Msg  model/pointnet2multiview.py:179-233     (the MSG semseg stack, point branch)
 
 Attribute names match the reference so its state_dicts load unchanged.  In eval mode under
 torch.no_grad() the forward is 17 kernel launches (2 layout transposes, 4 x (FPS+gather, ball
@@ -13,7 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import pointnet2_utils
-from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, SpatialGrid, _FoldCache, _fusable, fps_gather_cl,
+from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, PointNetSetAbstractionMsg, SpatialGrid, _FoldCache, _fusable, fps_gather_cl,
                             get_mlp_precision, grid_max_points, three_nn_weights_cl,
                             to_channel_last)
 
@@ -201,6 +203,123 @@ class PointNet2Backbone(nn.Module):
         l2_points = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points)
         l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
         return self.fp1(xyz, l1_xyz, None, l1_points)
+
+
+class _MultiviewStackBase(nn.Module):
+    """Shared plumbing of the multi-view networks' point branch (everything after ENet + lifting):
+    geometry branch on xyz only, feature branch on the lifted image features, concatenated at level 2."""
+
+    reduce = "max"
+
+    def _head(self, l0_points):
+        x = self.drop1(F.relu(self.bn1(self.conv1(l0_points))))
+        return self.conv2(x).permute(0, 2, 1)
+
+    def _fp1_with_head(self):
+        convs = list(self.fp1.mlp_convs) + [self.conv1, self.conv2]
+        bns = list(self.fp1.mlp_bns) + [self.bn1, None]
+        relus = [True] * len(self.fp1.mlp_convs) + [True, False]
+        return self._head_fold.get(convs, bns, relus)
+
+    def forward_fused(self, xyz, image_features):
+        """Channel-last fused path; the two level-1/level-2 branches share ONE sampling and ball query each
+        (the reference recomputes them on identical coordinates, model/pointnet2multiview.py:104-107)."""
+        xyz_cl, img_cl = to_channel_last(xyz), to_channel_last(image_features)
+        geo1 = self._geometry(self.sa1_geo, xyz_cl)
+        l1_xyz, l1g = self.sa1_geo.forward_cl(xyz_cl, None, geometry=geo1)
+        _, l1f = self.sa1_feat.forward_cl(xyz_cl, img_cl, geometry=geo1)
+        geo2 = self._geometry(self.sa2_geo, l1_xyz)
+        l2_xyz, l2g = self.sa2_geo.forward_cl(l1_xyz, l1g, geometry=geo2)
+        _, l2f = self.sa2_feat.forward_cl(l1_xyz, l1f, geometry=geo2)
+        l2 = torch.cat((l2g, l2f), dim=2)
+        l3_xyz, l3 = self.sa3.forward_cl(l2_xyz, l2)
+        l4_xyz, l4 = self.sa4.forward_cl(l3_xyz, l3)
+        l3 = self.fp4.forward_cl(l3_xyz, l4_xyz, l3, l4)
+        l2 = self.fp3.forward_cl(l2_xyz, l3_xyz, l2, l3)
+        l1 = self.fp2.forward_cl(l1_xyz, l2_xyz, l1g, l2)
+        return self.fp1.forward_cl(xyz_cl, l1_xyz, None, l1, mlp=self._fp1_with_head())
+
+    @staticmethod
+    def _geometry(sa, xyz_cl):
+        _, new_xyz = fps_gather_cl(xyz_cl, sa.npoint)
+        if hasattr(sa, "radius_list"):
+            return new_xyz, [pointnet2_utils.ball_query(r, k, xyz_cl, new_xyz) for r, k in zip(sa.radius_list, sa.nsample_list)]
+        return new_xyz, pointnet2_utils.ball_query(sa.radius, sa.nsample, xyz_cl, new_xyz)
+
+    def forward(self, xyz, image_features):
+        """xyz (B, 3, N), image_features (B, 128, N) (lifted 2-D features) -> (B, N, num_classes)"""
+        if _fusable(self, xyz, image_features):
+            return self.forward_fused(xyz, image_features)
+        l1_xyz, l1_points = self.sa1_geo(xyz, None)
+        l2_xyz, l2_points = self.sa2_geo(l1_xyz, l1_points)
+        l1_xyz_feat, l1_points_feat = self.sa1_feat(xyz, image_features)
+        _, l2_points_feat = self.sa2_feat(l1_xyz_feat, l1_points_feat)
+        l2_points = torch.cat((l2_points, l2_points_feat), dim=1)
+        l3_xyz, l3_points = self.sa3(l2_xyz, l2_points)
+        l4_xyz, l4_points = self.sa4(l3_xyz, l3_points)
+        l3_points = self.fp4(l3_xyz, l4_xyz, l3_points, l4_points)
+        l2_points = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points)
+        l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
+        l0_points = self.fp1(xyz, l1_xyz, None, l1_points)
+        return self._head(l0_points)
+
+    def forward_views(self, xyz, feats, depth, camera_to_world, intrinsic, depth_min, depth_max, image_dims, accuracy):
+        """Lifting + point branch: feats (B, V, 128, H, W) are the 2-D feature maps (ENet output in the reference)."""
+        from .projection import lift_views
+        points = xyz.permute(0, 2, 1).contiguous()
+        image_features = lift_views(points, feats, depth, camera_to_world, intrinsic, depth_min, depth_max, image_dims,
+                                    accuracy, reduce=self.reduce)
+        return self.forward(xyz, image_features)
+
+
+class PointNet2Multiview2(_MultiviewStackBase):
+    """Point branch of `PointNet2Multiview2` (model/pointnet2multiview.py:61-121; the model the training script
+    instantiates, train_scannet_multiview_semseg.py:73).  View reduction: first view, fill all-zero columns (:93-98)."""
+
+    reduce = "first"
+
+    def __init__(self, num_classes):
+        super().__init__()
+        self.sa1_geo = PointNetSetAbstraction(1024, 0.1, 32, 0 + 3, [32, 32, 64], False)
+        self.sa2_geo = PointNetSetAbstraction(256, 0.2, 32, 64 + 3, [64, 64, 128], False)
+        self.sa1_feat = PointNetSetAbstraction(1024, 0.1, 32, 128 + 3, [32, 32, 64], False)
+        self.sa2_feat = PointNetSetAbstraction(256, 0.2, 32, 64 + 3, [64, 64, 128], False)
+        self.sa3 = PointNetSetAbstraction(64, 0.4, 32, 256 + 3, [128, 128, 256], False)
+        self.sa4 = PointNetSetAbstraction(16, 0.8, 32, 256 + 3, [256, 256, 512], False)
+        self.fp4 = PointNetFeaturePropagation(768, [256, 256])
+        self.fp3 = PointNetFeaturePropagation(512, [256, 256])
+        self.fp2 = PointNetFeaturePropagation(320, [256, 128])
+        self.fp1 = PointNetFeaturePropagation(128, [128, 128, 128])
+        self.conv1 = nn.Conv1d(128, 128, 1)
+        self.bn1 = nn.BatchNorm1d(128)
+        self.drop1 = nn.Dropout(0.5)
+        self.conv2 = nn.Conv1d(128, num_classes, 1)
+        self._head_fold = _FoldCache()
+
+
+class PointNet2Multiview2Msg(_MultiviewStackBase):
+    """Point branch of `PointNet2Multiview2Msg` (model/pointnet2multiview.py:179-233), the only multi-scale-grouping
+    semantic-segmentation stack of the reference (BASELINE config 2).  View reduction: max over views (:210)."""
+
+    reduce = "max"
+
+    def __init__(self, num_classes):
+        super().__init__()
+        self.sa1_geo = PointNetSetAbstractionMsg(1024, [0.05, 0.1], [16, 32], 0, [[16, 16, 32], [32, 32, 64]])
+        self.sa2_geo = PointNetSetAbstractionMsg(256, [0.1, 0.2], [16, 32], 96, [[64, 64, 128], [64, 96, 128]])
+        self.sa1_feat = PointNetSetAbstractionMsg(1024, [0.05, 0.1], [16, 32], 128, [[16, 16, 32], [32, 32, 64]])
+        self.sa2_feat = PointNetSetAbstractionMsg(256, [0.1, 0.2], [16, 32], 96, [[64, 64, 128], [64, 96, 128]])
+        self.sa3 = PointNetSetAbstractionMsg(64, [0.2, 0.4], [16, 32], 512, [[128, 196, 256], [128, 196, 256]])
+        self.sa4 = PointNetSetAbstractionMsg(16, [0.4, 0.8], [16, 32], 512, [[256, 256, 512], [256, 384, 512]])
+        self.fp4 = PointNetFeaturePropagation(1536, [512, 512])
+        self.fp3 = PointNetFeaturePropagation(1024, [512, 512])
+        self.fp2 = PointNetFeaturePropagation(608, [256, 256])
+        self.fp1 = PointNetFeaturePropagation(256, [128, 128, 128])
+        self.conv1 = nn.Conv1d(128, 128, 1)
+        self.bn1 = nn.BatchNorm1d(128)
+        self.drop1 = nn.Dropout(0.5)
+        self.conv2 = nn.Conv1d(128, num_classes, 1)
+        self._head_fold = _FoldCache()
 
 
 class GraphedForward:

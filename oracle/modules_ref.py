@@ -139,3 +139,22 @@ def backbone_forward_ref(model, xyz, points):
         l2_points = fp_forward_ref(model.fp3, l2_xyz, l3_xyz, l2_points, l3_points)
         l1_points = fp_forward_ref(model.fp2, l1_xyz, l2_xyz, l1_points, l2_points)
         return fp_forward_ref(model.fp1, xyz, l1_xyz, None, l1_points)
+
+
+def multiview_stack_forward_ref(model, xyz, image_features):
+    """Point branch of PointNet2Multiview2 / PointNet2Multiview2Msg (model/pointnet2multiview.py:104-120, 216-232)."""
+    sa = sa_msg_forward_ref if hasattr(model.sa1_geo, "radius_list") else sa_forward_ref
+    with torch.no_grad():
+        l1_xyz, l1_points = sa(model.sa1_geo, xyz, None)
+        l2_xyz, l2_points = sa(model.sa2_geo, l1_xyz, l1_points)
+        l1_xyz_feat, l1_points_feat = sa(model.sa1_feat, xyz, image_features)
+        _, l2_points_feat = sa(model.sa2_feat, l1_xyz_feat, l1_points_feat)
+        l2_points = torch.cat((l2_points, l2_points_feat), dim=1)
+        l3_xyz, l3_points = sa(model.sa3, l2_xyz, l2_points)
+        l4_xyz, l4_points = sa(model.sa4, l3_xyz, l3_points)
+        l3_points = fp_forward_ref(model.fp4, l3_xyz, l4_xyz, l3_points, l4_points)
+        l2_points = fp_forward_ref(model.fp3, l2_xyz, l3_xyz, l2_points, l3_points)
+        l1_points = fp_forward_ref(model.fp2, l1_xyz, l2_xyz, l1_points, l2_points)
+        l0_points = fp_forward_ref(model.fp1, xyz, l1_xyz, None, l1_points)
+        x = model.drop1(F.relu(model.bn1(model.conv1(l0_points))))
+        return model.conv2(x).permute(0, 2, 1)

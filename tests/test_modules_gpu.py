@@ -14,7 +14,7 @@ import torch
 
 from oracle import modules_ref
 from pn2_b200 import scenes
-from pn2_b200.models import PointNet2Backbone, PointNet2SemSeg
+from pn2_b200.models import PointNet2Backbone, PointNet2Multiview2, PointNet2Multiview2Msg, PointNet2SemSeg
 from pn2_b200.pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, PointNetSetAbstractionMsg)
 
 pytestmark = pytest.mark.gpu
@@ -160,6 +160,61 @@ def test_backbone_forward_nuscenes_shape(cuda, precision):
     torch.manual_seed(2)
     model = PointNet2Backbone().eval()
     xyz_np, feat_np = scenes.lidar_sweep(0, 8192)
+    xyz = torch.from_numpy(xyz_np.T.copy())[None]
+    feat = torch.from_numpy(feat_np.T.copy())[None]
+    want = modules_ref.backbone_forward_ref(model, xyz, feat)
+    with torch.no_grad():
+        got = copy.deepcopy(model).to(cuda)(xyz.to(cuda), feat.to(cuda))
+    assert_close(got, want, tol(precision, 2e-5))
+
+
+@pytest.mark.parametrize("cls", [PointNet2Multiview2, PointNet2Multiview2Msg])
+def test_multiview_point_branch_matches_reference_composition(cuda, precision, cls):
+    """BASELINE configs 2 / 3: the MSG semseg stack and the multi-view stack on lifted image features."""
+    torch.manual_seed(4)
+    model = cls(21).eval()
+    randomize_bn(model, 9)
+    B, N = 2, 8192
+    xyz, img = scene_batch(B, N, 300, 128)
+    want = modules_ref.multiview_stack_forward_ref(model, xyz, img)
+    with torch.no_grad():
+        got = copy.deepcopy(model).to(cuda)(xyz.to(cuda), img.to(cuda))
+    assert got.shape == (B, N, 21)
+    assert_close(got, want, tol(precision, 2e-5))
+
+
+def test_multiview_forward_views_end_to_end(cuda):
+    """Lifting + point branch in one call equals lifting with the oracle followed by the reference composition."""
+    from oracle import oracle as orc
+    from pn2_b200 import projection
+    torch.manual_seed(5)
+    model = PointNet2Multiview2(21).eval()
+    B, N, V = 1, 8192, 3
+    x, _ = scenes.scannet_scene(500, N)
+    feats, depth, poses = scenes.multiview_inputs(500, x, V, 128)
+    xyz = torch.from_numpy(x.T.copy())[None]
+    t = lambda a: torch.from_numpy(a)[None].to(cuda)
+    intr = torch.from_numpy(scenes.SCANNET_INTRINSIC)
+    dmin, dmax = scenes.SCANNET_DEPTH_RANGE
+    from pn2_b200 import pointnet_util
+    prev = pointnet_util.set_mlp_precision("fp32")
+    try:
+        with torch.no_grad():
+            got = copy.deepcopy(model).to(cuda).forward_views(xyz.to(cuda), t(feats), t(depth), t(poses), intr, dmin, dmax,
+                                                              scenes.SCANNET_IMAGE_DIMS, scenes.SCANNET_ACCURACY)
+            lifted = projection.lift_views(t(x), t(feats), t(depth), t(poses), intr, dmin, dmax, scenes.SCANNET_IMAGE_DIMS,
+                                           scenes.SCANNET_ACCURACY, reduce="first")
+    finally:
+        pointnet_util.set_mlp_precision(prev)
+    want = modules_ref.multiview_stack_forward_ref(model, xyz, lifted.cpu())
+    assert_close(got, want, 2e-5)
+
+
+def test_backbone_nuscenes_16384_points(cuda, precision):
+    """BASELINE config 4 at the loader's real size (16 384 points): cluster FPS with 16 points per thread, 4096 centroids."""
+    torch.manual_seed(6)
+    model = PointNet2Backbone().eval()
+    xyz_np, feat_np = scenes.lidar_sweep(1, 16384)
     xyz = torch.from_numpy(xyz_np.T.copy())[None]
     feat = torch.from_numpy(feat_np.T.copy())[None]
     want = modules_ref.backbone_forward_ref(model, xyz, feat)
