@@ -1,0 +1,71 @@
+"""Training-mode parity (BASELINE config 2 is a train step): forward with batch-statistics BatchNorm and the backward
+kernels (group_points_grad / three_interpolate_grad scatter-adds) inside the real SA -> FP composition, against a
+differentiable CPU restatement.  fp32; tolerance 2e-4 relative to the largest gradient entry (atomic accumulation
+order differs run to run, as in the reference)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import train_ref
+from pn2_b200 import scenes
+from pn2_b200.pointnet_util import PointNetFeaturePropagation, PointNetSetAbstraction
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def test_sa_fp_train_step_matches_reference_gradients(cuda):
+    torch.manual_seed(0)
+    B, N, D = 2, 2048, 6
+    sa = PointNetSetAbstraction(256, 0.25, 32, D + 3, [16, 32], False).train()
+    fp = PointNetFeaturePropagation(D + 32, [24, 8]).train()
+    pts = scenes.scannet_batch(40, B, N)
+    xyz = torch.from_numpy(pts[:, :, :3]).permute(0, 2, 1).contiguous()
+    feat = torch.randn(B, D, N)
+    target = torch.randn(B, 8, N)
+
+    def run(sa_m, fp_m, dev, ref):
+        x, f = xyz.to(dev), feat.clone().to(dev).requires_grad_(True)
+        if ref:
+            new_xyz, l1 = train_ref.sa_train_ref(sa_m, x, f)
+            out = train_ref.fp_train_ref(fp_m, x, new_xyz, f, l1)
+        else:
+            new_xyz, l1 = sa_m(x, f)
+            out = fp_m(x, new_xyz, f, l1)
+        loss = ((out - target.to(dev)) ** 2).mean()
+        loss.backward()
+        return loss, f.grad, [p.grad for p in list(sa_m.parameters()) + list(fp_m.parameters())]
+
+    sa_g, fp_g = copy.deepcopy(sa).to(cuda), copy.deepcopy(fp).to(cuda)
+    loss_ref, fgrad_ref, pgrads_ref = run(sa, fp, "cpu", True)
+    # the 1x1 convs of the training path are torch.nn (cuDNN) as in the reference; pin them to true fp32 for the comparison
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        loss, fgrad, pgrads = run(sa_g, fp_g, cuda, False)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    # conv biases feeding a train-mode BatchNorm have an exactly-zero true gradient (both sides hold ~1e-9 noise):
+    # errors are therefore measured against the largest parameter gradient, not per tensor
+    scale = max(float(r.abs().max()) for r in pgrads_ref)
+    errs = [rel_err(fgrad, fgrad_ref)] + [float((g.detach().cpu() - r).abs().max()) / max(float(r.abs().max()), 0.05 * scale)
+                                          for g, r in zip(pgrads, pgrads_ref)]
+    print("loss", float(loss.detach()), float(loss_ref.detach()), "max rel grad err", max(errs))
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 1e-5 * abs(float(loss_ref.detach()))
+    assert max(errs) <= 2e-4, errs
+    # the running statistics were updated identically (momentum 0.1, batch statistics over (B, K, S))
+    for m_g, m_r in zip(sa_g.mlp_bns, sa.mlp_bns):
+        np.testing.assert_allclose(m_g.running_mean.cpu().numpy(), m_r.running_mean.numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(m_g.running_var.cpu().numpy(), m_r.running_var.numpy(), rtol=1e-4, atol=1e-6)
+    # one optimiser step on the GPU modules runs and changes the weights
+    opt = torch.optim.Adam(list(sa_g.parameters()) + list(fp_g.parameters()), lr=1e-3)
+    before = sa_g.mlp_convs[0].weight.detach().clone()
+    opt.step()
+    assert not torch.equal(before, sa_g.mlp_convs[0].weight.detach())
