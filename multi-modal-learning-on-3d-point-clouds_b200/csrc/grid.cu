@@ -16,7 +16,7 @@
 namespace pn2 {
 namespace {
 
-constexpr int GRID_MAX_N = 16384;       // points per cloud the single-CTA sort handles (128 KB of keys)
+constexpr int GRID_MAX_N = 32768;       // points per cloud the single-CTA sort handles (128 KB of 32-bit keys)
 constexpr int GRID_MAX_CELLS = 1 << 16; // cells per cloud (dense start table)
 constexpr int GRID_MAX_DIM = 1024;
 
@@ -36,7 +36,7 @@ __device__ __forceinline__ int cell_coord(float p, float o, float inv_h, int dim
 __global__ void __launch_bounds__(1024, 1)
 grid_build_kernel(int n, float h, const float *__restrict__ xyz_all, float4 *__restrict__ sorted_all,
                   int32_t *__restrict__ cell_start_all, int32_t *__restrict__ order_all, GridMeta *__restrict__ meta_all) {
-    extern __shared__ unsigned long long keys[];  // np2 entries
+    extern __shared__ uint32_t keys[];  // np2 entries: (cell << 16) | index  (cells and indices both fit 16 bits)
     __shared__ float red[6][32];
     __shared__ GridMeta sm;
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -110,13 +110,13 @@ grid_build_kernel(int n, float h, const float *__restrict__ xyz_all, float4 *__r
     __syncthreads();
     const GridMeta g = sm;
     for (int k = t; k < np2; k += 1024) {
-        unsigned long long key = ~0ull;
+        uint32_t key = 0xffffffffu;
         if (k < n) {
             const int cx = cell_coord(xyz[3 * k], g.ox, g.inv_h, g.dx);
             const int cy = cell_coord(xyz[3 * k + 1], g.oy, g.inv_h, g.dy);
             const int cz = cell_coord(xyz[3 * k + 2], g.oz, g.inv_h, g.dz);
             const unsigned cell = (unsigned)(cx + g.dx * (cy + g.dy * cz));
-            key = ((unsigned long long)cell << 32) | (unsigned)k;
+            key = (cell << 16) | (unsigned)k;
         }
         keys[k] = key;
     }
@@ -127,7 +127,7 @@ grid_build_kernel(int n, float h, const float *__restrict__ xyz_all, float4 *__r
                 const int lo_i = 2 * i - (i & (stride - 1));   // insert a zero bit at position log2(stride)
                 const int hi_i = lo_i + stride;
                 const bool up = (lo_i & size) == 0;
-                const unsigned long long a = keys[lo_i], c = keys[hi_i];
+                const uint32_t a = keys[lo_i], c = keys[hi_i];
                 if ((a > c) == up) {
                     keys[lo_i] = c;
                     keys[hi_i] = a;
@@ -140,11 +140,11 @@ grid_build_kernel(int n, float h, const float *__restrict__ xyz_all, float4 *__r
     int32_t *order = order_all ? order_all + (size_t)b * n : nullptr;
     int32_t *cell_start = cell_start_all + (size_t)b * (GRID_MAX_CELLS + 1);
     for (int i = t; i <= n; i += 1024) {
-        const int c_prev = i > 0 ? (int)(keys[i - 1] >> 32) : -1;
-        const int c_cur = i < n ? (int)(keys[i] >> 32) : g.ncells;
+        const int c_prev = i > 0 ? (int)(keys[i - 1] >> 16) : -1;
+        const int c_cur = i < n ? (int)(keys[i] >> 16) : g.ncells;
         for (int c = c_prev + 1; c <= c_cur; ++c) cell_start[c] = i;
         if (i < n) {
-            const int k = (int)(keys[i] & 0xffffffffu);
+            const int k = (int)(keys[i] & 0xffffu);
             sorted[i] = make_float4(xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2], __int_as_float(k));
             if (order) order[i] = k;
         }
@@ -365,7 +365,7 @@ extern "C" int pn2_grid_build(int b, int n, const float *xyz, float cell, float 
     PN2_REQUIRE((((uintptr_t)sorted) & 15) == 0, "grid_build: sorted must be 16-byte aligned");
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
-    const size_t smem = (size_t)np2 * sizeof(unsigned long long);
+    const size_t smem = (size_t)np2 * sizeof(uint32_t);
     if (smem > 40 * 1024)
         PN2_CUDA(cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     grid_build_kernel<<<b, 1024, smem, (cudaStream_t)stream>>>(n, cell, xyz, reinterpret_cast<float4 *>(sorted), cell_start, order,

@@ -226,7 +226,7 @@ def test_aliases_and_query_and_group(cuda):
 
 # ---- uniform-grid neighbour search: bit-identical to the brute-force kernels (and hence to the reference) ------------
 
-GRID_BQ = [("uniform", 1, 16384, 512, 0.04, 32, 1.01), ("scannet", 2, 8192, 1024, 0.1, 32, 1.01), ("scannet", 2, 8192, 1024, 0.2, 32, 1.01), ("dup", 2, 4096, 300, 0.1, 16, 1.5),
+GRID_BQ = [("uniform", 1, 32768, 256, 0.03, 32, 1.01), ("uniform", 1, 16384, 512, 0.04, 32, 1.01), ("scannet", 2, 8192, 1024, 0.1, 32, 1.01), ("scannet", 2, 8192, 1024, 0.2, 32, 1.01), ("dup", 2, 4096, 300, 0.1, 16, 1.5),
            ("lattice", 1, 3000, 100, 0.25, 64, 1.01), ("uniform", 1, 2500, 40, 10.0, 128, 1.01), ("uniform", 2, 5000, 300, 0.05, 16, 1.01),
            ("dup", 2, 1024, 256, 0.3, 32, 1.01), ("uniform", 1, 700, 64, 0.3, 200, 0.3), ("scannet", 1, 8192, 512, 0.8, 32, 1.01)]
 
