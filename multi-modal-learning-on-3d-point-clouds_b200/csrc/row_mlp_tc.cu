@@ -717,10 +717,12 @@ Plan make_plan_capped(const pn2_mlp *mlp, int nblk_cap) {
     return P;
 }
 
+int g_tc_max_ctas = 8;  // developer knob (pn2_debug_set_tc_max_ctas)
+
 int ctas_per_sm(const Plan &P) {
     int per_sm = (int)((TC_SMEM_LIMIT + 1024) / P.smem_bytes);
     if (per_sm > 512 / P.tmem_cols) per_sm = 512 / P.tmem_cols;
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > g_tc_max_ctas) per_sm = g_tc_max_ctas;
     return per_sm < 1 ? 1 : per_sm;
 }
 
@@ -779,6 +781,8 @@ int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, c
 
 }  // namespace
 }  // namespace pn2
+
+extern "C" void pn2_debug_set_tc_max_ctas(int n) { pn2::g_tc_max_ctas = n < 1 ? 1 : n; }
 
 extern "C" int pn2_mlp_bf16_supported(const pn2_mlp *mlp) {
     if (!mlp || mlp->num_layers < 1 || mlp->num_layers > PN2_MAX_LAYERS) return 0;
