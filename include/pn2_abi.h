@@ -144,14 +144,20 @@ int pn2_fp_mlp(int b, int n, int m, int d1, int d2, const float *feat1, const fl
 int pn2_mlp_bf16_supported(const pn2_mlp *mlp);       /* 1 if the widths fit shared memory / TMEM */
 long long pn2_mlp_pack_bf16_size(const pn2_mlp *mlp); /* bytes of the packed image (16-byte aligned buffer) */
 int pn2_mlp_pack_bf16(const pn2_mlp *mlp, int first_layer_rotate, void *packed, void *stream);
+/* flags: activations that only travel between tensor-core blocks may be stored as bf16 (they are rounded to bf16 for
+ * the MMA operand anyway; for SA gathers the result is bit-identical).  The pointer types below stay `float *`; with a
+ * flag set the buffer holds bf16 elements of the same logical shape. */
+#define PN2_FLAG_IN_BF16 1   /* SA: feat, FP: feat2 (needs d resp. d2 % 8 == 0, 16-byte aligned rows) */
+#define PN2_FLAG_SKIP_BF16 2 /* FP: feat1 (needs PN2_FLAG_IN_BF16 and d1 % 8 == 0) */
+#define PN2_FLAG_OUT_BF16 4  /* out */
 int pn2_sa_mlp_max_bf16(int b, int n, int m, int k, int d, const float *xyz, const float *feat, const float *new_xyz,
                         const int32_t *idx, const pn2_mlp *mlp, const void *packed, float *out, int out_stride,
-                        int out_offset, void *stream);
+                        int out_offset, int flags, void *stream);
 /* row_perm (B,n) int32 or NULL: processing order of the rows of each cloud (a permutation, e.g. the `order` of
  * pn2_grid_build); the result is the same, a spatially coherent order makes the 3-row gather cache friendly. */
 int pn2_fp_mlp_bf16(int b, int n, int m, int d1, int d2, const float *feat1, const float *feat2, const int32_t *idx,
                     const float *weight, const pn2_mlp *mlp, const void *packed, const int32_t *row_perm, float *out,
-                    void *stream);
+                    int flags, void *stream);
 
 /* three_nn followed by the reference's weight computation (model/pointnet_util.py:205-208):
  * dist = sqrt(dist2); clamp 1e-10; w = 1/dist; w /= sum.  -> idx (B,n,3), weight (B,n,3) */

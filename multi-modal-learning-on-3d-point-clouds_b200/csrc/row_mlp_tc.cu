@@ -58,6 +58,9 @@ struct TcParams {
     const float *feat1, *feat2, *weight;
     int feat_aligned;  // gathered feature rows are 16-byte aligned (float4 loads allowed)
     const int32_t *row_perm;  // FP: optional (B, n) processing order (index within the cloud)
+    int in_bf16;       // block0 features (SA feat / FP feat2) are stored as bf16
+    int skip_bf16;     // FP skip features (feat1) are stored as bf16
+    int out_bf16;      // write the result as bf16 (activations that only feed another tensor-core block)
     int kchunk;        // k-blocks of the first layer's operand produced per pass (see gather_chunk_tc)
     long long *dbg;    // optional phase timestamps of CTA 0 / warp 0 (developer profiling; NULL in production)
 };
@@ -231,10 +234,95 @@ __device__ __forceinline__ RowCtx row_setup(const TcParams &p, long long tile, i
     return c;
 }
 
+template <bool kInBf16>
 __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &x, unsigned char *a, int r, int c8_begin,
                                                int c8_from, int c8_end) {
     const bool ok = x.ok;
-    if (p.mode == MODE_SA) {
+    if constexpr (kInBf16) {
+        // bf16 activations: a 16-byte load is a whole 8-column chunk.  SA: the chunk IS the operand chunk (pure copy,
+        // bit-identical to converting fp32 features here); FP: three chunks are unpacked, interpolated in fp32, repacked.
+        const int Dm = p.mode == MODE_SA ? p.d : p.d2;
+        const __nv_bfloat16 *b0 = reinterpret_cast<const __nv_bfloat16 *>(p.mode == MODE_SA ? (const void *)p.feat : (const void *)p.feat2);
+        const bool fp3 = p.mode != MODE_SA && p.fp_m != 1;
+        int c8 = c8_from;
+        const int c8_blk0 = min(c8_end, Dm / 8);
+        for (; c8 < c8_blk0; c8 += 4) {
+            const int nq = min(4, c8_blk0 - c8);
+            uint4 q0[4], q1[4], q2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                q0[q] = make_uint4(0u, 0u, 0u, 0u);
+                q1[q] = q0[q];
+                q2[q] = q0[q];
+                if (q < nq && ok) {
+                    q0[q] = __ldg(reinterpret_cast<const uint4 *>(b0 + x.src0) + c8 + q);
+                    if (fp3) {
+                        q1[q] = __ldg(reinterpret_cast<const uint4 *>(b0 + x.src1) + c8 + q);
+                        q2[q] = __ldg(reinterpret_cast<const uint4 *>(b0 + x.src2) + c8 + q);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q >= nq) break;
+                uint4 o = q0[q];
+                if (fp3) {
+                    const uint32_t *u0 = reinterpret_cast<const uint32_t *>(&q0[q]);
+                    const uint32_t *u1 = reinterpret_cast<const uint32_t *>(&q1[q]);
+                    const uint32_t *u2 = reinterpret_cast<const uint32_t *>(&q2[q]);
+                    uint32_t *uo = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        // bf16 -> fp32 is a 16-bit shift; same rn sequence as three_interpolate
+                        const float a0l = __uint_as_float(u0[e] << 16), a0h = __uint_as_float(u0[e] & 0xffff0000u);
+                        const float a1l = __uint_as_float(u1[e] << 16), a1h = __uint_as_float(u1[e] & 0xffff0000u);
+                        const float a2l = __uint_as_float(u2[e] << 16), a2h = __uint_as_float(u2[e] & 0xffff0000u);
+                        const float lo = __fmaf_rn(x.w2, a2l, __fmaf_rn(x.w0, a0l, __fmul_rn(x.w1, a1l)));
+                        const float hi = __fmaf_rn(x.w2, a2h, __fmaf_rn(x.w0, a0h, __fmul_rn(x.w1, a1h)));
+                        uo[e] = pack_bf16(lo, hi);
+                    }
+                }
+                *reinterpret_cast<uint4 *>(a + swz_chunk(r, c8 + q - c8_begin, TC_ROWS)) = o;
+            }
+        }
+        // skip features stored as bf16 and chunk aligned: pure copies as well
+        if (p.mode != MODE_SA && p.skip_bf16 && (Dm & 7) == 0 && (p.d1 & 7) == 0) {
+            const __nv_bfloat16 *b1 = reinterpret_cast<const __nv_bfloat16 *>(p.feat1);
+            const int c8_skip_end = min(c8_end, (Dm + p.d1) / 8);
+            for (; c8 < c8_skip_end; ++c8) {
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) o = __ldg(reinterpret_cast<const uint4 *>(b1 + x.out_row * p.d1) + (c8 - Dm / 8));
+                *reinterpret_cast<uint4 *>(a + swz_chunk(r, c8 - c8_begin, TC_ROWS)) = o;
+            }
+        }
+        // remaining chunks: centred xyz (SA) / fp32 skip channels (FP) / zero padding
+        for (; c8 < c8_end; ++c8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c8 * 8 + j;
+                float y = 0.f;
+                if (ok) {
+                    if (p.mode == MODE_SA) {
+                        if (c < Dm) y = __bfloat162float(b0[x.src0 + c]);
+                        else if (c == Dm) y = x.dx;
+                        else if (c == Dm + 1) y = x.dy;
+                        else if (c == Dm + 2) y = x.dz;
+                    } else if (c < Dm) {
+                        y = fp3 ? __fmaf_rn(x.w2, __bfloat162float(b0[x.src2 + c]),
+                                            __fmaf_rn(x.w0, __bfloat162float(b0[x.src0 + c]), __fmul_rn(x.w1, __bfloat162float(b0[x.src1 + c]))))
+                                : __bfloat162float(b0[x.src0 + c]);
+                    } else if (c < Dm + p.d1) {
+                        y = p.skip_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(p.feat1)[x.out_row * p.d1 + (c - Dm)])
+                                        : __ldg(p.feat1 + x.out_row * p.d1 + (c - Dm));
+                    }
+                }
+                v[j] = y;
+            }
+            st_chunk(a, r, c8 - c8_begin, v);
+        }
+        return;
+    } else if (p.mode == MODE_SA) {
         const int D = p.d;
         const float *f = x.f;
         const bool vec = ok && (D % 4 == 0) && p.feat_aligned;
@@ -350,7 +438,9 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_constant__ TcParams p) {
+// Two instantiations: fp32 gathered features (lean: 4 CTAs/SM) and bf16 gathered features (3 CTAs/SM).
+template <bool kInBf16>
+__global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment for the 128B-swizzled operand tiles
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -484,7 +574,7 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
                     // one thread per row, several 128-bit loads in flight per thread.  (A warp-cooperative variant -- one
                     // coalesced row per instruction, 8x fewer L1 wavefronts -- measured 10-25 % SLOWER: it serialises the
                     // rows of a warp and leaves too few loads in flight; see profiles/README.md.)
-                    gather_tail_tc(p, ctx, a_buf, r, cb, cb, ce);
+                    gather_tail_tc<kInBf16>(p, ctx, a_buf, r, cb, cb, ce);
                     fence_proxy_async();
                     mbar_arrive(bar_a);
                 }
@@ -563,8 +653,11 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
                             }
                             const long long g = tile * (TC_ROWS / K) + gl;
                             const int col = c0 + lane;
-                            if (gl >= 0 && g < p.groups && col < cout)
-                                p.out[(size_t)g * p.out_stride + p.out_offset + col] = keep;
+                            if (gl >= 0 && g < p.groups && col < cout) {
+                                const size_t o = (size_t)g * p.out_stride + p.out_offset + col;
+                                if (p.out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.out)[o] = __float2bfloat16_rn(keep);
+                                else p.out[o] = keep;
+                            }
                         } else {
                             // nsample < 32: segmented butterflies inside the warp
                             const int gpw = 32 / K;
@@ -580,7 +673,11 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
 #pragma unroll
                                     for (int j = 0; j < 32; ++j) {
                                         const int col = c0 + j;
-                                        if (col < cout) p.out[(size_t)g * p.out_stride + p.out_offset + col] = v[j];
+                                        if (col < cout) {
+                                            const size_t o = (size_t)g * p.out_stride + p.out_offset + col;
+                                            if (p.out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.out)[o] = __float2bfloat16_rn(v[j]);
+                                            else p.out[o] = v[j];
+                                        }
                                     }
                                 }
                             }
@@ -595,7 +692,10 @@ __global__ void __launch_bounds__(TC_THREADS) row_mlp_tc_kernel(const __grid_con
                         const int col = c0 + lane;
                         for (int rr = 0; rr < 32; ++rr) {
                             const long long dst = __shfl_sync(0xffffffffu, out_row, rr);  // lane rr's (permuted) output row
-                            if (row0 + rr < p.rows && col < cout) p.out[(size_t)dst * cout + col] = stg[rr * 33 + lane];
+                            if (row0 + rr < p.rows && col < cout) {
+                                if (p.out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.out)[(size_t)dst * cout + col] = __float2bfloat16_rn(stg[rr * 33 + lane]);
+                                else p.out[(size_t)dst * cout + col] = stg[rr * 33 + lane];
+                            }
                         }
                         __syncwarp();
                     }
@@ -769,12 +869,19 @@ int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, c
     p.bias_floats = P.bias_floats;
     p.kchunk = P.kchunk;
     p.tiles = tiles;
-    PN2_CUDA(cudaFuncSetAttribute(row_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+    if (p.in_bf16)
+        PN2_CUDA(cudaFuncSetAttribute(row_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+    else
+        PN2_CUDA(cudaFuncSetAttribute(row_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
     // persistent grid: as many CTAs as can be resident (shared memory, 512 TMEM columns, threads), at most one per tile
-    const int per_sm = ctas_per_sm(P);
+    int per_sm = ctas_per_sm(P);
+    if (p.in_bf16 && per_sm > 3) per_sm = 3;  // register budget of the bf16-input instantiation
     long long grid = (long long)per_sm * sm_count();
     if (grid > tiles) grid = tiles;
-    row_mlp_tc_kernel<<<(unsigned)grid, TC_THREADS, P.smem_bytes, s>>>(p);
+    if (p.in_bf16)
+        row_mlp_tc_kernel<true><<<(unsigned)grid, TC_THREADS, P.smem_bytes, s>>>(p);
+    else
+        row_mlp_tc_kernel<false><<<(unsigned)grid, TC_THREADS, P.smem_bytes, s>>>(p);
     PN2_LAUNCH_OK("row_mlp_tc_kernel");
     return PN2_OK;
 }
@@ -815,7 +922,7 @@ extern "C" int pn2_mlp_pack_bf16(const pn2_mlp *mlp, int first_layer_rotate, voi
 
 extern "C" int pn2_sa_mlp_max_bf16(int b, int n, int m, int k, int d, const float *xyz, const float *feat,
                                    const float *new_xyz, const int32_t *idx, const pn2_mlp *mlp, const void *packed,
-                                   float *out, int out_stride, int out_offset, void *stream) {
+                                   float *out, int out_stride, int out_offset, int flags, void *stream) {
     using namespace pn2;
     PN2_REQUIRE(b >= 0 && n >= 1 && m >= 0 && k >= 1 && d >= 0, "sa_mlp_max_bf16: bad dims b=%d n=%d m=%d k=%d d=%d", b, n, m, k, d);
     if (int st = check_mlp_tc("sa_mlp_max_bf16", mlp, 3 + d)) return st;
@@ -836,13 +943,16 @@ extern "C" int pn2_sa_mlp_max_bf16(int b, int n, int m, int k, int d, const floa
     p.xyz = xyz; p.feat = feat; p.new_xyz = new_xyz; p.idx = idx;
     p.out = out; p.out_stride = out_stride; p.out_offset = out_offset;
     p.feat_aligned = (((uintptr_t)feat) & 15) == 0;
+    p.in_bf16 = (flags & PN2_FLAG_IN_BF16) != 0;
+    p.out_bf16 = (flags & PN2_FLAG_OUT_BF16) != 0;
+    if (p.in_bf16) PN2_REQUIRE(d % 8 == 0 && p.feat_aligned, "sa_mlp_max_bf16: bf16 features need d %% 8 == 0 and 16-byte alignment");
     const long long tiles = (p.groups * k + TC_ROWS - 1) / TC_ROWS;
     return launch_tc(p, P, packed, tiles, (cudaStream_t)stream);
 }
 
 extern "C" int pn2_fp_mlp_bf16(int b, int n, int m, int d1, int d2, const float *feat1, const float *feat2,
                                const int32_t *idx, const float *weight, const pn2_mlp *mlp, const void *packed,
-                               const int32_t *row_perm, float *out, void *stream) {
+                               const int32_t *row_perm, float *out, int flags, void *stream) {
     using namespace pn2;
     PN2_REQUIRE(b >= 0 && n >= 0 && m >= 1 && d1 >= 0 && d2 >= 1, "fp_mlp_bf16: bad dims b=%d n=%d m=%d d1=%d d2=%d", b, n, m, d1, d2);
     if (int st = check_mlp_tc("fp_mlp_bf16", mlp, d1 + d2)) return st;
@@ -858,6 +968,12 @@ extern "C" int pn2_fp_mlp_bf16(int b, int n, int m, int d1, int d2, const float 
     p.out = out;
     p.feat_aligned = (((uintptr_t)feat2) & 15) == 0;
     p.row_perm = row_perm;
+    p.in_bf16 = (flags & PN2_FLAG_IN_BF16) != 0;
+    p.skip_bf16 = (flags & PN2_FLAG_SKIP_BF16) != 0;
+    p.out_bf16 = (flags & PN2_FLAG_OUT_BF16) != 0;
+    if (p.in_bf16) PN2_REQUIRE(d2 % 8 == 0 && p.feat_aligned, "fp_mlp_bf16: bf16 features need d2 %% 8 == 0 and 16-byte alignment");
+    if (p.skip_bf16)
+        PN2_REQUIRE(p.in_bf16 && d1 % 8 == 0 && (((uintptr_t)feat1) & 15) == 0, "fp_mlp_bf16: bf16 skip features need bf16 coarse features, d1 %% 8 == 0 and 16-byte alignment");
     const long long tiles = (p.rows + TC_ROWS - 1) / TC_ROWS;
     return launch_tc(p, P, packed, tiles, (cudaStream_t)stream);
 }

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(CSRC, "libpn2_b200.so")
 PN2_MAX_LAYERS = 6
 REDUCE_MAX, REDUCE_FIRST = 0, 1
 ORDER_XYZ_FIRST, ORDER_FEAT_FIRST = 0, 1
+FLAG_IN_BF16, FLAG_SKIP_BF16, FLAG_OUT_BF16 = 1, 2, 4
 
 _c_int, _c_float, _vp = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 
@@ -45,8 +46,8 @@ _SIGNATURES = {
     "pn2_sa_mlp_max": [_c_int] * 5 + [_vp] * 4 + [_c_int, ctypes.POINTER(Pn2Mlp), _vp, _c_int, _c_int, _vp],
     "pn2_fp_mlp": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp],
     "pn2_mlp_pack_bf16": [ctypes.POINTER(Pn2Mlp), _c_int, _vp, _vp],
-    "pn2_sa_mlp_max_bf16": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp, _c_int, _c_int, _vp],
-    "pn2_fp_mlp_bf16": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp, _vp, _vp],
+    "pn2_sa_mlp_max_bf16": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp, _c_int, _c_int, _c_int, _vp],
+    "pn2_fp_mlp_bf16": [_c_int] * 5 + [_vp] * 4 + [ctypes.POINTER(Pn2Mlp), _vp, _vp, _vp, _c_int, _vp],
     "pn2_grid_build": [_c_int, _c_int, _vp, _c_float, _vp, _vp, _vp, _vp, _vp],
     "pn2_ball_query_grid": [_c_int, _c_int, _c_int, _c_float, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_three_nn_grid": [_c_int, _c_int, _c_int] + [_vp] * 10,

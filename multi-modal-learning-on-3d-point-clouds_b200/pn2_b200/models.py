@@ -124,18 +124,22 @@ class PointNet2SemSeg(nn.Module):
             for t in keep:
                 t.record_stream(main)
 
+        # activations between tensor-core blocks travel as bf16 (they are rounded to bf16 for the MMA operand anyway;
+        # halves the gather traffic).  Only when every block of the network runs on the tensor-core path.
+        blocks = [sa.folded() for sa in sas] + [self.fp4.folded(), self.fp3.folded(), self.fp2.folded(), self._fp1_with_head()]
+        act = torch.bfloat16 if (get_mlp_precision() == "bf16" and all(b.bf16_ok() for b in blocks)) else torch.float32
         feats = [feat_cl]
         for i, sa in enumerate(sas):
             main.wait_event(bq_done[i])
-            _, out = sa.forward_cl(levels[i], feats[i], geometry=(levels[i + 1], balls[i]))
+            _, out = sa.forward_cl(levels[i], feats[i], geometry=(levels[i + 1], balls[i]), out_dtype=act)
             feats.append(out)
         l1, l2, l3, l4 = feats[1:]
         main.wait_event(nn_done[0])
-        l3 = self.fp4.forward_cl(levels[3], levels[4], l3, l4, nn_weights=nnw[0])
+        l3 = self.fp4.forward_cl(levels[3], levels[4], l3, l4, nn_weights=nnw[0], out_dtype=act)
         main.wait_event(nn_done[1])
-        l2 = self.fp3.forward_cl(levels[2], levels[3], l2, l3, nn_weights=nnw[1])
+        l2 = self.fp3.forward_cl(levels[2], levels[3], l2, l3, nn_weights=nnw[1], out_dtype=act)
         main.wait_event(nn_done[2])
-        l1 = self.fp2.forward_cl(levels[1], levels[2], l1, l2, nn_weights=nnw[2])
+        l1 = self.fp2.forward_cl(levels[1], levels[2], l1, l2, nn_weights=nnw[2], out_dtype=act)
         main.wait_event(nn_done[3])
         order0 = grids[0].order if 0 in grids else None
         if self.timers is None:

@@ -240,18 +240,33 @@ def grid_table_stride():
     return _GRID_LIMITS["s"]
 
 
-def sa_mlp_max_cl(xyz_cl, feat_cl, new_xyz_cl, idx, order, mlp, out=None, out_offset=0):
-    """Fused grouping + MLP + max.  Returns (B, M, cout) (or writes a channel slice of `out`)."""
+def _bf16_flags(block0, skip, out):
+    f = 0
+    if block0 is not None and block0.dtype == torch.bfloat16:
+        f |= _lib.FLAG_IN_BF16
+    if skip is not None and skip.dtype == torch.bfloat16:
+        f |= _lib.FLAG_SKIP_BF16
+    if out.dtype == torch.bfloat16:
+        f |= _lib.FLAG_OUT_BF16
+    return f
+
+
+def sa_mlp_max_cl(xyz_cl, feat_cl, new_xyz_cl, idx, order, mlp, out=None, out_offset=0, out_dtype=torch.float32):
+    """Fused grouping + MLP + max.  Returns (B, M, cout) (or writes a channel slice of `out`).  bf16 feature / output
+    tensors are accepted by the tensor-core path only (activations travelling between tensor-core blocks)."""
     B, N, _ = xyz_cl.shape
     M, K = idx.shape[1], idx.shape[2]
     D = 0 if feat_cl is None else feat_cl.shape[2]
     if out is None:
-        out = torch.empty((B, M, mlp.cout), dtype=torch.float32, device=xyz_cl.device)
+        out = torch.empty((B, M, mlp.cout), dtype=out_dtype, device=xyz_cl.device)
     with torch.cuda.device(xyz_cl.device):
         if _PRECISION == "bf16" and mlp.bf16_ok():
             rotate = (3 % mlp.cin) if order == _lib.ORDER_XYZ_FIRST else 0
             _lib.call("pn2_sa_mlp_max_bf16", B, N, M, K, D, ptr(xyz_cl), ptr(feat_cl), ptr(new_xyz_cl), ptr(idx),
-                      mlp.desc, ptr(mlp.packed(rotate)), ptr(out), out.shape[2], out_offset, _lib.stream_ptr(xyz_cl.device))
+                      mlp.desc, ptr(mlp.packed(rotate)), ptr(out), out.shape[2], out_offset, _bf16_flags(feat_cl, None, out),
+                      _lib.stream_ptr(xyz_cl.device))
+        elif (feat_cl is not None and feat_cl.dtype != torch.float32) or out.dtype != torch.float32:
+            raise _lib.Pn2Error("bf16 activations need the tensor-core path (set_mlp_precision('bf16') and widths it supports)")
         else:
             _lib.call("pn2_sa_mlp_max", B, N, M, K, D, ptr(xyz_cl), ptr(feat_cl), ptr(new_xyz_cl), ptr(idx), order,
                       mlp.desc, ptr(out), out.shape[2], out_offset, _lib.stream_ptr(xyz_cl.device))
@@ -271,14 +286,17 @@ def three_nn_weights_cl(xyz1_cl, xyz2_cl):
     return idx, w
 
 
-def fp_mlp_cl(feat1_cl, feat2_cl, idx, weight, mlp, n, row_order=None):
+def fp_mlp_cl(feat1_cl, feat2_cl, idx, weight, mlp, n, row_order=None, out_dtype=torch.float32):
     B, m, D2 = feat2_cl.shape
     D1 = 0 if feat1_cl is None else feat1_cl.shape[2]
-    out = torch.empty((B, n, mlp.cout), dtype=torch.float32, device=feat2_cl.device)
+    out = torch.empty((B, n, mlp.cout), dtype=out_dtype, device=feat2_cl.device)
     with torch.cuda.device(feat2_cl.device):
         if _PRECISION == "bf16" and mlp.bf16_ok():
             _lib.call("pn2_fp_mlp_bf16", B, n, m, D1, D2, ptr(feat1_cl), ptr(feat2_cl), ptr(idx), ptr(weight), mlp.desc,
-                      ptr(mlp.packed(D1)), ptr(row_order), ptr(out), _lib.stream_ptr(feat2_cl.device))
+                      ptr(mlp.packed(D1)), ptr(row_order), ptr(out), _bf16_flags(feat2_cl, feat1_cl, out),
+                      _lib.stream_ptr(feat2_cl.device))
+        elif feat2_cl.dtype != torch.float32 or out.dtype != torch.float32 or (feat1_cl is not None and feat1_cl.dtype != torch.float32):
+            raise _lib.Pn2Error("bf16 activations need the tensor-core path (set_mlp_precision('bf16') and widths it supports)")
         else:
             _lib.call("pn2_fp_mlp", B, n, m, D1, D2, ptr(feat1_cl), ptr(feat2_cl), ptr(idx), ptr(weight), mlp.desc, ptr(out),
                       _lib.stream_ptr(feat2_cl.device))
@@ -339,7 +357,7 @@ class PointNetSetAbstraction(nn.Module):
     def folded(self):
         return self._fold.get(self.mlp_convs, self.mlp_bns, [True] * len(self.mlp_convs))
 
-    def forward_cl(self, xyz_cl, feat_cl, geometry=None):
+    def forward_cl(self, xyz_cl, feat_cl, geometry=None, out_dtype=torch.float32):
         """Channel-last fused path: xyz (B, N, 3), feat (B, N, D) or None -> new_xyz (B, S, 3), (B, S, D').
         `geometry` = (new_xyz, ball_idx) lets several modules share one sampling / ball query."""
         if geometry is None:
@@ -347,7 +365,7 @@ class PointNetSetAbstraction(nn.Module):
             idx = pointnet2_utils.ball_query(self.radius, self.nsample, xyz_cl, new_xyz)
         else:
             new_xyz, idx = geometry
-        out = sa_mlp_max_cl(xyz_cl, feat_cl, new_xyz, idx, _lib.ORDER_XYZ_FIRST, self.folded())
+        out = sa_mlp_max_cl(xyz_cl, feat_cl, new_xyz, idx, _lib.ORDER_XYZ_FIRST, self.folded(), out_dtype=out_dtype)
         return new_xyz, out
 
     def forward(self, xyz, points):
@@ -449,7 +467,8 @@ class PointNetFeaturePropagation(nn.Module):
     def folded(self):
         return self._fold.get(self.mlp_convs, self.mlp_bns, [True] * len(self.mlp_convs))
 
-    def forward_cl(self, xyz1_cl, xyz2_cl, feat1_cl, feat2_cl, mlp=None, nn_weights=None, row_order=None):
+    def forward_cl(self, xyz1_cl, xyz2_cl, feat1_cl, feat2_cl, mlp=None, nn_weights=None, row_order=None,
+                   out_dtype=torch.float32):
         """xyz1 (B, N, 3), xyz2 (B, S, 3), feat1 (B, N, D1) or None, feat2 (B, S, D2) -> (B, N, D').
         `mlp` overrides the folded stack (a network appends its head to the last block);
         `nn_weights` = (idx, weight) computed elsewhere (e.g. on a side stream); `row_order` (B, N) int32 = a
@@ -462,7 +481,7 @@ class PointNetFeaturePropagation(nn.Module):
             idx, w = nn_weights
         else:
             idx, w = three_nn_weights_cl(xyz1_cl, xyz2_cl)
-        return fp_mlp_cl(feat1_cl, feat2_cl, idx, w, mlp, n, row_order=row_order)
+        return fp_mlp_cl(feat1_cl, feat2_cl, idx, w, mlp, n, row_order=row_order, out_dtype=out_dtype)
 
     def forward(self, xyz1, xyz2, points1, points2):
         """xyz1 (B, 3, N), xyz2 (B, 3, S), points1 (B, D1, N) or None, points2 (B, D2, S) -> (B, D', N)"""
