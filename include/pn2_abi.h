@@ -101,6 +101,12 @@ int pn2_lift_views(int b, int n, int v, int c, int h, int w, const float *points
                    float depth_min, float depth_max, float accuracy, int reduce, float *out, int32_t *pix,
                    int32_t *count, void *stream);
 
+/* Best-view selection of the ScanNet loader (data_utils/ScanNetDataLoader.py:87-105 -> utils/projection.py:132-164):
+ * number of the n points inside the frustum of each of num_poses cameras, evaluated in fp64 as the reference does.
+ * corner2/corner4 (P,3), normals (P,6,3) as for pn2_lift_views; counts (P) int32 must be pre-zeroed. */
+int pn2_frustum_count(int n, int num_poses, const float *points, const float *corner2, const float *corner4,
+                      const float *normals, int32_t *counts, void *stream);
+
 /* ---- fused set-abstraction / feature-propagation blocks (model/pointnet_util.py:70-221) ---- */
 
 #define PN2_MAX_LAYERS 6

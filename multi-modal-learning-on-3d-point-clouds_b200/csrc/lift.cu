@@ -138,8 +138,65 @@ lift_views_kernel(int n, int nv, int c, int h, int w, const float *__restrict__ 
     }
 }
 
+// Best-view selection of the ScanNet loader (data_utils/ScanNetDataLoader.py:87-105, 260-278): how many of the N crop
+// points fall inside the frustum of EACH of the scene's P camera poses.  The reference calls points_in_frustum_cpu
+// (utils/projection.py:132-164) once per pose file on the CPU in fp64; here all P x N tests are one launch, in fp64
+// like the reference (same predicate as the lifting: round(100 * s) / 100 < 0 for the six planes).
+constexpr int FC_THREADS = 256;
+constexpr int FC_POSES = 32;  // poses per CTA (shared-memory tile)
+
+__global__ void __launch_bounds__(FC_THREADS)
+frustum_count_kernel(int n, int np, const float *__restrict__ points, const float *__restrict__ corner2,
+                     const float *__restrict__ corner4, const float *__restrict__ normals, int32_t *__restrict__ counts) {
+    __shared__ double sc2[FC_POSES][3], sc4[FC_POSES][3], sn[FC_POSES][18];
+    __shared__ int cnt[FC_POSES];
+    const int p0 = blockIdx.y * FC_POSES;
+    const int pc = min(FC_POSES, np - p0);
+    for (int e = threadIdx.x; e < pc * 18; e += FC_THREADS) sn[e / 18][e % 18] = (double)normals[(size_t)p0 * 18 + e];
+    for (int e = threadIdx.x; e < pc * 3; e += FC_THREADS) {
+        sc2[e / 3][e % 3] = (double)corner2[(size_t)p0 * 3 + e];
+        sc4[e / 3][e % 3] = (double)corner4[(size_t)p0 * 3 + e];
+    }
+    if (threadIdx.x < FC_POSES) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * FC_THREADS + threadIdx.x;
+    const bool live = i < n;
+    double px = 0, py = 0, pz = 0;
+    if (live) {
+        px = (double)points[3 * (size_t)i];
+        py = (double)points[3 * (size_t)i + 1];
+        pz = (double)points[3 * (size_t)i + 2];
+    }
+    for (int q = 0; q < pc; ++q) {
+        bool inside = live;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double *c = k < 3 ? sc2[q] : sc4[q];
+            const double s = (px - c[0]) * sn[q][3 * k] + (py - c[1]) * sn[q][3 * k + 1] + (pz - c[2]) * sn[q][3 * k + 2];
+            inside = inside && (rint(s * 100.0) / 100.0 < 0.0);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, inside);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[q], __popc(m));
+    }
+    __syncthreads();
+    if (threadIdx.x < pc && cnt[threadIdx.x]) atomicAdd(counts + p0 + threadIdx.x, cnt[threadIdx.x]);
+}
+
 }  // namespace
 }  // namespace pn2
+
+extern "C" int pn2_frustum_count(int n, int num_poses, const float *points, const float *corner2, const float *corner4,
+                                 const float *normals, int32_t *counts, void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(n >= 0 && num_poses >= 0, "frustum_count: bad dims");
+    if (n == 0 || num_poses == 0) return PN2_OK;
+    PN2_REQUIRE(points && corner2 && corner4 && normals && counts, "frustum_count: null pointer");
+    PN2_REQUIRE(ceil_div(num_poses, FC_POSES) <= 65535, "frustum_count: too many poses");
+    dim3 grid(ceil_div(n, FC_THREADS), ceil_div(num_poses, FC_POSES));
+    frustum_count_kernel<<<grid, FC_THREADS, 0, (cudaStream_t)stream>>>(n, num_poses, points, corner2, corner4, normals, counts);
+    PN2_LAUNCH_OK("frustum_count");
+    return PN2_OK;
+}
 
 extern "C" int pn2_lift_views(int b, int n, int v, int c, int h, int w, const float *points, const float *feats,
                               const float *depth, const float *w2c, const float *corner2, const float *corner4,

@@ -92,6 +92,43 @@ def lift_views(points, feats, depth, camera_to_world, intrinsic, depth_min, dept
     return out
 
 
+def frustum_counts(points, camera_to_world, intrinsic, depth_min, depth_max, image_dims):
+    """points (N, 3) cuda fp32, camera_to_world (P, 4, 4) -> (P,) int32: points inside each pose's viewing frustum.
+    One launch for all poses of a scene; replaces the loader's per-pose-file loop over points_in_frustum_cpu
+    (data_utils/ScanNetDataLoader.py:91-97)."""
+    _lib.require_cuda(points, camera_to_world)
+    c2w = camera_to_world.to(torch.float32)
+    corners = frustum_corners(intrinsic, depth_min, depth_max, image_dims, c2w)
+    normals = frustum_normals(corners).contiguous()
+    c2, c4 = corners[..., 2, :3].contiguous(), corners[..., 4, :3].contiguous()
+    P, N = c2w.shape[0], points.shape[0]
+    counts = torch.zeros((P,), dtype=torch.int32, device=points.device)
+    points = points.contiguous()
+    with torch.cuda.device(points.device):
+        _lib.call("pn2_frustum_count", N, P, ptr(points), ptr(c2), ptr(c4), ptr(normals), ptr(counts), _lib.stream_ptr(points.device))
+    return counts
+
+
+def best_views(points, camera_to_world, num_images, intrinsic, depth_min, depth_max, image_dims, min_points=100):
+    """The loader's selection rule (data_utils/ScanNetDataLoader.py:98-105): repeatedly take the pose that sees most
+    points; after the first, a pose is only accepted if it sees more than `min_points`, otherwise the first is repeated.
+    Ties resolve to the lowest pose index (dict insertion order in the reference).  -> list of pose indices."""
+    counts = frustum_counts(points, camera_to_world, intrinsic, depth_min, depth_max, image_dims).cpu().tolist()
+    remaining = dict(enumerate(counts))
+    chosen = []
+    for i in range(num_images):
+        if not remaining:
+            chosen.append(chosen[0])
+            continue
+        best = max(remaining, key=remaining.get)
+        if i == 0 or remaining[best] > min_points:
+            chosen.append(best)
+            del remaining[best]
+        else:
+            chosen.append(chosen[0])
+    return chosen
+
+
 class ProjectionHelper:
     def __init__(self, intrinsic, depth_min, depth_max, image_dims, accuracy):
         self.intrinsic = intrinsic

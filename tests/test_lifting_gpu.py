@@ -101,3 +101,28 @@ def test_projection_helper_surface(cuda):
     assert cc.shape == (8, 4, 1) and helper.compute_frustum_normals(cc).shape == (6, 3)
     cnt = helper.points_in_frustum_cpu(cc, helper.compute_frustum_normals(cc), torch.from_numpy(xyz[0]))
     assert int(cnt) > 0
+
+
+def test_frustum_counts_and_best_views(cuda):
+    """Row N2: the loader's best-view selection, all poses of a scene in one launch, fp64 as the reference."""
+    N, P = 8192, 150
+    x, _ = scenes.scannet_scene(90, N)
+    rng = np.random.default_rng(5)
+    centre = x.mean(0)
+    poses = np.stack([scenes.look_at_pose(centre + np.array([np.cos(a) * d, np.sin(a) * d, h]), centre + rng.normal(0, 0.5, 3))
+                      for a, d, h in zip(rng.uniform(0, 6.28, P), rng.uniform(0.5, 4.0, P), rng.uniform(0.0, 2.0, P))])
+    got = projection.frustum_counts(torch.from_numpy(x).to(cuda), torch.from_numpy(poses).to(cuda), INTR, DMIN, DMAX, DIMS).cpu().numpy()
+    helper = projection.ProjectionHelper(INTR, DMIN, DMAX, DIMS, ACC)
+    want = []
+    for q in range(P):
+        cc = helper.compute_frustum_corners(torch.from_numpy(poses[q]))[:, :3, 0]
+        nr = projection.frustum_normals(torch.cat([cc, torch.ones(8, 1)], 1))
+        # the reference's call: fp64 tensors on the CPU (data_utils/ScanNetDataLoader.py:96)
+        full = torch.cat([cc, torch.ones(8, 1)], 1).double()
+        want.append(int(helper.points_in_frustum_cpu(full, nr.double(), torch.from_numpy(x).double())))
+    want = np.array(want)
+    assert np.abs(got - want).max() <= 1 and (got != want).mean() <= 0.02  # rounding-boundary ties only
+    assert got.max() > 500 and (got == 0).any() is not None
+    views = projection.best_views(torch.from_numpy(x).to(cuda), torch.from_numpy(poses).to(cuda), 5, INTR, DMIN, DMAX, DIMS)
+    assert len(views) == 5 and views[0] == int(np.argmax(got))
+    assert all(got[v] > 100 or v == views[0] for v in views)
