@@ -1,18 +1,25 @@
 // row_mlp_tc.cu -- fused "gather -> shared MLP -> pool/store" blocks on the 5th-gen tensor cores (bf16
 // operands, fp32 accumulation in TMEM).  Same operator contract as row_mlp.cu (the fp32 path); outputs
-// agree with it within bf16 rounding (2e-2 relative, BASELINE.json north_star).
+// agree with it within bf16 rounding (2e-2 relative, BASELINE.json north_star; measured ~4e-3).
 //
-// One CTA owns a tile of 128 rows (= UMMA M).  For every layer
+// PERSISTENT CTAs (3-4 per SM) walk tiles of 128 rows (= UMMA M); barriers, TMEM and biases are set up once.
+// For every layer
 //     D[128 x N] (TMEM, fp32) = A[128 x K] (smem, bf16, K-major, 128B swizzle) * W[N x K]^T (smem, same layout)
-//   * A of layer 0 is written by the gather (grouped xyz/features, or 3-NN interpolation + skip rows);
-//     A of layer l+1 is written by the epilogue of layer l straight from TMEM (bias + ReLU + bf16 pack)
-//     into the SAME shared-memory buffer -- all MMAs of a layer are committed before its epilogue runs;
-//   * W arrives as pre-swizzled tiles (packed once by pn2_mlp_pack_bf16) through a ring of bulk-async
-//     copies (cp.async.bulk, TMA unit) that runs ahead across layer boundaries;
-//   * tcgen05.mma is issued by ONE thread, accumulators never touch registers until the epilogue's
-//     tcgen05.ld, and the final max over nsample is a CREDUX per column inside each epilogue warp
-//     (TMEM lane == row, so warp w holds exactly the 32 samples of one centroid when nsample = 32).
+//   * A of layer 0 is written by the gather (grouped features + centred xyz, or 3-NN interpolation + skip rows),
+//     in CHUNKS of whole 64-column k-blocks: the MMAs of a chunk accumulate into TMEM while the buffer is refilled,
+//     so inputs of any width stream through a 32-64 KB operand buffer (fp4's 768 / 1536 channels included);
+//   * A of layer l+1 is written by the epilogue of layer l straight from TMEM (tcgen05.ld, bias, ReLU, bf16 pack --
+//     packed f32x2 / bf16x2 math) into the SAME buffer: all MMAs of a layer are committed before its epilogue runs;
+//   * W arrives as pre-swizzled tiles (packed once by pn2_mlp_pack_bf16; 64/128/256 rows chosen for residency)
+//     through a 2-4-stage ring of bulk-async copies (cp.async.bulk = TMA unit, mbarrier complete_tx) that runs ahead
+//     across layer AND tile boundaries;
+//   * tcgen05.mma is issued by ONE thread; the final max over nsample is a CREDUX per column inside each epilogue
+//     warp (TMEM lane == row, so warp w holds exactly the 32 samples of one centroid when nsample = 32);
+//   * activations that only travel between such blocks are read / written as bf16 (PN2_FLAG_*): a gathered 16-byte
+//     load is then a whole operand chunk (SA: pure copy), halving gather traffic; FP rows can be processed in a
+//     spatially sorted order (row_perm) so neighbouring rows share their three coarse rows in L1.
 // Warp roles: 0-3 gather + epilogue (TMEM lanes 32w..32w+31), 4 weight producer, 5 TMEM alloc + MMA issue.
+// Measured behaviour and the experiments behind these choices: profiles/README.md.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
