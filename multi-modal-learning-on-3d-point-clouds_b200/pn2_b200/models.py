@@ -121,8 +121,15 @@ class PointNet2SemSeg(nn.Module):
             keep += gr.tensors()
         keep += levels[1:] + balls + [t for pair in nnw if pair is not None for t in pair]
         if not torch.cuda.is_current_stream_capturing():
+            # eager mode: these tensors are produced on one stream and read on others; tell the caching allocator
+            # about every consumer stream so their memory is not reused while a consumer is still queued
             for t in keep:
-                t.record_stream(main)
+                for st in (main, s_fps, s_bq):
+                    t.record_stream(st)
+            for t in (xyz_cl, feat_cl):
+                if t is not None:
+                    t.record_stream(s_fps)
+                    t.record_stream(s_bq)
 
         # activations between tensor-core blocks travel as bf16 (they are rounded to bf16 for the MMA operand anyway;
         # halves the gather traffic).  Only when every block of the network runs on the tensor-core path.
