@@ -177,6 +177,38 @@ def time_ref_gpu(model, device, batch):
                     "TF32 allowed as torch defaults), batch %d, inputs resident, 5 steps" % batch}
 
 
+def time_train_step_msg(device, batch=8, steps=4):
+    """BASELINE config[1] as a data point: MSG semseg TRAIN step (forward + backward + Adam) on this GPU.  Geometry and its
+    backward scatter-adds are our kernels; conv / BatchNorm(train) / autograd are torch, as in the reference (the fused
+    training kernels are SURVEY 8f row N1, not built yet)."""
+    import torch.nn.functional as F
+    from pn2_b200 import scenes
+    from pn2_b200.models import PointNet2Multiview2Msg
+    torch.manual_seed(0)
+    net = PointNet2Multiview2Msg(NUM_CLASSES).to(device).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
+    pts = torch.from_numpy(scenes.scannet_batch(77, batch, NPOINTS)).to(device)
+    xyz = pts[:, :, :3].permute(0, 2, 1).contiguous()
+    img = torch.randn(batch, 128, NPOINTS, device=device)
+    target = (pts[:, :, 2].clamp(0, 2.69) / 2.7 * 20).long() + 1
+    ts = []
+    for i in range(steps + 2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = F.cross_entropy(net(xyz, img).reshape(-1, NUM_CLASSES), target.reshape(-1), ignore_index=0)
+        loss.backward()
+        opt.step()
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    ms = float(np.median(ts[2:])) * 1e3
+    del net, opt
+    torch.cuda.empty_cache()
+    return {"value": batch / ms * 1e3, "unit": "scenes/s", "ms_per_step": ms, "batch": batch,
+            "what": "PointNet2Multiview2Msg point branch (model/pointnet2multiview.py:179-233), fwd + bwd + Adam, synthetic lifted "
+                    "features, one GPU; geometry on our kernels, conv/BN/autograd torch (unfused training path)"}
+
+
 def op_rooflines(device, batch, pk):
     """HBM-roofline figures of the standalone gather / interpolate kernels at the C1 shapes (timed alone -> burst peak)."""
     from pn2_b200 import _lib as _lib_mod
@@ -416,6 +448,7 @@ def run_ours(args):
         if world == 1 and not args.no_extras:
             line["kernels"] = op_rooflines(device, B, pk)
             line["ref_gpu"] = time_ref_gpu(model, device, B)
+            line["train_step_msg"] = time_train_step_msg(device)
             cpu_v, cpu_ms, cores = cpu_reference_scenes_per_sec(3, 1, 4)
             line["cpu_baseline"] = {"value": cpu_v, "unit": "scenes/s", "cores": cores, "kind": "port",
                                     "sample": "4 scenes per step x 3 steps (+1 warm-up); restated CPU path (the reference ships "
