@@ -194,7 +194,7 @@ int pn2_three_nn_grid(int b, int n, int m, const float *unknown, const float *kn
 /* ---- developer hooks (tests / profiling; not part of the operator surface) ---- */
 /* FPS kernel choice for 1024 < n <= 8192: 0 automatic, 1 one CTA per cloud, 2 four-CTA cluster per cloud. */
 void pn2_debug_set_fps_mode(int mode);
-/* The next pn2_*_bf16 launch on this thread records clock64() phase stamps of CTA 0 into buf (>= 240 int64, device). */
+/* The next pn2_*_bf16 launch on this thread records clock64() phase stamps of CTA 0 into buf (>= 512 int64, device; MMA issuer stamps from [256]). */
 void pn2_debug_set_tc_timestamps(long long *buf);
 
 #ifdef __cplusplus

@@ -129,6 +129,45 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Issuer-warp variants: the WHOLE warp runs the schedule in uniform control flow and `leader` (one elected lane)
+// predicates the instruction; the descriptors' high words are constant (SBO 1024 B, version 1, SWIZZLE_128B) and only
+// the 14-bit start-address field of the low word moves, so a step along K is one 32-bit add.
+constexpr uint32_t DESC_HI = 0x40004040u;
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void tc_mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t leader) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %6};\n\t"
+        "mov.b64 db, {%2, %6};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(leader), "r"(DESC_HI)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_if(uint32_t bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(bar), "r"(leader)
+        : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t <-> lane base + t)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -196,54 +235,75 @@ struct RowCtx {
     long long out_row;  // FP: destination row (after the optional permutation)
 };
 
-__device__ __forceinline__ RowCtx row_setup(const TcParams &p, long long tile, int r) {
-    RowCtx c = {};
+// What a row needs from "index" memory (sample index / 3-NN indices and weights, centred xyz): 9 registers, loaded for
+// tile i+1 while the layers of tile i run, so the gather of a tile starts with its second-level loads.
+struct RowPre {
+    bool ok;
+    int i0, i1, i2;     // SA: i0 = global source row (b*n + pt).  FP: global coarse rows (b*m + idx)
+    float a, b, c;      // SA: centred xyz.  FP: interpolation weights
+    long long row;      // FP: destination row (after the optional permutation)
+};
+
+__device__ __forceinline__ RowPre row_prefetch(const TcParams &p, long long tile, int r) {
+    RowPre c = {};
+    if (tile >= p.tiles) return c;
     if (p.mode == MODE_SA) {
-        const int K = p.k, D = p.d;
-        const long long g = tile * (TC_ROWS / K) + r / K;
-        c.ok = g < p.groups;
+        const int K = p.k;
+        const int g = (int)tile * (TC_ROWS / K) + r / K;
+        c.ok = g < (int)p.groups;
         if (c.ok) {
-            const int b = (int)(g / p.m);
-            const int pt = __ldg(p.idx + g * K + (r % K));
-            const size_t src = (size_t)b * p.n + pt;
-            c.f = p.feat + src * D;
-            c.src0 = (long long)(src * D);
-            c.dx = __fsub_rn(__ldg(p.xyz + src * 3 + 0), __ldg(p.new_xyz + g * 3 + 0));
-            c.dy = __fsub_rn(__ldg(p.xyz + src * 3 + 1), __ldg(p.new_xyz + g * 3 + 1));
-            c.dz = __fsub_rn(__ldg(p.xyz + src * 3 + 2), __ldg(p.new_xyz + g * 3 + 2));
+            const int b = g / p.m;
+            const int pt = __ldg(p.idx + (size_t)g * K + (r % K));
+            const int src = b * p.n + pt;
+            c.i0 = src;
+            c.a = __fsub_rn(__ldg(p.xyz + (size_t)src * 3 + 0), __ldg(p.new_xyz + (size_t)g * 3 + 0));
+            c.b = __fsub_rn(__ldg(p.xyz + (size_t)src * 3 + 1), __ldg(p.new_xyz + (size_t)g * 3 + 1));
+            c.c = __fsub_rn(__ldg(p.xyz + (size_t)src * 3 + 2), __ldg(p.new_xyz + (size_t)g * 3 + 2));
         }
     } else {
-        const int D1 = p.d1, D2 = p.d2;
-        long long row = tile * TC_ROWS + r;
-        c.ok = row < p.rows;
+        int row = (int)tile * TC_ROWS + r;
+        c.ok = row < (int)p.rows;
         if (c.ok) {
-            const int b = (int)(row / p.n);
-            if (p.row_perm) row = (long long)b * p.n + __ldg(p.row_perm + row);  // spatially coherent processing order
-            const float *f2 = p.feat2 + (size_t)b * p.fp_m * D2;
-            const long long base2 = (long long)b * p.fp_m * D2;
+            const int b = row / p.n;
+            if (p.row_perm) row = b * p.n + __ldg(p.row_perm + row);  // spatially coherent processing order
             if (p.fp_m == 1) {
-                c.r0 = c.r1 = c.r2 = f2;  // S == 1: the coarse row is repeated
-                c.w0 = 1.f;
-                c.src0 = c.src1 = c.src2 = base2;
+                c.i0 = c.i1 = c.i2 = b;  // S == 1: the coarse row is repeated
+                c.a = 1.f;
             } else {
                 const int32_t *id = p.idx + (size_t)row * 3;
                 const float *w = p.weight + (size_t)row * 3;
-                c.r0 = f2 + (size_t)__ldg(id) * D2;
-                c.r1 = f2 + (size_t)__ldg(id + 1) * D2;
-                c.r2 = f2 + (size_t)__ldg(id + 2) * D2;
-                c.w0 = __ldg(w); c.w1 = __ldg(w + 1); c.w2 = __ldg(w + 2);
-                c.src0 = base2 + (c.r0 - f2); c.src1 = base2 + (c.r1 - f2); c.src2 = base2 + (c.r2 - f2);
+                c.i0 = b * p.fp_m + __ldg(id);
+                c.i1 = b * p.fp_m + __ldg(id + 1);
+                c.i2 = b * p.fp_m + __ldg(id + 2);
+                c.a = __ldg(w); c.b = __ldg(w + 1); c.c = __ldg(w + 2);
             }
-            c.f1 = p.feat1 + (size_t)row * D1;
         }
-        c.out_row = row;
+        c.row = row;
+    }
+    return c;
+}
+
+__device__ __forceinline__ RowCtx row_expand(const TcParams &p, const RowPre &q) {
+    RowCtx c = {};
+    c.ok = q.ok;
+    if (p.mode == MODE_SA) {
+        c.src0 = (long long)q.i0 * p.d;
+        c.f = p.feat + c.src0;
+        c.dx = q.a; c.dy = q.b; c.dz = q.c;
+    } else {
+        const long long D2 = p.d2;
+        c.src0 = q.i0 * D2; c.src1 = q.i1 * D2; c.src2 = q.i2 * D2;
+        c.r0 = p.feat2 + c.src0; c.r1 = p.feat2 + c.src1; c.r2 = p.feat2 + c.src2;
+        c.w0 = q.a; c.w1 = q.b; c.w2 = q.c;
+        c.f1 = p.feat1 + q.row * p.d1;
+        c.out_row = q.row;
     }
     return c;
 }
 
 template <bool kInBf16>
 __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &x, unsigned char *a, int r, int c8_begin,
-                                               int c8_from, int c8_end) {
+                                               int c8_from, int c8_end, const float (&sk)[8], bool sk_valid) {
     const bool ok = x.ok;
     if constexpr (kInBf16) {
         // bf16 activations: a 16-byte load is a whole 8-column chunk.  SA: the chunk IS the operand chunk (pure copy,
@@ -319,6 +379,8 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
                         y = fp3 ? __fmaf_rn(x.w2, __bfloat162float(b0[x.src2 + c]),
                                             __fmaf_rn(x.w0, __bfloat162float(b0[x.src0 + c]), __fmul_rn(x.w1, __bfloat162float(b0[x.src1 + c]))))
                                 : __bfloat162float(b0[x.src0 + c]);
+                    } else if (sk_valid && c8 == (Dm >> 3)) {
+                        y = sk[j];  // narrow fp32 skip block, loaded at the start of the tile
                     } else if (c < Dm + p.d1) {
                         y = p.skip_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(p.feat1)[x.out_row * p.d1 + (c - Dm)])
                                         : __ldg(p.feat1 + x.out_row * p.d1 + (c - Dm));
@@ -457,8 +519,9 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
     // bars: [0..4) full, [4..8) empty, [8] a_ready, [9] acc_ready, [10] a_free; then the TMEM base slot, exchange, biases
     const int S = p.stages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
-    float *xchg = reinterpret_cast<float *>(tmem_slot + 4);  // [4 warps][32] for nsample > 32
-    float *sbias = xchg + 4 * 32;                            // all layers' biases, zero padded to npad
+    float *xchg = reinterpret_cast<float *>(tmem_slot + 4);  // SA: [4 warps][32] maxima for nsample > 32
+    long long *srow = reinterpret_cast<long long *>(xchg);   // FP: destination row of each tile row (-1 = past the end)
+    float *sbias = xchg + 4 * 32 * 2;                        // all layers' biases, zero padded to npad
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
@@ -516,34 +579,50 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
             }
         }
     } else if (warp == 5) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: all 32 lanes walk the schedule (uniform control flow), one elected lane issues =====
+        {
+            const uint32_t leader = elect_one();
             int stage = 0;
             uint32_t phase = 0, it = 0;
-            const uint32_t a_addr = smem_u32(a_buf);
+            const uint32_t a_lo0 = desc_lo(smem_u32(a_buf));
+            const uint32_t w_lo0 = desc_lo(smem_u32(w_ring));
+            const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
+            const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
+            long long *dbgm = (p.dbg && blockIdx.x == 0 && lane == 0) ? p.dbg + 256 : nullptr;  // operand seen / MMAs issued
+            int dm = 0;
             for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 for (int l = 0; l < p.num_layers; ++l) {
-                    const TcLayer &L = p.layer[l];
-                    const int nkb = (L.kpad + KBLK - 1) / KBLK;
-                    const int nnb = L.npad / L.nblk;
-                    const uint32_t idesc = umma_idesc(L.nblk);
+                    const int kpad = p.layer[l].kpad, nblk = p.layer[l].nblk;
+                    const int nkb = (kpad + KBLK - 1) / KBLK;
+                    const int nnb = p.layer[l].npad / nblk;
+                    const uint32_t idesc = umma_idesc(nblk);
                     const int kch = l == 0 ? p.kchunk : nkb;
                     for (int k0 = 0; k0 < nkb; k0 += kch, ++it) {
                         mbar_wait(bar_a, it & 1);  // this chunk of the operand is in shared memory
                         tc_fence_after();
+                        if (dbgm && dm < 120) dbgm[dm++] = clock64();
+                        long long wsum = 0;
                         const int k1 = min(k0 + kch, nkb);
                         for (int nb = 0; nb < nnb; ++nb) {
-                            for (int kb = k0; kb < k1; ++kb) {
+                            const uint32_t d = tmem_d + (uint32_t)(nb * nblk);
+                            uint32_t a_lo = a_lo0;
+                            for (int kb = k0; kb < k1; ++kb, a_lo += A_BLOCK_BYTES >> 4) {
+                                const long long w0 = dbgm ? clock64() : 0;
                                 mbar_wait(bar_full + 8 * stage, phase);
                                 tc_fence_after();
-                                const uint32_t w_addr = smem_u32(w_ring + (size_t)stage * p.stage_bytes);
-                                const int k16n = min(KBLK, L.kpad - kb * KBLK) / 16;
-                                for (int k = 0; k < k16n; ++k) {
-                                    const uint64_t ad = umma_desc(a_addr + (kb - k0) * A_BLOCK_BYTES + k * 32);
-                                    const uint64_t bd = umma_desc(w_addr + k * 32);
-                                    tc_mma(tmem_base + (uint32_t)(nb * L.nblk), ad, bd, idesc, (uint32_t)((kb | k) != 0));
+                                if (dbgm) wsum += clock64() - w0;
+                                const uint32_t w_lo = w_lo0 + (uint32_t)stage * stage_step;
+                                const int k16n = min(KBLK, kpad - kb * KBLK) / 16;
+                                if (k16n == 4) {
+                                    tc_mma_lo(d, a_lo, w_lo, idesc, (uint32_t)(kb != 0), leader);
+                                    tc_mma_lo(d, a_lo + 2, w_lo + 2, idesc, 1u, leader);
+                                    tc_mma_lo(d, a_lo + 4, w_lo + 4, idesc, 1u, leader);
+                                    tc_mma_lo(d, a_lo + 6, w_lo + 6, idesc, 1u, leader);
+                                } else {
+                                    for (int k = 0; k < k16n; ++k)
+                                        tc_mma_lo(d, a_lo + 2 * k, w_lo + 2 * k, idesc, (uint32_t)((kb | k) != 0), leader);
                                 }
-                                tc_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
+                                tc_commit_if(bar_empty + 8 * stage, leader);  // frees the ring slot when these MMAs retire
                                 if (++stage == S) {
                                     stage = 0;
                                     phase ^= 1;
@@ -551,10 +630,15 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                             }
                         }
                         // accumulators complete (last chunk) / operand buffer reusable (earlier chunks)
-                        tc_commit(k1 == nkb ? bar_acc : bar_afree);
+                        tc_commit_if(k1 == nkb ? bar_acc : bar_afree, leader);
+                        if (dbgm && dm < 120) {
+                            dbgm[128 + dm / 2] = wsum + 1;  // cycles spent waiting for weight tiles in this chunk
+                            dbgm[dm++] = clock64();
+                        }
                     }
                 }
             }
+            __syncwarp();
         }
     } else {
         // ===== gather + epilogue warps: thread <-> row <-> TMEM lane =====
@@ -562,16 +646,25 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
         const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
         uint32_t it = 0;
         long long out_row = 0;
+        bool srow_ok = false;
         long long *dbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg : nullptr;
         int di = 0;
         uint32_t afree_it = 0;
+        RowPre pre = row_prefetch(p, blockIdx.x, r);
         for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             if (dbg && di < 240) dbg[di++] = clock64();
             {
-                const RowCtx ctx = row_setup(p, tile, r);
+                const RowCtx ctx = row_expand(p, pre);
                 out_row = ctx.out_row;
+                srow_ok = ctx.ok;
+                if (p.mode == MODE_FP) srow[r] = ctx.ok ? ctx.out_row : -1;  // read after the layer barriers, same warp
                 const int nkb0 = (p.layer[0].kpad + KBLK - 1) / KBLK;
                 const int c8_total = p.layer[0].kpad / 8;
+                // a narrow fp32 skip block (the xyz/colour rows of fp1) is fetched now, not after the first chunk's MMAs
+                float sk[8];
+                const bool sk_valid = kInBf16 && p.mode == MODE_FP && !p.skip_bf16 && p.d1 <= 8 && (p.d2 & 7) == 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sk[j] = (sk_valid && ctx.ok && j < p.d1) ? __ldg(ctx.f1 + j) : 0.f;
                 for (int k0 = 0; k0 < nkb0; k0 += p.kchunk) {
                     if (k0 > 0) {
                         mbar_wait(bar_afree, afree_it & 1);  // the MMAs of the previous chunk have consumed the buffer
@@ -581,11 +674,12 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                     // one thread per row, several 128-bit loads in flight per thread.  (A warp-cooperative variant -- one
                     // coalesced row per instruction, 8x fewer L1 wavefronts -- measured 10-25 % SLOWER: it serialises the
                     // rows of a warp and leaves too few loads in flight; see profiles/README.md.)
-                    gather_tail_tc<kInBf16>(p, ctx, a_buf, r, cb, cb, ce);
+                    gather_tail_tc<kInBf16>(p, ctx, a_buf, r, cb, cb, ce, sk, sk_valid);
                     fence_proxy_async();
                     mbar_arrive(bar_a);
                 }
             }
+            pre = row_prefetch(p, tile + gridDim.x, r);  // next tile's index-level loads fly while this tile's layers run
             if (dbg && di < 240) dbg[di++] = clock64();
             for (int l = 0; l < p.num_layers; ++l, ++it) {
                 const TcLayer &L = p.layer[l];
@@ -690,21 +784,49 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                             }
                         }
                     } else {
-                        // FP: rows are independent; stage through the (now idle) A buffer for coalesced stores
-                        float *stg = reinterpret_cast<float *>(a_buf) + warp * (32 * 33);
+                        // FP: rows are independent
+                        const int esz = p.out_bf16 ? 2 : 4;
+                        if (((cout * esz) & 15) == 0) {
+                            // rows start 16-byte aligned: the thread's 32 consecutive columns go out as 128-bit stores
+                            if (srow_ok) {
+                                if (p.out_bf16) {
+                                    uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.out) + (size_t)out_row * cout + c0);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
-                        __syncwarp();
-                        const long long row0 = tile * TC_ROWS + warp * 32;
-                        const int col = c0 + lane;
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const long long dst = __shfl_sync(0xffffffffu, out_row, rr);  // lane rr's (permuted) output row
-                            if (row0 + rr < p.rows && col < cout) {
-                                if (p.out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.out)[(size_t)dst * cout + col] = __float2bfloat16_rn(stg[rr * 33 + lane]);
-                                else p.out[(size_t)dst * cout + col] = stg[rr * 33 + lane];
+                                    for (int q = 0; q < 4; ++q)
+                                        if (c0 + 8 * q < cout) {
+                                            uint4 o;
+                                            o.x = pack_bf16(v[8 * q + 0], v[8 * q + 1]);
+                                            o.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+                                            o.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]);
+                                            o.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+                                            dst[q] = o;
+                                        }
+                                } else {
+                                    float4 *dst = reinterpret_cast<float4 *>(p.out + (size_t)out_row * cout + c0);
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q)
+                                        if (c0 + 4 * q < cout) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                                }
                             }
+                        } else {
+                            // odd widths (the 21-class head): transpose through the (now idle) A buffer, one row per store
+                            float *stg = reinterpret_cast<float *>(a_buf) + warp * (32 * 33);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+                            __syncwarp();
+                            const int col = c0 + lane;
+                            if (col < cout) {
+#pragma unroll 8
+                                for (int rr = 0; rr < 32; ++rr) {
+                                    const long long dst = srow[warp * 32 + rr];
+                                    if (dst >= 0) {
+                                        if (p.out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.out)[(size_t)dst * cout + col] = __float2bfloat16_rn(stg[rr * 33 + lane]);
+                                        else p.out[(size_t)dst * cout + col] = stg[rr * 33 + lane];
+                                    }
+                                }
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
                 }
                 if (!last) {
@@ -762,7 +884,7 @@ struct Plan {
 };
 
 constexpr size_t TC_SMEM_LIMIT = 227 * 1024;
-constexpr int TC_TAIL_BYTES = (2 * MAX_STAGES + 4) * 8 + 16 + 4 * 32 * 4;  // barriers, TMEM slot, exchange (+ biases)
+constexpr int TC_TAIL_BYTES = (2 * MAX_STAGES + 4) * 8 + 16 + 4 * 32 * 8;  // barriers, TMEM slot, exchange / row table (+ biases)
 
 Plan make_plan_capped(const pn2_mlp *mlp, int nblk_cap) {
     Plan P = {};
@@ -864,7 +986,11 @@ namespace {
 
 int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, cudaStream_t s) {
     p.dbg = take_tc_dbg();
-    PN2_REQUIRE(tiles <= 2147483647ll, "row_mlp_tc: too many tiles");
+    PN2_REQUIRE(tiles * TC_ROWS <= 2147483647ll, "row_mlp_tc: more than 2^31 rows in one launch");
+    if (p.mode == MODE_SA)
+        PN2_REQUIRE((p.groups / p.m) * (long long)p.n <= 2147483647ll, "row_mlp_tc: more than 2^31 source points in one launch");
+    else
+        PN2_REQUIRE((p.rows / p.n) * (long long)p.fp_m <= 2147483647ll, "row_mlp_tc: more than 2^31 coarse points in one launch");
     PN2_REQUIRE(((uintptr_t)packed & 15) == 0, "row_mlp_tc: packed weights must be 16-byte aligned");
     p.num_layers = P.num_layers;
     for (int l = 0; l < P.num_layers; ++l) p.layer[l] = P.layer[l];
@@ -986,7 +1112,8 @@ extern "C" int pn2_fp_mlp_bf16(int b, int n, int m, int d1, int d2, const float 
 }
 
 // Developer hook: the next pn2_*_bf16 launch on this thread records phase timestamps (clock64 of CTA 0, thread 0:
-// tile start, gather done, then per layer accumulator-ready / epilogue-done) into `buf` (>= 240 int64, device).
+// tile start, gather done, then per layer accumulator-ready / epilogue-done; from [256]: the MMA issuer's operand-seen /
+// MMAs-issued stamps per operand chunk) into `buf` (>= 512 int64, device).
 static thread_local long long *g_tc_dbg = nullptr;
 extern "C" void pn2_debug_set_tc_timestamps(long long *buf) { g_tc_dbg = buf; }
 namespace pn2 { long long *take_tc_dbg() { long long *b = g_tc_dbg; g_tc_dbg = nullptr; return b; } }
