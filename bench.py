@@ -279,8 +279,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     pk = peaks()
     B = args.batch
+    if args.fps_mode:
+        import ctypes
+        from pn2_b200 import _lib
+        _lib.load().pn2_debug_set_fps_mode(ctypes.c_int(args.fps_mode))
     if args.tc_max_ctas > 0:
         import ctypes
+        from pn2_b200 import _lib
         _lib.load().pn2_debug_set_tc_max_ctas(ctypes.c_int(args.tc_max_ctas))
     model = build_model(device)
     # rotating inputs: 24 distinct batches = 151 MB of input (+ the activations they produce) > the 126 MB L2
@@ -466,6 +471,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="scenes per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pipeline", type=int, default=6, help="batches in flight (graph instances on separate streams)")
+    ap.add_argument("--fps-mode", type=int, default=0, help="developer knob: 1 = one CTA per cloud, 2 = 4-CTA cluster per cloud")
     ap.add_argument("--tc-max-ctas", type=int, default=0, help="developer knob: cap resident CTAs/SM of the tensor-core MLP kernel")
     ap.add_argument("--no-graph", action="store_true", help="launch the forward eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the op rooflines / ref_gpu / cpu_baseline legs (for ncu runs)")

@@ -191,8 +191,19 @@ int pn2_three_nn_grid(int b, int n, int m, const float *unknown, const float *kn
                       const int32_t *cell_start, const float *meta, const int32_t *query_order, float *dist2,
                       int32_t *idx, float *weight, void *stream);
 
+/* ---- tuning ---- */
+/* Kernel policy of furthest point sampling for 1024 < n <= 8192 points per cloud.  Process-wide; read when a launch is
+ * issued (or captured into a CUDA graph).  The sampled indices are identical under every policy.
+ *   PN2_FPS_AUTO     a 4-CTA cluster per cloud while 4*b CTAs fit the GPU (lowest latency of a single batch), else ONE_CTA;
+ *   PN2_FPS_ONE_CTA  one 1024-thread CTA per cloud: ~30 % slower alone, but it occupies b SMs instead of 4*b, which is
+ *                    what counts when several batches are in flight (measured: 44.2 k -> 52.2 k scenes/s, profiles/README.md);
+ *   PN2_FPS_CLUSTER  always the cluster kernel.
+ * Returns the previous policy, or -1 for an unknown value. */
+enum { PN2_FPS_AUTO = 0, PN2_FPS_ONE_CTA = 1, PN2_FPS_CLUSTER = 2 };
+int pn2_set_fps_policy(int policy);
+
 /* ---- developer hooks (tests / profiling; not part of the operator surface) ---- */
-/* FPS kernel choice for 1024 < n <= 8192: 0 automatic, 1 one CTA per cloud, 2 four-CTA cluster per cloud. */
+/* Same switch as pn2_set_fps_policy, without the return value (kept for the profiling scripts). */
 void pn2_debug_set_fps_mode(int mode);
 /* The next pn2_*_bf16 launch on this thread records clock64() phase stamps of CTA 0 into buf (>= 512 int64, device; MMA issuer stamps from [256]). */
 void pn2_debug_set_tc_timestamps(long long *buf);

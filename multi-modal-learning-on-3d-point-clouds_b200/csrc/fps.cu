@@ -424,6 +424,12 @@ int launch_reg_small(int b, int n, int m, const float *xyz, int32_t *idx, float 
 // 0 = automatic, 1 = always one CTA per cloud, 2 = always the cluster kernel (tests / benchmarking)
 static int g_fps_mode = 0;
 extern "C" void pn2_debug_set_fps_mode(int mode) { g_fps_mode = mode; }
+extern "C" int pn2_set_fps_policy(int policy) {
+    if (policy < PN2_FPS_AUTO || policy > PN2_FPS_CLUSTER) return -1;
+    const int prev = g_fps_mode;
+    g_fps_mode = policy;
+    return prev;
+}
 
 namespace pn2 {
 namespace {

@@ -62,6 +62,7 @@ _OTHER = {
     "pn2_mlp_bf16_supported": ([ctypes.POINTER(Pn2Mlp)], _c_int),
     "pn2_grid_max_points": ([], _c_int),
     "pn2_grid_table_stride": ([], _c_int),
+    "pn2_set_fps_policy": ([_c_int], _c_int),
     "pn2_debug_set_fps_mode": ([_c_int], None),
     "pn2_debug_set_tc_timestamps": ([_vp], None),
     "pn2_mlp_pack_bf16_size": ([ctypes.POINTER(Pn2Mlp)], ctypes.c_longlong),

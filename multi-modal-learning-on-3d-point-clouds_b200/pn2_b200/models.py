@@ -15,7 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import pointnet2_utils
-from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, PointNetSetAbstractionMsg, SpatialGrid, _FoldCache, _fusable, fps_gather_cl,
+from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, PointNetSetAbstractionMsg, SpatialGrid, _FoldCache, _fusable, fps_gather_cl, fps_policy,
                             get_mlp_precision, grid_max_points, three_nn_weights_cl,
                             to_channel_last)
 
@@ -372,11 +372,13 @@ class PipelinedForward:
         self.depth = depth
         self.streams = [torch.cuda.Stream(example_xyz.device) for _ in range(depth)]
         self.slots = []
-        for st in self.streams:
-            st.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(st):
-                self.slots.append(GraphedForward(model, example_xyz, example_points))
-            torch.cuda.current_stream().wait_stream(st)
+        # with several batches in flight the sampling kernel should occupy few SMs rather than finish early
+        with fps_policy("throughput" if depth > 1 else "auto"):
+            for st in self.streams:
+                st.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(st):
+                    self.slots.append(GraphedForward(model, example_xyz, example_points))
+                torch.cuda.current_stream().wait_stream(st)
         self.kernels_per_replay = self.slots[0].kernels_per_replay
         self.i = 0
 

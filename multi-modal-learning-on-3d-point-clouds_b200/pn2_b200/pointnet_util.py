@@ -170,6 +170,26 @@ def to_channel_first(x):
     return out
 
 
+FPS_POLICIES = {"auto": 0, "throughput": 1, "latency": 2}
+
+
+class fps_policy:
+    """Context manager over pn2_set_fps_policy (include/pn2_abi.h): "auto", "throughput" (one CTA per cloud: leaves the
+    SMs to the other batches in flight) or "latency" (4-CTA cluster per cloud).  The policy is read when the sampling
+    kernel is launched or captured; results are identical."""
+
+    def __init__(self, policy):
+        self.policy = FPS_POLICIES[policy]
+
+    def __enter__(self):
+        self.prev = _lib.load().pn2_set_fps_policy(self.policy)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().pn2_set_fps_policy(self.prev)
+        return False
+
+
 def fps_gather_cl(xyz_cl, npoint):
     """xyz (B, N, 3) -> (idx (B, npoint) int32, new_xyz (B, npoint, 3)); the sampler writes the picked
     coordinates itself, replacing gather_operation + two layout copies (model/pointnet_util.py:34-35)."""

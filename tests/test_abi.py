@@ -46,6 +46,19 @@ def test_abi_version_and_error_string_without_gpu():
     assert lib.pn2_furthest_point_sampling(0, 8, 4, None, None, None, None) == 0  # empty batch: no-op
 
 
+def test_fps_policy_switch_returns_previous_value():
+    from pn2_b200 import _lib
+    lib = _lib.load()
+    assert lib.pn2_set_fps_policy(1) == 0
+    assert lib.pn2_set_fps_policy(2) == 1
+    assert lib.pn2_set_fps_policy(7) == -1          # unknown policy: refused, state unchanged
+    assert lib.pn2_set_fps_policy(0) == 2
+    from pn2_b200.pointnet_util import fps_policy
+    with fps_policy("throughput"):
+        assert lib.pn2_set_fps_policy(1) == 1
+    assert lib.pn2_set_fps_policy(0) == 0
+
+
 def test_pointnet2_cuda_dropin_surface():
     import pointnet2_cuda  # top-level shim next to the package, as model/pointnet2_utils.py:7 imports it
     for name in ["ball_query_wrapper", "group_points_wrapper", "group_points_grad_wrapper", "gather_points_wrapper",
