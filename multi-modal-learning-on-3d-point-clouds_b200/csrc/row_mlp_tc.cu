@@ -69,6 +69,8 @@ struct TcParams {
     int skip_bf16;     // FP skip features (feat1) are stored as bf16
     int out_bf16;      // write the result as bf16 (activations that only feed another tensor-core block)
     int kchunk;        // k-blocks of the first layer's operand produced per pass (see gather_chunk_tc)
+    int pool_t;        // SA: the last layer is computed TRANSPOSED (channels on TMEM lanes, samples on columns; see kernel)
+    int thin;          // the first layer's last k-block holds only 16 columns and lives in its own 4 KB region (see Plan)
     long long *dbg;    // optional phase timestamps of CTA 0 / warp 0 (developer profiling; NULL in production)
 };
 
@@ -116,23 +118,11 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 // Issuer-warp variants: the WHOLE warp runs the schedule in uniform control flow and `leader` (one elected lane)
 // predicates the instruction; the descriptors' high words are constant (SBO 1024 B, version 1, SWIZZLE_128B) and only
 // the 14-bit start-address field of the low word moves, so a step along K is one 32-bit add.
-constexpr uint32_t DESC_HI = 0x40004040u;
+constexpr uint32_t DESC_HI = 0x40004040u;        // SBO 1024 B | version 1 | SWIZZLE_128B
+constexpr uint32_t DESC_HI_THIN = 0x00004010u;   // SBO 256 B | version 1 | no swizzle (core-matrix layout)
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint32_t elect_one() {
     uint32_t pred;
@@ -145,18 +135,18 @@ __device__ __forceinline__ uint32_t elect_one() {
         : "=r"(pred));
     return pred;
 }
-__device__ __forceinline__ void tc_mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
-                                          uint32_t leader) {
+__device__ __forceinline__ void tc_mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate, uint32_t leader) {
     asm volatile(
         "{\n\t"
         ".reg .pred p, q;\n\t"
         ".reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %6};\n\t"
+        "mov.b64 da, {%1, %7};\n\t"
         "mov.b64 db, {%2, %6};\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "setp.ne.b32 q, %5, 0;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(leader), "r"(DESC_HI)
+        "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(leader), "r"(b_hi), "r"(a_hi)
         : "memory");
 }
 __device__ __forceinline__ void tc_commit_if(uint32_t bar, uint32_t leader) {
@@ -182,17 +172,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
-// (cute/arch/mma_sm100_desc.hpp: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;             // LBO (unused for swizzled K-major; canonical value 1)
-    d |= (uint64_t)(1024 >> 4) << 32;   // SBO: 8 rows * 128 B
-    d |= (uint64_t)1 << 46;             // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;             // SWIZZLE_128B
-    return d;
-}
+// UMMA shared-memory descriptors (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout type [61,64).  Operands are K-major with 128-byte swizzle and 8-row groups 1024 B apart
+// (desc_lo / DESC_HI above); the thin tail block is K-major without swizzle (DESC_HI_THIN).
 // Instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n  (cute UMMA::InstrDescriptor)
 __device__ __forceinline__ uint32_t umma_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
@@ -209,13 +191,27 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
-__device__ __forceinline__ void st_chunk(unsigned char *a, int r, int c8, const float (&v)[8]) {
+// Where the gather puts the 8-column chunk c8 of row r.  Chunks of whole 64-column k-blocks go to the swizzled pass
+// buffer (relative to the first chunk of the pass); the chunks of a THIN last k-block (16 columns: the xyz / colour
+// tail of most layers) go to a separate 4 KB region in the un-swizzled K-major core-matrix layout
+// (8 rows x 16 B contiguous, K step 128 B, 8-row groups 256 B apart), so the tail never costs a pass of its own.
+struct ADst {
+    unsigned char *a;
+    int r, c8_begin, thin_c8;
+    uint32_t thin_off;
+    __device__ __forceinline__ unsigned char *operator()(int c8) const {
+        if (c8 >= thin_c8) return a + thin_off + ((r >> 3) << 8) + ((c8 - thin_c8) << 7) + ((r & 7) << 4);
+        return a + swz_chunk(r, c8 - c8_begin, TC_ROWS);
+    }
+};
+
+__device__ __forceinline__ void st_chunk(unsigned char *dst, const float (&v)[8]) {
     uint4 q;
     q.x = pack_bf16(v[0], v[1]);
     q.y = pack_bf16(v[2], v[3]);
     q.z = pack_bf16(v[4], v[5]);
     q.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4 *>(a + swz_chunk(r, c8, TC_ROWS)) = q;
+    *reinterpret_cast<uint4 *>(dst) = q;
 }
 
 // ---- layer-0 operand: one thread per row, layout [block0 | block1 | zero pad] ---------------------------
@@ -302,8 +298,8 @@ __device__ __forceinline__ RowCtx row_expand(const TcParams &p, const RowPre &q)
 }
 
 template <bool kInBf16>
-__device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &x, unsigned char *a, int r, int c8_begin,
-                                               int c8_from, int c8_end, const float (&sk)[8], bool sk_valid) {
+__device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &x, const ADst &dst, int c8_from, int c8_end,
+                                               const float (&sk)[8], bool sk_valid) {
     const bool ok = x.ok;
     if constexpr (kInBf16) {
         // bf16 activations: a 16-byte load is a whole 8-column chunk.  SA: the chunk IS the operand chunk (pure copy,
@@ -349,7 +345,7 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
                         uo[e] = pack_bf16(lo, hi);
                     }
                 }
-                *reinterpret_cast<uint4 *>(a + swz_chunk(r, c8 + q - c8_begin, TC_ROWS)) = o;
+                *reinterpret_cast<uint4 *>(dst(c8 + q)) = o;
             }
         }
         // skip features stored as bf16 and chunk aligned: pure copies as well
@@ -359,7 +355,7 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
             for (; c8 < c8_skip_end; ++c8) {
                 uint4 o = make_uint4(0u, 0u, 0u, 0u);
                 if (ok) o = __ldg(reinterpret_cast<const uint4 *>(b1 + x.out_row * p.d1) + (c8 - Dm / 8));
-                *reinterpret_cast<uint4 *>(a + swz_chunk(r, c8 - c8_begin, TC_ROWS)) = o;
+                *reinterpret_cast<uint4 *>(dst(c8)) = o;
             }
         }
         // remaining chunks: centred xyz (SA) / fp32 skip channels (FP) / zero padding
@@ -388,7 +384,7 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
                 }
                 v[j] = y;
             }
-            st_chunk(a, r, c8 - c8_begin, v);
+            st_chunk(dst(c8), v);
         }
         return;
     } else if (p.mode == MODE_SA) {
@@ -406,7 +402,7 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
                 for (int q = 0; q < 4; ++q) {
                     const float v[8] = {u[2 * q].x, u[2 * q].y, u[2 * q].z, u[2 * q].w,
                                         u[2 * q + 1].x, u[2 * q + 1].y, u[2 * q + 1].z, u[2 * q + 1].w};
-                    st_chunk(a, r, c8 - c8_begin + q, v);
+                    st_chunk(dst(c8 + q), v);
                 }
             }
         }
@@ -432,7 +428,7 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
                     v[j] = y;
                 }
             }
-            st_chunk(a, r, c8 - c8_begin, v);
+            st_chunk(dst(c8), v);
         }
     } else {
         const int D1 = p.d1, D2 = p.d2;
@@ -465,7 +461,7 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
                                                      __ffma2_rn(ww0, make_float2(x0.z, x0.w), __fmul2_rn(ww1, make_float2(x1.z, x1.w))));
                         v[4 * q + 0] = lo.x; v[4 * q + 1] = lo.y; v[4 * q + 2] = hi.x; v[4 * q + 3] = hi.y;
                     }
-                    st_chunk(a, r, c8 - c8_begin + h, v);
+                    st_chunk(dst(c8 + h), v);
                 }
             }
         }
@@ -502,7 +498,7 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
                     v[j] = y;
                 }
             }
-            st_chunk(a, r, c8 - c8_begin, v);
+            st_chunk(dst(c8), v);
         }
     }
 }
@@ -516,9 +512,11 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
     unsigned char *a_buf = smem;
     unsigned char *w_ring = smem + p.a_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(w_ring + (size_t)p.stages * p.stage_bytes);
-    // bars: [0..4) full, [4..8) empty, [8] a_ready, [9] acc_ready, [10] a_free; then the TMEM base slot, exchange, biases
+    // bars: [0..4) full, [4..8) empty, [8] a_ready, [9] acc_ready, [10] a_free, [12..16) acc_ready of the transposed last
+    // layer's 128-channel blocks (one barrier per block: each completes once per tile, so the issuer can never run two
+    // phases ahead of a waiting warp); then the TMEM base slot, exchange, biases
     const int S = p.stages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 4);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 8);
     float *xchg = reinterpret_cast<float *>(tmem_slot + 4);  // SA: [4 warps][32] maxima for nsample > 32
     long long *srow = reinterpret_cast<long long *>(xchg);   // FP: destination row of each tile row (-1 = past the end)
     float *sbias = xchg + 4 * 32 * 2;                        // all layers' biases, zero padded to npad
@@ -527,6 +525,7 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
     const uint32_t bar_a = smem_u32(bars + 2 * MAX_STAGES), bar_acc = smem_u32(bars + 2 * MAX_STAGES + 1);
     const uint32_t bar_afree = smem_u32(bars + 2 * MAX_STAGES + 2);
+    const uint32_t bar_blk = smem_u32(bars + 2 * MAX_STAGES + 4);  // [4]
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -536,6 +535,7 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
         mbar_init(bar_a, TC_ROWS);
         mbar_init(bar_acc, 1);
         mbar_init(bar_afree, 1);
+        for (int q = 0; q < 4; ++q) mbar_init(bar_blk + 8 * q, 1);
         fence_mbar_init();
     }
     for (int l = 0; l < p.num_layers; ++l) {
@@ -559,17 +559,35 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                 for (int l = 0; l < p.num_layers; ++l) {
                     const TcLayer &L = p.layer[l];
                     const int nkb = (L.kpad + KBLK - 1) / KBLK;
-                    const int nnb = L.npad / L.nblk;
-                    const uint32_t bytes = (uint32_t)L.nblk * 128u;
+                    const bool tr = p.pool_t && l == p.num_layers - 1;
+                    // normal layers: one [nblk x 64] tile per stage.  Transposed last layer: a 128-row block of W (the
+                    // M operand) per stage, assembled from the same packed tiles.
+                    const int nnb = tr ? (L.npad + 127) / 128 : L.npad / L.nblk;
+                    const uint32_t tile_bytes = (uint32_t)L.nblk * 128u;
                     const unsigned char *src = p.packed + L.w_off;
                     const int kch = l == 0 ? p.kchunk : nkb;  // same (chunk, n-block, k-block) order as the MMA issuer
-                    for (int k0 = 0; k0 < nkb; k0 += kch)
+                    const int nfull = (l == 0) ? nkb - p.thin : nkb;
+                    for (int k0 = 0; k0 < nfull; k0 += kch)
                         for (int nb = 0; nb < nnb; ++nb)
-                            for (int kb = k0; kb < min(k0 + kch, nkb); ++kb) {
+                            for (int kb = k0; kb < (k0 + kch >= nfull ? nkb : k0 + kch); ++kb) {
                                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                                mbar_expect_tx(bar_full + 8 * stage, bytes);
-                                bulk_g2s(smem_u32(w_ring + (size_t)stage * p.stage_bytes), src + (size_t)(nb * nkb + kb) * bytes,
-                                         bytes, bar_full + 8 * stage);
+                                const uint32_t dst = smem_u32(w_ring + (size_t)stage * p.stage_bytes);
+                                if (!tr) {
+                                    mbar_expect_tx(bar_full + 8 * stage, tile_bytes);
+                                    bulk_g2s(dst, src + (size_t)(nb * nkb + kb) * tile_bytes, tile_bytes, bar_full + 8 * stage);
+                                } else {
+                                    const int row0 = nb * 128, rows = min(128, L.npad - row0);
+                                    mbar_expect_tx(bar_full + 8 * stage, (uint32_t)rows * 128u);
+                                    if (L.nblk >= 128) {
+                                        const int t = row0 / L.nblk, off = row0 % L.nblk;
+                                        bulk_g2s(dst, src + (size_t)(t * nkb + kb) * tile_bytes + (size_t)off * 128, (uint32_t)rows * 128u,
+                                                 bar_full + 8 * stage);
+                                    } else {
+                                        for (int q = 0; q * L.nblk < rows; ++q)
+                                            bulk_g2s(dst + (uint32_t)q * tile_bytes, src + (size_t)((row0 / L.nblk + q) * nkb + kb) * tile_bytes,
+                                                     tile_bytes, bar_full + 8 * stage);
+                                    }
+                                }
                                 if (++stage == S) {
                                     stage = 0;
                                     phase ^= 1;
@@ -586,23 +604,29 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
             uint32_t phase = 0, it = 0;
             const uint32_t a_lo0 = desc_lo(smem_u32(a_buf));
             const uint32_t w_lo0 = desc_lo(smem_u32(w_ring));
+            // thin region: un-swizzled K-major, LBO (K step between core matrices) 128 B, SBO (8-row groups) 256 B
+            const uint32_t thin_lo = (((smem_u32(a_buf) + (uint32_t)p.a_bytes - 4096u) & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
             const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
             const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0);
             long long *dbgm = (p.dbg && blockIdx.x == 0 && lane == 0) ? p.dbg + 256 : nullptr;  // operand seen / MMAs issued
             int dm = 0;
             for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 for (int l = 0; l < p.num_layers; ++l) {
-                    const int kpad = p.layer[l].kpad, nblk = p.layer[l].nblk;
+                    const bool tr = p.pool_t && l == p.num_layers - 1;  // D^T = W * A^T: W is the M operand, 128 samples are N
+                    const int kpad = p.layer[l].kpad, nblk = tr ? 128 : p.layer[l].nblk;
                     const int nkb = (kpad + KBLK - 1) / KBLK;
-                    const int nnb = p.layer[l].npad / nblk;
+                    const int nnb = tr ? (p.layer[l].npad + 127) / 128 : p.layer[l].npad / nblk;
                     const uint32_t idesc = umma_idesc(nblk);
                     const int kch = l == 0 ? p.kchunk : nkb;
-                    for (int k0 = 0; k0 < nkb; k0 += kch, ++it) {
+                    const int thin_kb = (l == 0 && p.thin) ? nkb - 1 : -1;  // the thin k-block rides with the last pass
+                    const int nfull = nkb - (thin_kb >= 0);
+                    for (int k0 = 0; k0 < nfull; k0 += kch, ++it) {
                         mbar_wait(bar_a, it & 1);  // this chunk of the operand is in shared memory
                         tc_fence_after();
                         if (dbgm && dm < 120) dbgm[dm++] = clock64();
                         long long wsum = 0;
-                        const int k1 = min(k0 + kch, nkb);
+                        const int k1 = (k0 + kch >= nfull) ? nkb : k0 + kch;
+                        const bool per_block = tr && nfull <= kch;  // single pass: hand over each 128-channel block as it completes
                         for (int nb = 0; nb < nnb; ++nb) {
                             const uint32_t d = tmem_d + (uint32_t)(nb * nblk);
                             uint32_t a_lo = a_lo0;
@@ -613,14 +637,23 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                                 if (dbgm) wsum += clock64() - w0;
                                 const uint32_t w_lo = w_lo0 + (uint32_t)stage * stage_step;
                                 const int k16n = min(KBLK, kpad - kb * KBLK) / 16;
-                                if (k16n == 4) {
-                                    tc_mma_lo(d, a_lo, w_lo, idesc, (uint32_t)(kb != 0), leader);
-                                    tc_mma_lo(d, a_lo + 2, w_lo + 2, idesc, 1u, leader);
-                                    tc_mma_lo(d, a_lo + 4, w_lo + 4, idesc, 1u, leader);
-                                    tc_mma_lo(d, a_lo + 6, w_lo + 6, idesc, 1u, leader);
+                                if (tr) {
+                                    // operands swapped: the weight block is the 128-row M operand
+                                    if (kb == thin_kb)
+                                        tc_mma_lo(d, w_lo, DESC_HI, thin_lo, DESC_HI_THIN, idesc, 1u, leader);
+                                    else
+                                        for (int k = 0; k < k16n; ++k)
+                                            tc_mma_lo(d, w_lo + 2 * k, DESC_HI, a_lo + 2 * k, DESC_HI, idesc, (uint32_t)((kb | k) != 0), leader);
+                                } else if (kb == thin_kb) {
+                                    tc_mma_lo(d, thin_lo, DESC_HI_THIN, w_lo, DESC_HI, idesc, 1u, leader);  // never the first k-block
+                                } else if (k16n == 4) {
+                                    tc_mma_lo(d, a_lo, DESC_HI, w_lo, DESC_HI, idesc, (uint32_t)(kb != 0), leader);
+                                    tc_mma_lo(d, a_lo + 2, DESC_HI, w_lo + 2, DESC_HI, idesc, 1u, leader);
+                                    tc_mma_lo(d, a_lo + 4, DESC_HI, w_lo + 4, DESC_HI, idesc, 1u, leader);
+                                    tc_mma_lo(d, a_lo + 6, DESC_HI, w_lo + 6, DESC_HI, idesc, 1u, leader);
                                 } else {
                                     for (int k = 0; k < k16n; ++k)
-                                        tc_mma_lo(d, a_lo + 2 * k, w_lo + 2 * k, idesc, (uint32_t)((kb | k) != 0), leader);
+                                        tc_mma_lo(d, a_lo + 2 * k, DESC_HI, w_lo + 2 * k, DESC_HI, idesc, (uint32_t)((kb | k) != 0), leader);
                                 }
                                 tc_commit_if(bar_empty + 8 * stage, leader);  // frees the ring slot when these MMAs retire
                                 if (++stage == S) {
@@ -628,9 +661,10 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                                     phase ^= 1;
                                 }
                             }
+                            if (per_block) tc_commit_if(bar_blk + 8 * nb, leader);
                         }
                         // accumulators complete (last chunk) / operand buffer reusable (earlier chunks)
-                        tc_commit_if(k1 == nkb ? bar_acc : bar_afree, leader);
+                        if (!per_block) tc_commit_if(k1 == nkb ? bar_acc : bar_afree, leader);
                         if (dbgm && dm < 120) {
                             dbgm[128 + dm / 2] = wsum + 1;  // cycles spent waiting for weight tiles in this chunk
                             dbgm[dm++] = clock64();
@@ -649,7 +683,7 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
         bool srow_ok = false;
         long long *dbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg : nullptr;
         int di = 0;
-        uint32_t afree_it = 0;
+        uint32_t afree_it = 0, tile_it = 0;
         RowPre pre = row_prefetch(p, blockIdx.x, r);
         for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             if (dbg && di < 240) dbg[di++] = clock64();
@@ -665,30 +699,105 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                 const bool sk_valid = kInBf16 && p.mode == MODE_FP && !p.skip_bf16 && p.d1 <= 8 && (p.d2 & 7) == 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) sk[j] = (sk_valid && ctx.ok && j < p.d1) ? __ldg(ctx.f1 + j) : 0.f;
-                for (int k0 = 0; k0 < nkb0; k0 += p.kchunk) {
+                const int nfull0 = nkb0 - p.thin;  // whole 64-column k-blocks; a thin last block rides with the last pass
+                ADst dst;
+                dst.a = a_buf;
+                dst.r = r;
+                dst.thin_c8 = p.thin ? nfull0 * 8 : (1 << 30);
+                dst.thin_off = (uint32_t)p.a_bytes - 4096u;
+                for (int k0 = 0; k0 < nfull0; k0 += p.kchunk) {
                     if (k0 > 0) {
                         mbar_wait(bar_afree, afree_it & 1);  // the MMAs of the previous chunk have consumed the buffer
                         ++afree_it;
                     }
-                    const int cb = k0 * 8, ce = min((k0 + p.kchunk) * 8, c8_total);
+                    const int cb = k0 * 8;
+                    const int ce = (k0 + p.kchunk >= nfull0) ? c8_total : (k0 + p.kchunk) * 8;
+                    dst.c8_begin = cb;
                     // one thread per row, several 128-bit loads in flight per thread.  (A warp-cooperative variant -- one
                     // coalesced row per instruction, 8x fewer L1 wavefronts -- measured 10-25 % SLOWER: it serialises the
                     // rows of a warp and leaves too few loads in flight; see profiles/README.md.)
-                    gather_tail_tc<kInBf16>(p, ctx, a_buf, r, cb, cb, ce, sk, sk_valid);
+                    gather_tail_tc<kInBf16>(p, ctx, dst, cb, ce, sk, sk_valid);
                     fence_proxy_async();
                     mbar_arrive(bar_a);
                 }
             }
             pre = row_prefetch(p, tile + gridDim.x, r);  // next tile's index-level loads fly while this tile's layers run
             if (dbg && di < 240) dbg[di++] = clock64();
-            for (int l = 0; l < p.num_layers; ++l, ++it) {
+            for (int l = 0; l < p.num_layers; ++l) {
                 const TcLayer &L = p.layer[l];
                 const bool last = (l == p.num_layers - 1);
                 const int npad = L.npad, cout = L.cout, relu = L.relu;
                 const float *bl = sbias + L.bias_off;
-                mbar_wait(bar_acc, it & 1);
-                tc_fence_after();
+                // the transposed last layer hands its accumulators over per 128-channel block (when it is one pass)
+                bool per_block = false;
+                if (last && p.pool_t) {
+                    const int nkb = (L.kpad + KBLK - 1) / KBLK;
+                    per_block = (l == 0 ? nkb - p.thin : nkb) <= (l == 0 ? p.kchunk : nkb);
+                }
+                if (!per_block) {
+                    mbar_wait(bar_acc, it & 1);
+                    ++it;
+                    tc_fence_after();
+                }
                 if (dbg && di < 240) dbg[di++] = clock64();
+                if (last && p.pool_t) {
+                    // Transposed last layer of an SA block: TMEM lane = output channel, column = sample, so the max over
+                    // the nsample rows of a group is a register-local tree (no shuffles / CREDUX), bias and ReLU are
+                    // applied once per group (max(x)+b == max(x+b) in fp32: rounding is monotone), and the 32 lanes of a
+                    // warp store 32 consecutive channels.
+                    const int K = p.k;
+                    const int ncb = (npad + 127) / 128;
+                    for (int cb = 0; cb < ncb; ++cb) {
+                        if (per_block) {
+                            mbar_wait(bar_blk + 8 * cb, tile_it & 1);
+                            tc_fence_after();
+                        }
+                        const int ch0 = cb * 128 + warp * 32;
+                        if (ch0 >= cout) continue;  // warp-uniform: e.g. 64 channels keep two warps busy
+                        const int ch = ch0 + lane;
+                        const float bias = bl[ch];
+                        float run = 0.f;
+                        for (int s0 = 0; s0 < TC_ROWS; s0 += 32) {
+                            uint32_t acc[32];
+                            tmem_ld32(lane_base + (uint32_t)(cb * 128 + s0), acc);
+                            float v[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                if (o < K) {
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 2 * o) v[j] = fmaxf(v[j], v[j + o]);
+                                }
+                            }
+                            if (K >= 32) {
+                                run = (s0 & (K - 1)) == 0 ? v[0] : fmaxf(run, v[0]);
+                                if (((s0 + 32) & (K - 1)) == 0) {
+                                    const long long g = tile * (TC_ROWS / K) + ((s0 + 32) / K - 1);
+                                    if (g < p.groups && ch < cout) {
+                                        const float y = relu ? fmaxf(run + bias, 0.f) : run + bias;
+                                        const size_t o = (size_t)g * p.out_stride + p.out_offset + ch;
+                                        if (p.out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.out)[o] = __float2bfloat16_rn(y);
+                                        else p.out[o] = y;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    if ((j & (K - 1)) == 0) {
+                                        const long long g = tile * (TC_ROWS / K) + (s0 + j) / K;
+                                        if (g < p.groups && ch < cout) {
+                                            const float y = relu ? fmaxf(v[j] + bias, 0.f) : v[j] + bias;
+                                            const size_t o = (size_t)g * p.out_stride + p.out_offset + ch;
+                                            if (p.out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.out)[o] = __float2bfloat16_rn(y);
+                                            else p.out[o] = y;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                } else
                 for (int c0 = 0; c0 < npad; c0 += 32) {
                     uint32_t acc[32];
                     tmem_ld32(lane_base + (uint32_t)c0, acc);
@@ -730,60 +839,7 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
-                    if (p.mode == MODE_SA) {
-                        // max over the nsample rows of each group (rows of a group are consecutive TMEM lanes)
-                        const int K = p.k;
-                        float keep = 0.f;
-                        if (K >= 32) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                // post-ReLU values are >= 0, so the unsigned order of the bits is the float order
-                                const uint32_t mx = __reduce_max_sync(0xffffffffu, __float_as_uint(v[j]));
-                                if (lane == j) keep = __uint_as_float(mx);
-                            }
-                            int gl = warp;  // group index within the tile
-                            if (K > 32) {
-                                // nsample 64 / 128: combine the per-warp maxima through shared memory
-                                xchg[warp * 32 + lane] = keep;
-                                asm volatile("bar.sync 1, 128;" ::: "memory");
-                                const int wpg = K / 32;
-                                if (warp % wpg == 0)
-                                    for (int q = 1; q < wpg; ++q) keep = fmaxf(keep, xchg[(warp + q) * 32 + lane]);
-                                asm volatile("bar.sync 1, 128;" ::: "memory");
-                                gl = (warp % wpg == 0) ? warp / wpg : -1;
-                            }
-                            const long long g = tile * (TC_ROWS / K) + gl;
-                            const int col = c0 + lane;
-                            if (gl >= 0 && g < p.groups && col < cout) {
-                                const size_t o = (size_t)g * p.out_stride + p.out_offset + col;
-                                if (p.out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.out)[o] = __float2bfloat16_rn(keep);
-                                else p.out[o] = keep;
-                            }
-                        } else {
-                            // nsample < 32: segmented butterflies inside the warp
-                            const int gpw = 32 / K;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                float x = v[j];
-                                for (int o = K / 2; o >= 1; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
-                                v[j] = x;
-                            }
-                            if (lane % K == 0) {
-                                const long long g = tile * (TC_ROWS / K) + warp * gpw + lane / K;
-                                if (g < p.groups) {
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) {
-                                        const int col = c0 + j;
-                                        if (col < cout) {
-                                            const size_t o = (size_t)g * p.out_stride + p.out_offset + col;
-                                            if (p.out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.out)[o] = __float2bfloat16_rn(v[j]);
-                                            else p.out[o] = v[j];
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                    } else {
+                    {
                         // FP: rows are independent
                         const int esz = p.out_bf16 ? 2 : 4;
                         if (((cout * esz) & 15) == 0) {
@@ -836,6 +892,7 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                 }
                 if (dbg && di < 240) dbg[di++] = clock64();
             }
+            ++tile_it;
             // the FP store staging aliases other warps' rows of A: all four warps leave the tile together
             tc_fence_before();
             asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -878,13 +935,13 @@ struct Plan {
     TcLayer layer[PN2_MAX_LAYERS];
     int num_layers;
     long long packed_bytes;
-    int a_bytes, stage_bytes, stages, tmem_cols, bias_floats, kchunk;
+    int a_bytes, stage_bytes, stages, tmem_cols, bias_floats, kchunk, thin;
     size_t smem_bytes;
     bool fits;
 };
 
 constexpr size_t TC_SMEM_LIMIT = 227 * 1024;
-constexpr int TC_TAIL_BYTES = (2 * MAX_STAGES + 4) * 8 + 16 + 4 * 32 * 8;  // barriers, TMEM slot, exchange / row table (+ biases)
+constexpr int TC_TAIL_BYTES = (2 * MAX_STAGES + 8) * 8 + 16 + 4 * 32 * 8;  // barriers, TMEM slot, exchange / row table (+ biases)
 
 Plan make_plan_capped(const pn2_mlp *mlp, int nblk_cap) {
     Plan P = {};
@@ -915,16 +972,21 @@ Plan make_plan_capped(const pn2_mlp *mlp, int nblk_cap) {
         nmax = nmax > L.npad ? nmax : L.npad;
     }
     P.packed_bytes = off;
-    // first-layer operand: produced in passes of `kchunk` k-blocks; at least 2, at most what the hidden layers need anyway
+    // first-layer operand: produced in passes of `kchunk` whole k-blocks; at least 2, at most what the hidden layers
+    // need anyway.  A last k-block of only 16 columns (67, 131, 134, 259 ... input channels: features + xyz / colour)
+    // gets its own 4 KB un-swizzled region and rides with the last pass instead of costing one.
     {
         const int nkb0 = (P.layer[0].kpad + KBLK - 1) / KBLK;
+        P.thin = (nkb0 >= 2 && P.layer[0].kpad % KBLK == 16) ? 1 : 0;
+        const int nfull0 = nkb0 - P.thin;
         int kc = amax > 2 ? amax : 2;
-        if (kc > nkb0) kc = nkb0;
+        if (kc > nfull0) kc = nfull0;
         P.kchunk = kc;
         amax = amax > kc ? amax : kc;
     }
     P.a_bytes = amax * A_BLOCK_BYTES;
     if (P.a_bytes < 4 * 32 * 33 * 4) P.a_bytes = ((4 * 32 * 33 * 4) + 1023) / 1024 * 1024;  // FP store staging
+    if (P.thin) P.a_bytes += 4096;  // thin region = the last 4 KB of the operand buffer
     P.stage_bytes = smax;
     P.tmem_cols = 32;
     while (P.tmem_cols < nmax) P.tmem_cols *= 2;
@@ -967,6 +1029,32 @@ Plan make_plan(const pn2_mlp *mlp) {
     return best;
 }
 
+// SA launches compute the last layer transposed: its weight block is the 128-row M operand (a ring stage must hold
+// 16 KB) and the accumulators take 128 columns per 128 output channels.  Same packed image, different residency:
+// prefer as many CTAs per SM as TMEM / registers allow, then the deepest ring.
+Plan sa_plan(const Plan &P0, bool in_bf16) {
+    Plan P = P0;
+    if (!P.fits) return P;
+    const TcLayer &L = P.layer[P.num_layers - 1];
+    const int need = (L.npad + 127) / 128 * 128;
+    while (P.tmem_cols < need) P.tmem_cols *= 2;
+    if (P.stage_bytes < 128 * 128) P.stage_bytes = 128 * 128;
+    P.fits = false;
+    if (P.tmem_cols > 512) return P;
+    const size_t fixed = 1024 + (size_t)P.a_bytes + TC_TAIL_BYTES + (size_t)P.bias_floats * 4;
+    int cmax = 512 / P.tmem_cols;
+    const int reg_cap = in_bf16 ? 3 : 4;
+    if (cmax > reg_cap) cmax = reg_cap;
+    for (int c = cmax; c >= 1 && !P.fits; --c)
+        for (int st = MAX_STAGES; st >= 2 && !P.fits; --st)
+            if ((size_t)c * (fixed + (size_t)st * P.stage_bytes + 1024) <= TC_SMEM_LIMIT + 1024) {
+                P.stages = st;
+                P.smem_bytes = fixed + (size_t)st * P.stage_bytes;
+                P.fits = true;
+            }
+    return P;
+}
+
 int check_mlp_tc(const char *op, const pn2_mlp *mlp, int c0) {
     PN2_REQUIRE(mlp, "%s: null mlp", op);
     PN2_REQUIRE(mlp->num_layers >= 1 && mlp->num_layers <= PN2_MAX_LAYERS, "%s: num_layers %d outside 1..%d", op,
@@ -1001,6 +1089,7 @@ int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, c
     p.tmem_cols = P.tmem_cols;
     p.bias_floats = P.bias_floats;
     p.kchunk = P.kchunk;
+    p.thin = P.thin;
     p.tiles = tiles;
     if (p.in_bf16)
         PN2_CUDA(cudaFuncSetAttribute(row_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
@@ -1026,7 +1115,8 @@ extern "C" void pn2_debug_set_tc_max_ctas(int n) { pn2::g_tc_max_ctas = n < 1 ? 
 
 extern "C" int pn2_mlp_bf16_supported(const pn2_mlp *mlp) {
     if (!mlp || mlp->num_layers < 1 || mlp->num_layers > PN2_MAX_LAYERS) return 0;
-    return pn2::make_plan(mlp).fits ? 1 : 0;
+    const pn2::Plan P = pn2::make_plan(mlp);  // must fit as an FP block and as an SA block (transposed last layer)
+    return (P.fits && pn2::sa_plan(P, true).fits) ? 1 : 0;
 }
 
 extern "C" long long pn2_mlp_pack_bf16_size(const pn2_mlp *mlp) {
@@ -1067,10 +1157,11 @@ extern "C" int pn2_sa_mlp_max_bf16(int b, int n, int m, int k, int d, const floa
         return set_error(PN2_ERR_UNSUPPORTED, "sa_mlp_max_bf16: nsample must be a power of two <= 128 (got %d)", k);
     for (int l = 0; l < mlp->num_layers; ++l)
         if (!mlp->relu[l]) return set_error(PN2_ERR_UNSUPPORTED, "sa_mlp_max_bf16: every SA layer must end in ReLU");
-    const Plan P = make_plan(mlp);
+    const Plan P = sa_plan(make_plan(mlp), (flags & PN2_FLAG_IN_BF16) != 0);
     if (!P.fits) return set_error(PN2_ERR_UNSUPPORTED, "sa_mlp_max_bf16: channel widths exceed shared memory / TMEM; use the fp32 path");
     TcParams p = {};
     p.mode = MODE_SA;
+    p.pool_t = 1;
     p.n = n; p.m = m; p.k = k; p.d = d;
     p.groups = (long long)b * m;
     p.xyz = xyz; p.feat = feat; p.new_xyz = new_xyz; p.idx = idx;
