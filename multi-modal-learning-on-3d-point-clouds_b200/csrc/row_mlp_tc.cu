@@ -532,7 +532,9 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        mbar_init(bar_a, TC_ROWS);
+        // one arrival per worker warp (after __syncwarp): every arrival wakes the warps parked on ANY barrier of the CTA,
+        // so 128 per-thread arrivals per layer kept the producer / issuer warps spinning (3 M wake-ups per sa1 launch)
+        mbar_init(bar_a, TC_ROWS / 32);
         mbar_init(bar_acc, 1);
         mbar_init(bar_afree, 1);
         for (int q = 0; q < 4; ++q) mbar_init(bar_blk + 8 * q, 1);
@@ -718,7 +720,8 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                     // rows of a warp and leaves too few loads in flight; see profiles/README.md.)
                     gather_tail_tc<kInBf16>(p, ctx, dst, cb, ce, sk, sk_valid);
                     fence_proxy_async();
-                    mbar_arrive(bar_a);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_a);
                 }
             }
             pre = row_prefetch(p, tile + gridDim.x, r);  // next tile's index-level loads fly while this tile's layers run
@@ -888,7 +891,8 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                 if (!last) {
                     tc_fence_before();    // TMEM reads done before the next layer's MMAs overwrite the accumulators
                     fence_proxy_async();  // bf16 activations visible to the tensor core (async proxy)
-                    mbar_arrive(bar_a);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_a);
                 }
                 if (dbg && di < 240) dbg[di++] = clock64();
             }
