@@ -30,6 +30,30 @@ __device__ __forceinline__ void warp_argmax(uint32_t &hi, uint32_t &lo) {
     hi = mh;
 }
 
+// Running-minimum update of a thread's P points against the newest pick.  Pairs of points go through the packed
+// f32x2 pipe (FADD2 / FMUL2 / FFMA2: half the issue slots of the scalar sequence); every lane performs exactly the
+// IEEE operations of dist_ref -- x - c is x + (-c), then rn(dy*dy), fma(dx,dx,.), fma(dz,dz,.) -- so the result is
+// bit-identical.
+template <int P>
+__device__ __forceinline__ void update_min(const float (&x)[P], const float (&y)[P], const float (&z)[P], float (&tm)[P],
+                                           float cx, float cy, float cz) {
+    if constexpr (P % 2 == 0) {
+        const float2 nx = make_float2(-cx, -cx), ny = make_float2(-cy, -cy), nz = make_float2(-cz, -cz);
+#pragma unroll
+        for (int i = 0; i < P; i += 2) {
+            const float2 dx = __fadd2_rn(make_float2(x[i], x[i + 1]), nx);
+            const float2 dy = __fadd2_rn(make_float2(y[i], y[i + 1]), ny);
+            const float2 dz = __fadd2_rn(make_float2(z[i], z[i + 1]), nz);
+            const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+            tm[i] = fminf(d.x, tm[i]);
+            tm[i + 1] = fminf(d.y, tm[i + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) tm[i] = fminf(dist_ref(x[i], y[i], z[i], cx, cy, cz), tm[i]);
+    }
+}
+
 template <int T>
 struct Log2 {
     static constexpr int value = 1 + Log2<T / 2>::value;
@@ -82,12 +106,11 @@ fps_reg_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__restr
     }
 
     for (int j = 1; j < m; ++j) {
-        tm[0] = fminf(dist_ref(x[0], y[0], z[0], x1, y1, z1), tm[0]);
+        update_min<P>(x, y, z, tm, x1, y1, z1);
         float best = tm[0];
         int besti = 0;
 #pragma unroll
         for (int i = 1; i < P; ++i) {
-            tm[i] = fminf(dist_ref(x[i], y[i], z[i], x1, y1, z1), tm[i]);
             if (tm[i] > best) {
                 best = tm[i];
                 besti = i;
@@ -214,11 +237,11 @@ fps_cluster_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__r
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_base + (uint32_t)par * 8u), "r"(32 * 20)
                          : "memory");
         // update the running minima, then a pairwise (log-depth) in-thread arg-max; on ties the lower i wins
+        update_min<P>(x, y, z, tm, x1, y1, z1);
         float bv[P];
         int bi[P];
 #pragma unroll
         for (int i = 0; i < P; ++i) {
-            tm[i] = fminf(dist_ref(x[i], y[i], z[i], x1, y1, z1), tm[i]);
             bv[i] = tm[i];
             bi[i] = i;
         }
