@@ -40,6 +40,7 @@ struct TcLayer {
     int kpad;            // cin rounded up to 16 (MMA K granularity)
     int npad;            // cout rounded up to 32 (MMA N, and the epilogue's 32-column loads)
     int nblk;            // rows of one weight tile: min(npad, 256)
+    int nnb, nkb;        // npad / nblk weight tiles along N, ceil(kpad / 64) k-blocks (host-computed: no device divisions)
     int relu;
     const float *bias;
     long long w_off;     // byte offset of this layer's first tile in the packed buffer
@@ -245,11 +246,16 @@ __device__ __forceinline__ RowPre row_prefetch(const TcParams &p, long long tile
     if (tile >= p.tiles) return c;
     if (p.mode == MODE_SA) {
         const int K = p.k;
-        const int g = (int)tile * (TC_ROWS / K) + r / K;
+        const int lgK = 31 - __clz(K);  // nsample is a power of two
+        const int gpt = TC_ROWS >> lgK;  // groups per tile
+        const int g0 = (int)tile * gpt;
+        const int g = g0 + (r >> lgK);
         c.ok = g < (int)p.groups;
         if (c.ok) {
-            const int b = g / p.m;
-            const int pt = __ldg(p.idx + (size_t)g * K + (r % K));
+            // the batch index of the tile's first group is uniform; a tile spans at most two clouds when gpt <= m
+            int b = g0 / p.m;
+            b = gpt <= p.m ? b + (g >= (b + 1) * p.m) : g / p.m;
+            const int pt = __ldg(p.idx + (size_t)g * K + (r & (K - 1)));
             const int src = b * p.n + pt;
             c.i0 = src;
             c.a = __fsub_rn(__ldg(p.xyz + (size_t)src * 3 + 0), __ldg(p.new_xyz + (size_t)g * 3 + 0));
@@ -257,10 +263,12 @@ __device__ __forceinline__ RowPre row_prefetch(const TcParams &p, long long tile
             c.c = __fsub_rn(__ldg(p.xyz + (size_t)src * 3 + 2), __ldg(p.new_xyz + (size_t)g * 3 + 2));
         }
     } else {
-        int row = (int)tile * TC_ROWS + r;
+        const int row0 = (int)tile * TC_ROWS;
+        int row = row0 + r;
         c.ok = row < (int)p.rows;
         if (c.ok) {
-            const int b = row / p.n;
+            int b = row0 / p.n;  // uniform; a tile spans at most two clouds when n >= 128
+            b = TC_ROWS <= p.n ? b + (row >= (b + 1) * p.n) : row / p.n;
             if (p.row_perm) row = b * p.n + __ldg(p.row_perm + row);  // spatially coherent processing order
             if (p.fp_m == 1) {
                 c.i0 = c.i1 = c.i2 = b;  // S == 1: the coarse row is repeated
@@ -503,6 +511,73 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
     }
 }
 
+// Warp-cooperative gather of bf16 feature rows: the warp's 32 rows x nc 16-byte chunks are walked as one flat list,
+// 32 items per step, so consecutive lanes read consecutive 16 bytes of the SAME source row (a 256-byte row is 2 L1
+// wavefronts instead of 16 scattered ones -- the per-thread-row gather is L1-wavefront bound).  A lane gets the source
+// row (and the interpolation weights) of the row it serves from that row's owner lane with shuffles.  U steps are
+// batched so U (SA: copy) or 3U (FP: three neighbours) 128-bit loads are in flight per lane.
+template <int U>
+__device__ __forceinline__ void coop_gather_bf16(const TcParams &p, const RowPre &pre, unsigned char *a, int warp, int lane,
+                                                 int c8_begin, int c8_from, int c8_to) {
+    const bool sa = p.mode == MODE_SA;
+    const __nv_bfloat16 *b0 = reinterpret_cast<const __nv_bfloat16 *>(sa ? (const void *)p.feat : (const void *)p.feat2);
+    const size_t Dm = sa ? p.d : p.d2;
+    const bool fp3 = !sa && p.fp_m != 1;
+    const int nc = c8_to - c8_from;  // power of two, >= 4
+    const int lg = 31 - __clz(nc);
+    const int my0 = pre.ok ? pre.i0 : -1, my1 = pre.i1, my2 = pre.i2;
+    for (int base = 0; base < 32 * nc; base += 32 * U) {
+        uint4 q0[U], q1[U], q2[U];
+        float w0[U], w1[U], w2[U];
+        int rw[U], ch[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int item = base + 32 * u + lane;
+            rw[u] = item >> lg;
+            ch[u] = item & (nc - 1);
+            const int s0 = __shfl_sync(0xffffffffu, my0, rw[u]);
+            q0[u] = make_uint4(0u, 0u, 0u, 0u);
+            q1[u] = q0[u];
+            q2[u] = q0[u];
+            if (fp3) {
+                const int s1 = __shfl_sync(0xffffffffu, my1, rw[u]);
+                const int s2 = __shfl_sync(0xffffffffu, my2, rw[u]);
+                w0[u] = __shfl_sync(0xffffffffu, pre.a, rw[u]);
+                w1[u] = __shfl_sync(0xffffffffu, pre.b, rw[u]);
+                w2[u] = __shfl_sync(0xffffffffu, pre.c, rw[u]);
+                if (s0 >= 0) {
+                    q0[u] = __ldg(reinterpret_cast<const uint4 *>(b0 + (size_t)s0 * Dm) + c8_from + ch[u]);
+                    q1[u] = __ldg(reinterpret_cast<const uint4 *>(b0 + (size_t)s1 * Dm) + c8_from + ch[u]);
+                    q2[u] = __ldg(reinterpret_cast<const uint4 *>(b0 + (size_t)s2 * Dm) + c8_from + ch[u]);
+                }
+            } else if (s0 >= 0) {
+                q0[u] = __ldg(reinterpret_cast<const uint4 *>(b0 + (size_t)s0 * Dm) + c8_from + ch[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint4 o = q0[u];
+            if (fp3) {
+                const uint32_t *u0 = reinterpret_cast<const uint32_t *>(&q0[u]);
+                const uint32_t *u1 = reinterpret_cast<const uint32_t *>(&q1[u]);
+                const uint32_t *u2 = reinterpret_cast<const uint32_t *>(&q2[u]);
+                uint32_t *uo = reinterpret_cast<uint32_t *>(&o);
+                const float2 ww0 = make_float2(w0[u], w0[u]), ww1 = make_float2(w1[u], w1[u]), ww2 = make_float2(w2[u], w2[u]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    // bf16 -> fp32 is a 16-bit shift; packed f32x2 = the scalar rn sequence of three_interpolate per lane
+                    const float2 a0 = make_float2(__uint_as_float(u0[e] << 16), __uint_as_float(u0[e] & 0xffff0000u));
+                    const float2 a1 = make_float2(__uint_as_float(u1[e] << 16), __uint_as_float(u1[e] & 0xffff0000u));
+                    const float2 a2 = make_float2(__uint_as_float(u2[e] << 16), __uint_as_float(u2[e] & 0xffff0000u));
+                    const float2 y = __ffma2_rn(ww2, a2, __ffma2_rn(ww0, a0, __fmul2_rn(ww1, a1)));
+                    uo[e] = pack_bf16(y.x, y.y);
+                }
+            }
+            *reinterpret_cast<uint4 *>(a + swz_chunk(warp * 32 + rw[u], c8_from + ch[u] - c8_begin, TC_ROWS)) = o;
+        }
+    }
+}
+
 // Two instantiations: fp32 gathered features (lean: 4 CTAs/SM) and bf16 gathered features (3 CTAs/SM).
 template <bool kInBf16>
 __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel(const __grid_constant__ TcParams p) {
@@ -560,11 +635,11 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
             for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 for (int l = 0; l < p.num_layers; ++l) {
                     const TcLayer &L = p.layer[l];
-                    const int nkb = (L.kpad + KBLK - 1) / KBLK;
+                    const int nkb = L.nkb;
                     const bool tr = p.pool_t && l == p.num_layers - 1;
                     // normal layers: one [nblk x 64] tile per stage.  Transposed last layer: a 128-row block of W (the
                     // M operand) per stage, assembled from the same packed tiles.
-                    const int nnb = tr ? (L.npad + 127) / 128 : L.npad / L.nblk;
+                    const int nnb = tr ? (L.npad + 127) / 128 : L.nnb;
                     const uint32_t tile_bytes = (uint32_t)L.nblk * 128u;
                     const unsigned char *src = p.packed + L.w_off;
                     const int kch = l == 0 ? p.kchunk : nkb;  // same (chunk, n-block, k-block) order as the MMA issuer
@@ -616,8 +691,8 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                 for (int l = 0; l < p.num_layers; ++l) {
                     const bool tr = p.pool_t && l == p.num_layers - 1;  // D^T = W * A^T: W is the M operand, 128 samples are N
                     const int kpad = p.layer[l].kpad, nblk = tr ? 128 : p.layer[l].nblk;
-                    const int nkb = (kpad + KBLK - 1) / KBLK;
-                    const int nnb = tr ? (p.layer[l].npad + 127) / 128 : p.layer[l].npad / nblk;
+                    const int nkb = p.layer[l].nkb;
+                    const int nnb = tr ? (p.layer[l].npad + 127) / 128 : p.layer[l].nnb;
                     const uint32_t idesc = umma_idesc(nblk);
                     const int kch = l == 0 ? p.kchunk : nkb;
                     const int thin_kb = (l == 0 && p.thin) ? nkb - 1 : -1;  // the thin k-block rides with the last pass
@@ -715,10 +790,20 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                     const int cb = k0 * 8;
                     const int ce = (k0 + p.kchunk >= nfull0) ? c8_total : (k0 + p.kchunk) * 8;
                     dst.c8_begin = cb;
-                    // one thread per row, several 128-bit loads in flight per thread.  (A warp-cooperative variant -- one
-                    // coalesced row per instruction, 8x fewer L1 wavefronts -- measured 10-25 % SLOWER: it serialises the
-                    // rows of a warp and leaves too few loads in flight; see profiles/README.md.)
-                    gather_tail_tc<kInBf16>(p, ctx, dst, cb, ce, sk, sk_valid);
+                    int from = cb;
+                    if constexpr (kInBf16) {
+                        // bf16 feature block: coalesced warp-cooperative gather when its chunk count in this pass is a
+                        // power of two (>= 4) and the block ends on a k-block boundary; the tail stays one thread per row
+                        const int Dm = p.mode == MODE_SA ? p.d : p.d2;
+                        const int blk0_end = min(ce, Dm >> 3);
+                        const int nc = blk0_end - cb;
+                        if ((Dm & 63) == 0 && nc >= 4 && (nc & (nc - 1)) == 0) {
+                            if (p.mode == MODE_SA) coop_gather_bf16<4>(p, pre, a_buf, warp, lane, cb, cb, blk0_end);
+                            else coop_gather_bf16<2>(p, pre, a_buf, warp, lane, cb, cb, blk0_end);
+                            from = blk0_end;
+                        }
+                    }
+                    if (from < ce) gather_tail_tc<kInBf16>(p, ctx, dst, from, ce, sk, sk_valid);
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_a);
@@ -749,6 +834,8 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                     // applied once per group (max(x)+b == max(x+b) in fp32: rounding is monotone), and the 32 lanes of a
                     // warp store 32 consecutive channels.
                     const int K = p.k;
+                    const int lgK = 31 - __clz(K);  // nsample is a power of two
+                    const long long g_tile = tile << (7 - lgK);  // first group of this tile (128 / K groups per tile)
                     const int ncb = (npad + 127) / 128;
                     for (int cb = 0; cb < ncb; ++cb) {
                         if (per_block) {
@@ -776,7 +863,7 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                             if (K >= 32) {
                                 run = (s0 & (K - 1)) == 0 ? v[0] : fmaxf(run, v[0]);
                                 if (((s0 + 32) & (K - 1)) == 0) {
-                                    const long long g = tile * (TC_ROWS / K) + ((s0 + 32) / K - 1);
+                                    const long long g = g_tile + (((s0 + 32) >> lgK) - 1);
                                     if (g < p.groups && ch < cout) {
                                         const float y = relu ? fmaxf(run + bias, 0.f) : run + bias;
                                         const size_t o = (size_t)g * p.out_stride + p.out_offset + ch;
@@ -788,7 +875,7 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
                                     if ((j & (K - 1)) == 0) {
-                                        const long long g = tile * (TC_ROWS / K) + (s0 + j) / K;
+                                        const long long g = g_tile + ((s0 + j) >> lgK);
                                         if (g < p.groups && ch < cout) {
                                             const float y = relu ? fmaxf(v[j] + bias, 0.f) : v[j] + bias;
                                             const size_t o = (size_t)g * p.out_stride + p.out_offset + ch;
@@ -966,6 +1053,8 @@ Plan make_plan_capped(const pn2_mlp *mlp, int nblk_cap) {
         L.bias_off = boff;
         boff += L.npad;
         const int nkb = (L.kpad + KBLK - 1) / KBLK;
+        L.nkb = nkb;
+        L.nnb = L.npad / L.nblk;
         off += (long long)L.npad * nkb * 128;
         if (l > 0) amax = amax > nkb ? amax : nkb;                        // operand of this layer (layer 0 is chunked)
         if (l + 1 < mlp->num_layers) {
