@@ -156,6 +156,9 @@ int pn2_mlp_pack_bf16(const pn2_mlp *mlp, int first_layer_rotate, void *packed, 
 #define PN2_FLAG_IN_BF16 1   /* SA: feat, FP: feat2 (needs d resp. d2 % 8 == 0, 16-byte aligned rows) */
 #define PN2_FLAG_SKIP_BF16 2 /* FP: feat1 (needs PN2_FLAG_IN_BF16 and d1 % 8 == 0) */
 #define PN2_FLAG_OUT_BF16 4  /* out */
+#define PN2_FLAG_OUT_ARGMAX 8 /* FP only: out is (B,n) uint8, the index of the largest output channel of each row (first
+                               * maximum, as numpy.argmax) -- the per-point class prediction the reference's evaluation
+                               * loop takes from the logits on the host (train_scannet_semseg.py:204-205).  <= 256 channels. */
 int pn2_sa_mlp_max_bf16(int b, int n, int m, int k, int d, const float *xyz, const float *feat, const float *new_xyz,
                         const int32_t *idx, const pn2_mlp *mlp, const void *packed, float *out, int out_stride,
                         int out_offset, int flags, void *stream);

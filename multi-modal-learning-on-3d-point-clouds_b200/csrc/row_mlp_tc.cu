@@ -69,6 +69,7 @@ struct TcParams {
     int in_bf16;       // block0 features (SA feat / FP feat2) are stored as bf16
     int skip_bf16;     // FP skip features (feat1) are stored as bf16
     int out_bf16;      // write the result as bf16 (activations that only feed another tensor-core block)
+    int out_argmax;    // FP: write one uint8 per row, the index of the largest output channel (first on ties)
     int kchunk;        // k-blocks of the first layer's operand produced per pass (see gather_chunk_tc)
     int pool_t;        // SA: the last layer is computed TRANSPOSED (channels on TMEM lanes, samples on columns; see kernel)
     int thin;          // the first layer's last k-block holds only 16 columns and lives in its own 4 KB region (see Plan)
@@ -887,7 +888,9 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                             }
                         }
                     }
-                } else
+                } else {
+                float am_best = 0.f;  // running arg-max over the channels of this thread's row (PN2_FLAG_OUT_ARGMAX)
+                int am_idx = -1;
                 for (int c0 = 0; c0 < npad; c0 += 32) {
                     uint32_t acc[32];
                     tmem_ld32(lane_base + (uint32_t)c0, acc);
@@ -932,7 +935,18 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                     {
                         // FP: rows are independent
                         const int esz = p.out_bf16 ? 2 : 4;
-                        if (((cout * esz) & 15) == 0) {
+                        if (p.out_argmax) {
+                            // class prediction: the thread holds every logit of its row, so the arg-max costs two
+                            // instructions per channel and the row leaves as one byte (np.argmax order: first maximum)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (c0 + j < cout && (am_idx < 0 || v[j] > am_best)) {
+                                    am_best = v[j];
+                                    am_idx = c0 + j;
+                                }
+                            }
+                            if (c0 + 32 >= npad && srow_ok) reinterpret_cast<unsigned char *>(p.out)[out_row] = (unsigned char)am_idx;
+                        } else if (((cout * esz) & 15) == 0) {
                             // rows start 16-byte aligned: the thread's 32 consecutive columns go out as 128-bit stores
                             if (srow_ok) {
                                 if (p.out_bf16) {
@@ -974,6 +988,7 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
                             __syncwarp();
                         }
                     }
+                }
                 }
                 if (!last) {
                     tc_fence_before();    // TMEM reads done before the next layer's MMAs overwrite the accumulators
@@ -1288,6 +1303,9 @@ extern "C" int pn2_fp_mlp_bf16(int b, int n, int m, int d1, int d2, const float 
     p.in_bf16 = (flags & PN2_FLAG_IN_BF16) != 0;
     p.skip_bf16 = (flags & PN2_FLAG_SKIP_BF16) != 0;
     p.out_bf16 = (flags & PN2_FLAG_OUT_BF16) != 0;
+    p.out_argmax = (flags & PN2_FLAG_OUT_ARGMAX) != 0;
+    if (p.out_argmax)
+        PN2_REQUIRE(!p.out_bf16 && mlp->cout[mlp->num_layers - 1] <= 256, "fp_mlp_bf16: arg-max output needs at most 256 channels and excludes PN2_FLAG_OUT_BF16");
     if (p.in_bf16) PN2_REQUIRE(d2 % 8 == 0 && p.feat_aligned, "fp_mlp_bf16: bf16 features need d2 %% 8 == 0 and 16-byte alignment");
     if (p.skip_bf16)
         PN2_REQUIRE(p.in_bf16 && d1 % 8 == 0 && (((uintptr_t)feat1) & 15) == 0, "fp_mlp_bf16: bf16 skip features need bf16 coarse features, d1 %% 8 == 0 and 16-byte alignment");

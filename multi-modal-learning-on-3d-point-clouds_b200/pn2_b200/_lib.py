@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(CSRC, "libpn2_b200.so")
 PN2_MAX_LAYERS = 6
 REDUCE_MAX, REDUCE_FIRST = 0, 1
 ORDER_XYZ_FIRST, ORDER_FEAT_FIRST = 0, 1
-FLAG_IN_BF16, FLAG_SKIP_BF16, FLAG_OUT_BF16 = 1, 2, 4
+FLAG_IN_BF16, FLAG_SKIP_BF16, FLAG_OUT_BF16, FLAG_OUT_ARGMAX = 1, 2, 4, 8
 
 _c_int, _c_float, _vp = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
 

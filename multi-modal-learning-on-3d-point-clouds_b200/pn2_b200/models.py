@@ -51,8 +51,9 @@ class PointNet2SemSeg(nn.Module):
         relus = [True] * len(self.fp1.mlp_convs) + [True, False]
         return self._head_fold.get(convs, bns, relus)
 
-    def forward_fused(self, xyz, points):
-        """xyz (B, 3, N), points (B, D, N) -> (B, N, num_classes), contiguous.
+    def forward_fused(self, xyz, points, labels=False):
+        """xyz (B, 3, N), points (B, D, N) -> (B, N, num_classes), contiguous; labels=True -> (B, N) uint8 class
+        predictions (arg-max fused into the head, see predict()).
 
         The geometry of every level depends on coordinates only, so it runs ahead of the feature path on two side
         streams: FPS chain + 3-NN on one, ball queries on another; the fused SA/FP kernels follow on the caller's
@@ -149,16 +150,33 @@ class PointNet2SemSeg(nn.Module):
         l1 = self.fp2.forward_cl(levels[1], levels[2], l1, l2, nn_weights=nnw[2], out_dtype=act)
         main.wait_event(nn_done[3])
         order0 = grids[0].order if 0 in grids else None
+        head_dtype = torch.uint8 if labels else torch.float32
         if self.timers is None:
             return self.fp1.forward_cl(xyz_cl, levels[1], feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw[3],
-                                       row_order=order0)
+                                       row_order=order0, out_dtype=head_dtype)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         out = self.fp1.forward_cl(xyz_cl, levels[1], feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw[3],
-                                  row_order=order0)
+                                  row_order=order0, out_dtype=head_dtype)
         t1.record()
         self.timers.setdefault("fp1_head", []).append((t0, t1))
         return out
+
+    def can_fuse_labels(self):
+        return get_mlp_precision() == "bf16" and self._fp1_with_head().bf16_ok() and self.conv2.out_channels <= 256
+
+    def predict(self, xyz, points):
+        """Per-point class predictions (B, N) uint8 = arg-max over the logits, what the reference's evaluation loop
+        computes on the host from `pred.cpu().numpy()` (train_scannet_semseg.py:204-205).  In inference on the
+        tensor-core path the arg-max is fused into the head kernel: the logits are never written and the result to
+        read back is 1 byte per point instead of 84."""
+        if _fusable(self, xyz, points) and self.can_fuse_labels():
+            return self.forward_fused(xyz, points, labels=True)
+        logits = self.forward(xyz, points)
+        # first maximum, as numpy.argmax (torch.argmax does not promise an order among ties)
+        classes = torch.arange(logits.shape[-1], device=logits.device)
+        first = torch.where(logits == logits.max(dim=-1, keepdim=True).values, classes, logits.shape[-1]).min(dim=-1).values
+        return first.to(torch.uint8)
 
     def forward(self, xyz, points):
         if _fusable(self, xyz, points):
@@ -338,22 +356,23 @@ class GraphedForward:
     one graph launch (no per-kernel Python / driver overhead).  `run(x)` copies x (device or pinned host, (B, C, N))
     into the static input and returns the static output tensor (valid until the next run)."""
 
-    def __init__(self, model, example_xyz, example_points, warmup=3):
+    def __init__(self, model, example_xyz, example_points, warmup=3, labels=False):
         self.model = model
         self.xyz = example_xyz.clone()
         self.points = example_points.clone()
+        kw = {"labels": True} if labels else {}  # labels: (B, N) uint8 predictions instead of logits (PointNet2SemSeg.predict)
         side = torch.cuda.Stream(example_xyz.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(warmup):
-                model.forward_fused(self.xyz, self.points)
+                model.forward_fused(self.xyz, self.points, **kw)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from . import _lib
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.out = model.forward_fused(self.xyz, self.points)
+            self.out = model.forward_fused(self.xyz, self.points, **kw)
         self.kernels_per_replay = _lib.launch_count() - n0  # our kernels captured in the graph
 
     def run(self, xyz, points):
@@ -368,7 +387,7 @@ class PipelinedForward:
     on SMs that the latency-bound sampling of a single batch leaves idle).  submit() returns the static output of the
     slot it used together with an event; the output stays valid until that slot is submitted again."""
 
-    def __init__(self, model, example_xyz, example_points, depth=2):
+    def __init__(self, model, example_xyz, example_points, depth=2, labels=False):
         self.depth = depth
         self.streams = [torch.cuda.Stream(example_xyz.device) for _ in range(depth)]
         self.slots = []
@@ -377,7 +396,7 @@ class PipelinedForward:
             for st in self.streams:
                 st.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(st):
-                    self.slots.append(GraphedForward(model, example_xyz, example_points))
+                    self.slots.append(GraphedForward(model, example_xyz, example_points, labels=labels))
                 torch.cuda.current_stream().wait_stream(st)
         self.kernels_per_replay = self.slots[0].kernels_per_replay
         self.i = 0

@@ -268,6 +268,8 @@ def _bf16_flags(block0, skip, out):
         f |= _lib.FLAG_SKIP_BF16
     if out.dtype == torch.bfloat16:
         f |= _lib.FLAG_OUT_BF16
+    if out.dtype == torch.uint8:
+        f |= _lib.FLAG_OUT_ARGMAX
     return f
 
 
@@ -307,9 +309,16 @@ def three_nn_weights_cl(xyz1_cl, xyz2_cl):
 
 
 def fp_mlp_cl(feat1_cl, feat2_cl, idx, weight, mlp, n, row_order=None, out_dtype=torch.float32):
+    """Fused 3-NN interpolation + skip concatenation + MLP.  -> (B, n, cout); with out_dtype=torch.uint8 -> (B, n)
+    class predictions: arg-max over the output channels, fused into the last layer (tensor-core path only)."""
     B, m, D2 = feat2_cl.shape
     D1 = 0 if feat1_cl is None else feat1_cl.shape[2]
-    out = torch.empty((B, n, mlp.cout), dtype=out_dtype, device=feat2_cl.device)
+    if out_dtype == torch.uint8:
+        if not (_PRECISION == "bf16" and mlp.bf16_ok()) or mlp.cout > 256:
+            raise _lib.Pn2Error("fused arg-max output needs the tensor-core path and at most 256 output channels")
+        out = torch.empty((B, n), dtype=torch.uint8, device=feat2_cl.device)
+    else:
+        out = torch.empty((B, n, mlp.cout), dtype=out_dtype, device=feat2_cl.device)
     with torch.cuda.device(feat2_cl.device):
         if _PRECISION == "bf16" and mlp.bf16_ok():
             _lib.call("pn2_fp_mlp_bf16", B, n, m, D1, D2, ptr(feat1_cl), ptr(feat2_cl), ptr(idx), ptr(weight), mlp.desc,

@@ -156,6 +156,56 @@ def test_semseg_forward_matches_reference_composition(cuda, precision, B, N):
     assert_close(got2, want2, tol(precision, 2e-5))
 
 
+def test_predict_labels_equal_argmax_of_logits(cuda, precision):
+    """predict() = np.argmax over the logits (train_scannet_semseg.py:204-205).  On the tensor-core path the arg-max is
+    fused into the head kernel (PN2_FLAG_OUT_ARGMAX): same logits, so the labels agree exactly, ties -> first class."""
+    torch.manual_seed(1)
+    model = PointNet2SemSeg(21).eval()
+    randomize_bn(model, 5)
+    with torch.no_grad():
+        # classes 2 and 7 share weights and bias: their logits tie bit for bit, the prediction must never be 7
+        model.conv2.weight[7] = model.conv2.weight[2]
+        model.conv2.bias[7] = model.conv2.bias[2]
+    pts = torch.from_numpy(scenes.scannet_batch(3, 2, 4096)).permute(0, 2, 1).contiguous()
+    g = model.to(cuda)
+    xyz, rgb = pts[:, :3, :].to(cuda), pts[:, 3:, :].to(cuda)
+    with torch.no_grad():
+        logits = g(xyz, rgb)
+        labels = g.predict(xyz, rgb)
+    assert labels.shape == (2, 4096) and labels.dtype == torch.uint8
+    np.testing.assert_array_equal(labels.cpu().numpy(), np.argmax(logits.cpu().numpy(), axis=2))
+    assert not (labels == 7).any()
+    if precision == "bf16":
+        assert g.can_fuse_labels()
+
+
+@pytest.mark.parametrize("N,S,D1,D2,classes", [(3000, 300, 6, 128, 21), (1000, 64, 0, 64, 40), (777, 1, 8, 32, 200)])
+def test_fused_argmax_output_of_an_fp_block(cuda, N, S, D1, D2, classes):
+    """PN2_FLAG_OUT_ARGMAX on random features (predictions vary from point to point): uint8 labels equal the first
+    maximum of the block's own fp32 output; the ReLU outputs tie at 0 often, which exercises the first-index rule."""
+    from pn2_b200 import pointnet_util
+    from pn2_b200.pointnet_util import to_channel_last
+    prev = pointnet_util.set_mlp_precision("bf16")
+    try:
+        torch.manual_seed(N)
+        mod = PointNetFeaturePropagation(D1 + D2, [64, classes]).eval()
+        randomize_bn(mod, S)
+        mod = mod.to(cuda)
+        xyz1, p1 = scene_batch(2, N, 7 + N, D1)
+        xyz2 = xyz1[:, :, :S].contiguous()
+        p2 = torch.randn(2, D2, S)
+        a = [to_channel_last(t.to(cuda)) if t is not None else None for t in (xyz1, xyz2, p1, p2)]
+        with torch.no_grad():
+            dense = mod.forward_cl(*a)
+            labels = mod.forward_cl(*a, out_dtype=torch.uint8)
+        assert labels.shape == (2, N) and labels.dtype == torch.uint8
+        want = np.argmax(dense.cpu().numpy(), axis=2)
+        np.testing.assert_array_equal(labels.cpu().numpy(), want)
+        assert len(np.unique(want)) > 3
+    finally:
+        pointnet_util.set_mlp_precision(prev)
+
+
 def test_backbone_forward_nuscenes_shape(cuda, precision):
     torch.manual_seed(2)
     model = PointNet2Backbone().eval()
