@@ -195,12 +195,13 @@ int pn2_three_nn_grid(int b, int n, int m, const float *unknown, const float *kn
                       int32_t *idx, float *weight, void *stream);
 
 /* ---- tuning ---- */
-/* Kernel policy of furthest point sampling for 1024 < n <= 8192 points per cloud.  Process-wide; read when a launch is
+/* Kernel policy of furthest point sampling for 4096 < n <= 8192 points per cloud.  Process-wide; read when a launch is
  * issued (or captured into a CUDA graph).  The sampled indices are identical under every policy.
- *   PN2_FPS_AUTO     a 4-CTA cluster per cloud while 4*b CTAs fit the GPU (lowest latency of a single batch), else ONE_CTA;
- *   PN2_FPS_ONE_CTA  one 1024-thread CTA per cloud: ~30 % slower alone, but it occupies b SMs instead of 4*b, which is
- *                    what counts when several batches are in flight (measured: 44.2 k -> 52.2 k scenes/s, profiles/README.md);
- *   PN2_FPS_CLUSTER  always the cluster kernel.
+ *   PN2_FPS_AUTO     a 4-CTA cluster per cloud while 4*b CTAs fit the GPU (lowest latency of a single batch: 0.45 ms for
+ *                    8192 -> 1024), else ONE_CTA;
+ *   PN2_FPS_ONE_CTA  one 256-thread CTA per cloud (0.54 ms): it occupies b SMs instead of 4*b, which is what counts when
+ *                    several batches are in flight (measured: 44.2 k -> 52.2 k scenes/s at the time, profiles/README.md);
+ *   PN2_FPS_CLUSTER  always the cluster kernel (also for smaller clouds).
  * Returns the previous policy, or -1 for an unknown value. */
 enum { PN2_FPS_AUTO = 0, PN2_FPS_ONE_CTA = 1, PN2_FPS_CLUSTER = 2 };
 int pn2_set_fps_policy(int policy);

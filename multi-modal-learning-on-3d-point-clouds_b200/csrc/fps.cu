@@ -11,10 +11,11 @@
 // memory at all.  The arg-max is a single 64-bit key  (float bits of temp | ~tie key)  reduced with
 // two CREDUX.MAX per warp, one shared-memory hop and ONE block barrier per round (slots are
 // double-buffered by round parity); the reference spends 10 barriers and 20*N bytes of L2 traffic
-// per round.  With few clouds in flight (4*B <= #SMs) or clouds larger than one CTA's registers
-// (8192 < N <= 49152) each cloud is split over a 4-CTA thread-block cluster whose warps exchange
-// their winners through distributed shared memory with st.async + mbarrier complete_tx
-// (fps_cluster_kernel): 0.44 us per round instead of 0.61 at N = 8192.
+// per round.  Clouds of 1024 < N <= 8192 points run on 256 threads with 8-32 points each (fps_few_kernel:
+// the per-warp cost of a round is paid by 8 warps, 0.53 us per round at N = 8192).  With few clouds in
+// flight (4*B <= #SMs) or clouds larger than one CTA's registers (8192 < N <= 49152) each cloud is split
+// over a 4-CTA thread-block cluster whose warps exchange their winners through distributed shared memory
+// with st.async + mbarrier complete_tx (fps_cluster_kernel): 0.44 us per round at N = 8192.
 #include "common.cuh"
 
 namespace pn2 {
@@ -135,6 +136,95 @@ fps_reg_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__restr
             idx[j] = k;
             if (new_xyz) {
                 new_xyz[3 * j] = x1; new_xyz[3 * j + 1] = y1; new_xyz[3 * j + 2] = z1;
+            }
+        }
+    }
+}
+
+// One CTA per cloud with FEWER THREADS than the reference block size (bs = 1024): T = 1024 / SUB threads own
+// P = SUB * Q points each (Q = capacity / 1024).  The fixed per-warp cost of a round (two CREDUX pairs, slot exchange,
+// barrier, decode) is paid by T/32 warps instead of 32, so a round issues ~30 % fewer instructions and the CTA holds
+// fewer registers -- the variant for several batches in flight, where SM time, not latency, is what FPS costs.
+// Thread t owns k = t + T*(SUB*q + s), q < Q, s < SUB.  Its tie key is (bitrev10(k mod 1024) << QB) | q with
+// bitrev10(t + T*s) = bitrev10(t) + bitrev_{log2 SUB}(s), so the in-thread tie order is "s in bit-reversed order, then
+// q ascending": the points are held in that order (slot j = bitrev(s)*Q + q) and the first strict maximum in ascending
+// j is the reference's winner.
+template <int T, int Q>
+__global__ void __launch_bounds__(T, 1)
+fps_few_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__restrict__ idx_all,
+               float *__restrict__ new_xyz_all) {
+    constexpr int SUB = 1024 / T, LS = Log2<SUB>::value, P = SUB * Q, NW = T / 32;
+    extern __shared__ float smem[];
+    float *sx = smem, *sy = smem + 1024 * Q, *sz = smem + 2 * 1024 * Q;
+    __shared__ unsigned long long slot[2][32];
+
+    const float *xyz = xyz_all + (size_t)blockIdx.x * n * 3;
+    int32_t *idx = idx_all + (size_t)blockIdx.x * m;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+    float x[P], y[P], z[P], tm[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int sr = j / Q, q = j % Q;                               // sr = bit-reversed s
+        const int sb = (int)(__brev((unsigned)sr) >> (32 - (LS > 0 ? LS : 1))) & (SUB - 1);
+        const int k = t + T * (SUB * q + sb);
+        const bool ok = k < n;
+        x[j] = ok ? xyz[3 * k + 0] : 0.f;
+        y[j] = ok ? xyz[3 * k + 1] : 0.f;
+        z[j] = ok ? xyz[3 * k + 2] : 0.f;
+        tm[j] = ok ? 1e10f : 0.f;  // padding never wins: see fps_reg_kernel
+        sx[k] = x[j];
+        sy[k] = y[j];
+        sz[k] = z[j];
+    }
+    const uint32_t rank0 = __brev((uint32_t)t) >> 22;  // bitrev10(t); t < T so its low log2(SUB) bits are free
+    const uint32_t inv_base = 0xFFFFFFFFu - (rank0 << QB);
+    float *new_xyz = new_xyz_all ? new_xyz_all + (size_t)blockIdx.x * m * 3 : nullptr;
+    if (t == 0) idx[0] = 0;
+    __syncthreads();
+    float x1 = sx[0], y1 = sy[0], z1 = sz[0];
+    if (t == 0 && new_xyz) {
+        new_xyz[0] = x1; new_xyz[1] = y1; new_xyz[2] = z1;
+    }
+
+    for (int r = 1; r < m; ++r) {
+        update_min<P>(x, y, z, tm, x1, y1, z1);
+        // pairwise (log-depth) arg-max; on ties the lower slot wins
+        float bv[P];
+        int bi[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            bv[j] = tm[j];
+            bi[j] = j;
+        }
+#pragma unroll
+        for (int s2 = 1; s2 < P; s2 *= 2) {
+#pragma unroll
+            for (int j = 0; j + s2 < P; j += 2 * s2) {
+                const bool take = bv[j + s2] > bv[j];
+                bv[j] = take ? bv[j + s2] : bv[j];
+                bi[j] = take ? bi[j + s2] : bi[j];
+            }
+        }
+        const int bj = bi[0];
+        uint32_t hi = __float_as_uint(bv[0]);
+        uint32_t lo = inv_base - ((((uint32_t)bj / Q) << QB) | ((uint32_t)bj % Q));
+        warp_argmax(hi, lo);
+        if (lane == 0) slot[r & 1][warp] = ((unsigned long long)hi << 32) | lo;
+        __syncthreads();
+        const unsigned long long v = lane < NW ? slot[r & 1][lane] : 0ull;
+        hi = (uint32_t)(v >> 32);
+        lo = (uint32_t)v;
+        warp_argmax(hi, lo);
+        const uint32_t tie = 0xFFFFFFFFu - lo;
+        const int k = (int)(tie & QMASK) * 1024 + (int)(__brev(tie >> QB) >> 22);
+        x1 = sx[k];
+        y1 = sy[k];
+        z1 = sz[k];
+        if (t == 0) {
+            idx[r] = k;
+            if (new_xyz) {
+                new_xyz[3 * r] = x1; new_xyz[3 * r + 1] = y1; new_xyz[3 * r + 2] = z1;
             }
         }
     }
@@ -413,6 +503,15 @@ int launch_reg(int b, int n, int m, const float *xyz, int32_t *idx, float *new_x
     return PN2_OK;
 }
 
+template <int T, int Q>
+int launch_few(int b, int n, int m, const float *xyz, int32_t *idx, float *new_xyz, cudaStream_t s) {
+    const size_t smem = (size_t)3 * 1024 * Q * sizeof(float);
+    PN2_CUDA(cudaFuncSetAttribute(fps_few_kernel<T, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fps_few_kernel<T, Q><<<b, T, smem, s>>>(n, m, xyz, idx, new_xyz);
+    PN2_LAUNCH_OK("fps_few_kernel");
+    return PN2_OK;
+}
+
 template <int P>
 int launch_cluster(int b, int n, int m, const float *xyz, int32_t *idx, float *new_xyz, cudaStream_t s) {
     constexpr int T = 256, C = 4;
@@ -444,7 +543,7 @@ int launch_reg_small(int b, int n, int m, const float *xyz, int32_t *idx, float 
 }  // namespace
 }  // namespace pn2
 
-// 0 = automatic, 1 = always one CTA per cloud, 2 = always the cluster kernel (tests / benchmarking)
+// 0 = automatic, 1 = one CTA per cloud, 2 = cluster kernel; 3 / 4 = developer variants (see fps_impl)
 static int g_fps_mode = 0;
 extern "C" void pn2_debug_set_fps_mode(int mode) { g_fps_mode = mode; }
 extern "C" int pn2_set_fps_policy(int policy) {
@@ -480,10 +579,15 @@ int fps_impl(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, f
         default: break;
     }
     if (n <= 1024) return launch_reg<1024, 1>(b, n, m, xyz, idx, new_xyz, s);
-    // Few clouds: split each over a 4-CTA cluster (4x less issue per round, DSMEM exchange).  Many clouds: one CTA
-    // per cloud already fills the SMs and avoids the exchange latency.
-    const bool use_cluster = fps_force_mode() == 2 || (fps_force_mode() == 0 && (long long)b * 4 <= sm_count());
-    if (use_cluster || n > 8192) {
+    // 1024 < n <= 8192.  One CTA per cloud = the 256-thread kernel (fps_few_kernel): 0.12 / 0.17 / 0.54 ms for
+    // 2048->512 / 4096->512 / 8192->1024, faster than both alternatives up to 4096 points.  At 4096 < n <= 8192 the
+    // 4-CTA cluster is 17 % faster (0.45 ms) but occupies four SMs per cloud: chosen automatically only while the
+    // clouds alone cannot fill the GPU; PN2_FPS_ONE_CTA keeps one SM per cloud (several batches in flight).
+    // Developer modes: 3 = 512-thread variant, 4 = the 1024-thread kernel (one point rank per thread).
+    const int mode = fps_force_mode();
+    const bool cluster_ok = (long long)b * 4 <= sm_count();
+    const bool use_cluster = n > 8192 || mode == PN2_FPS_CLUSTER || (mode == PN2_FPS_AUTO && n > 4096 && cluster_ok);
+    if (use_cluster) {
         if (n <= 2048) return launch_cluster<2>(b, n, m, xyz, idx, new_xyz, s);
         if (n <= 4096) return launch_cluster<4>(b, n, m, xyz, idx, new_xyz, s);
         if (n <= 8192) return launch_cluster<8>(b, n, m, xyz, idx, new_xyz, s);
@@ -491,10 +595,17 @@ int fps_impl(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, f
         if (n <= 24576) return launch_cluster<24>(b, n, m, xyz, idx, new_xyz, s);
         if (n <= 32768) return launch_cluster<32>(b, n, m, xyz, idx, new_xyz, s);
         if (n <= 49152) return launch_cluster<48>(b, n, m, xyz, idx, new_xyz, s);  // e.g. a raw 35k-point lidar sweep
+    } else if (mode == 4) {
+        if (n <= 2048) return launch_reg<1024, 2>(b, n, m, xyz, idx, new_xyz, s);
+        if (n <= 4096) return launch_reg<1024, 4>(b, n, m, xyz, idx, new_xyz, s);
+        return launch_reg<1024, 8>(b, n, m, xyz, idx, new_xyz, s);
+    } else if (mode == 3 && n > 4096) {
+        return launch_few<512, 8>(b, n, m, xyz, idx, new_xyz, s);
+    } else {
+        if (n <= 2048) return launch_few<256, 2>(b, n, m, xyz, idx, new_xyz, s);
+        if (n <= 4096) return launch_few<256, 4>(b, n, m, xyz, idx, new_xyz, s);
+        return launch_few<256, 8>(b, n, m, xyz, idx, new_xyz, s);
     }
-    if (n <= 2048) return launch_reg<1024, 2>(b, n, m, xyz, idx, new_xyz, s);
-    if (n <= 4096) return launch_reg<1024, 4>(b, n, m, xyz, idx, new_xyz, s);
-    if (n <= 8192) return launch_reg<1024, 8>(b, n, m, xyz, idx, new_xyz, s);
     if (!temp)
         return set_error(PN2_ERR_INVALID_ARGUMENT, "fps: n=%d exceeds the on-chip kernels; pass the (B,N) temp scratch", n);
     PN2_REQUIRE(n < (long long)(QMASK) * 1024ll, "fps: n too large for the tie key");

@@ -42,9 +42,12 @@ def main():
         x = xyz[:, :n].contiguous()
         print("fps %d->%d: med %.3f ms min %.3f" % ((n, m) + timeit(lambda: fps_gather_cl(x, m))))
     from pn2_b200 import _lib as L
-    for mode in (1, 2):
+    for mode in (1, 2, 3, 4):
         L.load().pn2_debug_set_fps_mode(mode)
         print("fps 8192->1024 mode %d: med %.3f ms min %.3f" % ((mode,) + timeit(lambda: fps_gather_cl(xyz, 1024))))
+        x4, x2 = xyz[:, :4096].contiguous(), xyz[:, :2048].contiguous()
+        print("fps 4096->512 mode %d: med %.3f ms min %.3f" % ((mode,) + timeit(lambda: fps_gather_cl(x4, 512))))
+        print("fps 2048->512 mode %d: med %.3f ms min %.3f" % ((mode,) + timeit(lambda: fps_gather_cl(x2, 512))))
     L.load().pn2_debug_set_fps_mode(0)
     idx, new_xyz = fps_gather_cl(xyz, 1024)
     print("ball_query r=.1: med %.3f min %.3f" % timeit(lambda: pu.ball_query(0.1, 32, xyz, new_xyz)))

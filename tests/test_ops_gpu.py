@@ -57,9 +57,25 @@ def test_fps_bit_exact(cuda, kind, B, N, M):
                                         ("uniform", 1, 12000, 150), ("dup", 2, 2048, 2100), ("uniform", 1, 20000, 120),
                                         ("dup", 1, 30000, 100), ("uniform", 1, 35000, 200), ("uniform", 1, 50000, 40)])
 def test_fps_single_cta_and_cluster_kernels_agree_with_reference(cuda, mode, kind, B, N, M):
-    """Both on-chip FPS kernels (one CTA per cloud / four-CTA cluster with DSMEM exchange) are bit-exact."""
+    """Both FPS policies (one 256-thread CTA per cloud / four-CTA cluster with DSMEM exchange) are bit-exact."""
     from pn2_b200 import _lib
     xyz = clouds(kind, B, N, 3 * N + M)
+    _lib.load().pn2_debug_set_fps_mode(mode)
+    try:
+        got = pu.furthest_point_sample(dev(xyz, cuda), M).cpu().numpy()
+    finally:
+        _lib.load().pn2_debug_set_fps_mode(0)
+    np.testing.assert_array_equal(got, orc.furthest_point_sample(xyz, M))
+
+
+@pytest.mark.parametrize("mode", [3, 4])
+@pytest.mark.parametrize("kind,B,N,M", [("scannet", 3, 8192, 1024), ("dup", 2, 8192, 700), ("lattice", 2, 8000, 300),
+                                        ("dup", 2, 5000, 5100), ("uniform", 2, 4097, 64), ("dup", 1, 6001, 300)])
+def test_fps_few_warp_kernels_agree_with_reference(cuda, mode, kind, B, N, M):
+    """Developer variants (512-thread kernel / the 1024-thread kernel with one tie rank per thread) are bit-exact too;
+    duplicated points and lattices make exact distance ties frequent, so the tie order is exercised."""
+    from pn2_b200 import _lib
+    xyz = clouds(kind, B, N, 5 * N + M)
     _lib.load().pn2_debug_set_fps_mode(mode)
     try:
         got = pu.furthest_point_sample(dev(xyz, cuda), M).cpu().numpy()
