@@ -194,6 +194,21 @@ int pn2_three_nn_grid(int b, int n, int m, const float *unknown, const float *kn
                       const int32_t *cell_start, const float *meta, const int32_t *query_order, float *dist2,
                       int32_t *idx, float *weight, void *stream);
 
+/* ---- deterministic backwards ----
+ * The three reference backwards above accumulate with atomicAdd, so the fp32 summation order changes from run to run.
+ * These two calls give the same gradients with a FIXED order (ascending source position) and no atomics.
+ * pn2_inverse_index: idx (b,j) int32 with values in [0,n) -> seg_start (b*n + 1) int32 and pos (b,j) int32: the source
+ * positions p of cloud `bb` whose idx == k are pos[bb*j + seg_start[bb*n + k] - bb*j ...]: precisely, slots
+ * seg_start[bb*n + k] .. seg_start[bb*n + k + 1] of the flattened `pos` hold them in ascending order.  One stable
+ * device radix sort; temporary storage comes from the stream-ordered allocator.
+ * pn2_scatter_rows_det: grad_points (b,c,n) += sum over those p of weight[bb,p] * grad_out[bb,c,p / div]
+ *   gather_points_grad : j = npoints,         div = 1, weight = NULL, grad_out (b,c,npoints)
+ *   group_points_grad  : j = npoints*nsample, div = 1, weight = NULL, grad_out (b,c,npoints,nsample)
+ *   three_interpolate_grad (n there = m here): j = 3*n_fine, div = 3, weight (b,n_fine,3), grad_out (b,c,n_fine). */
+int pn2_inverse_index(int b, int n, long long j, const int32_t *idx, int32_t *seg_start, int32_t *pos, void *stream);
+int pn2_scatter_rows_det(int b, int c, int n, long long j, int div, const float *grad_out, const int32_t *seg_start,
+                         const int32_t *pos, const float *weight, float *grad_points, void *stream);
+
 /* ---- tuning ---- */
 /* Kernel policy of furthest point sampling for 4096 < n <= 8192 points per cloud.  Process-wide; read when a launch is
  * issued (or captured into a CUDA graph).  The sampled indices are identical under every policy.

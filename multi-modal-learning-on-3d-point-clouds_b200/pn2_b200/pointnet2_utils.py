@@ -20,6 +20,39 @@ from . import pointnet2_cuda as _ext
 from ._lib import Pn2Error, require_cuda
 
 
+_DETERMINISTIC = None  # None: follow torch.are_deterministic_algorithms_enabled()
+
+
+def set_deterministic(flag):
+    """True: the gather / grouping / three_interpolate backwards sum every gradient element in a fixed order (inverse
+    index + segmented reduction, pn2_scatter_rows_det) instead of the reference's atomicAdd scatter, so training runs are
+    bit-reproducible.  None (default): follow torch.use_deterministic_algorithms().  Returns the previous setting."""
+    global _DETERMINISTIC
+    prev, _DETERMINISTIC = _DETERMINISTIC, flag
+    return prev
+
+
+def _deterministic():
+    return torch.are_deterministic_algorithms_enabled() if _DETERMINISTIC is None else bool(_DETERMINISTIC)
+
+
+def _scatter_det(grad_out, idx, n, weight=None):
+    """grad_out (B, C, ...) contiguous, idx (B, ...) int32 with values in [0, n) -> (B, C, n); see include/pn2_abi.h"""
+    from . import _lib
+    B, C = grad_out.shape[0], grad_out.shape[1]
+    J = idx[0].numel()
+    dev = grad_out.device
+    seg = torch.empty((B * n + 1,), dtype=torch.int32, device=dev)
+    pos = torch.empty((B, max(J, 1)), dtype=torch.int32, device=dev)
+    grad = torch.zeros((B, C, n), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        _lib.call("pn2_inverse_index", B, n, J, _lib.ptr(idx), _lib.ptr(seg), _lib.ptr(pos), st)
+        _lib.call("pn2_scatter_rows_det", B, C, n, J, 3 if weight is not None else 1, _lib.ptr(grad_out), _lib.ptr(seg), _lib.ptr(pos),
+                  _lib.ptr(weight), _lib.ptr(grad), st)
+    return grad
+
+
 def _grid_pays_off(n_points, n_queries):
     """Cell-list search (one sort per cloud) instead of brute force: worthwhile for mid-sized clouds with many queries."""
     from .pointnet_util import grid_max_points
@@ -75,6 +108,8 @@ class GatherOperation(Function):
         (idx,) = ctx.saved_tensors
         C, N = ctx.dims
         B, npoint = idx.size()
+        if _deterministic():
+            return _scatter_det(grad_out.contiguous(), idx, N), None
         grad = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
         _ext.gather_points_grad_wrapper(B, C, N, npoint, grad_out.contiguous(), idx, grad)
         return grad, None
@@ -129,6 +164,8 @@ class ThreeInterpolate(Function):
     def backward(ctx, grad_out):
         idx, weight = ctx.saved_tensors
         B, C, n = grad_out.size()
+        if _deterministic():
+            return _scatter_det(grad_out.contiguous(), idx, ctx.m, weight=weight), None, None
         grad = torch.zeros((B, C, ctx.m), dtype=torch.float32, device=grad_out.device)
         _ext.three_interpolate_grad_wrapper(B, C, n, ctx.m, grad_out.contiguous(), idx, weight, grad)
         return grad, None, None
@@ -156,6 +193,8 @@ class GroupingOperation(Function):
     def backward(ctx, grad_out):
         (idx,) = ctx.saved_tensors
         B, C, npoint, nsample = grad_out.size()
+        if _deterministic():
+            return _scatter_det(grad_out.contiguous(), idx, ctx.N), None
         grad = torch.zeros((B, C, ctx.N), dtype=torch.float32, device=grad_out.device)
         _ext.group_points_grad_wrapper(B, C, ctx.N, npoint, nsample, grad_out.contiguous(), idx, grad)
         return grad, None
