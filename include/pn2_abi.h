@@ -209,6 +209,22 @@ int pn2_inverse_index(int b, int n, long long j, const int32_t *idx, int32_t *se
 int pn2_scatter_rows_det(int b, int c, int n, long long j, int div, const float *grad_out, const int32_t *seg_start,
                          const int32_t *pos, const float *weight, float *grad_points, void *stream);
 
+/* ---- evaluation voxelisation ----
+ * utils/pc_util.py:39-51 point_cloud_label_to_surface_voxel_label_fast, as the evaluation loops call it per scene
+ * (train_scannet_semseg.py:226-227): over the points of each cloud with mask != 0 (mask NULL = all points),
+ * vidx = v0 + v1*nvox0 + v2*nvox0*nvox1 with v = ceil((p - min) / res), nvox = ceil((max - min) / res) in fp32, and
+ * numpy.unique(vidx, return_index=True): uvidx (b,n) fp32 ascending, first (b,n) int32 = index of the first point of
+ * each voxel, both padded with -1 after count[b] entries; nvox (b,3) fp32 or NULL. */
+int pn2_voxel_first_index(int b, int n, const float *xyz, const unsigned char *mask, float res, float *uvidx, int32_t *first,
+                          int32_t *count, float *nvox, void *stream);
+
+/* Confusion counters of the evaluation loops (train_scannet_semseg.py:218-223 point-wise, :232-239 voxel-wise), ADDED to
+ * out (3, num_classes) int64: [0][l] #(target == l), [1][l] #(target == l and pred == l), [2][l] #(target == l or pred == l).
+ * Points: select NULL -> every point i < n with mask[b,i] != 0 (mask NULL = all); voxels: select = `first`, count = `count`
+ * of pn2_voxel_first_index.  target (b,n) int64, pred (b,n) uint8 (PN2_FLAG_OUT_ARGMAX output). */
+int pn2_label_counts(int b, int n, int num_classes, const int32_t *select, const int32_t *count, const unsigned char *mask,
+                     const long long *target, const unsigned char *pred, long long *out, void *stream);
+
 /* ---- tuning ---- */
 /* Kernel policy of furthest point sampling for 4096 < n <= 8192 points per cloud.  Process-wide; read when a launch is
  * issued (or captured into a CUDA graph).  The sampled indices are identical under every policy.

@@ -39,3 +39,22 @@ def test_oracle_matches_reference_kernels(gold, name):
     np.testing.assert_allclose(w, gold[name + "/weight"], rtol=1e-6, atol=1e-9)
     interp = orc.three_interpolate(np.ascontiguousarray(feats[:, :, :M]), nn_idx, gold[name + "/weight"])
     np.testing.assert_array_equal(interp, gold[name + "/interp"])
+
+
+# ---- evaluation voxelisation: golden vectors from the reference's own utils/pc_util.py (imported, pure numpy) ----
+PC_NPZ = os.path.join(HERE, "golden", "pc_util_r1.npz")
+spec_pc = importlib.util.spec_from_file_location("make_golden_pc_util", os.path.join(HERE, "golden", "make_golden_pc_util.py"))
+mgp = importlib.util.module_from_spec(spec_pc)
+spec_pc.loader.exec_module(mgp)
+
+
+@pytest.mark.parametrize("name", list(mgp.CASES))
+def test_pc_util_restatement_matches_reference(name):
+    from oracle import pc_util_ref
+    gold = np.load(PC_NPZ)
+    pts, label = mgp.pc_util_inputs(name)
+    uvidx, uvlabel, nvox = pc_util_ref.point_cloud_label_to_surface_voxel_label_fast(pts, label, res=mgp.CASES[name][2])
+    np.testing.assert_array_equal(uvidx, gold[name + "/uvidx"])
+    np.testing.assert_array_equal(uvlabel, gold[name + "/uvlabel"])
+    np.testing.assert_array_equal(nvox, gold[name + "/nvox"])
+    assert uvidx.dtype == np.float32  # the reference computes the voxel index in float32
