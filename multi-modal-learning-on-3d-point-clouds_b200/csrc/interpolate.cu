@@ -150,11 +150,13 @@ three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points, 
 // chunk, and the output once.
 constexpr int TS_THREADS = 256;
 
-template <int CC>
+template <int CC, int PAD>
 __global__ void __launch_bounds__(TS_THREADS, 3)
 three_interpolate_smem_kernel(int c, int m, int n, const float *__restrict__ points, const int32_t *__restrict__ idx,
                               const float *__restrict__ weight, float *__restrict__ out) {
-    constexpr int CCP = CC + 4;  // row stride (floats): 16-byte aligned, rows spread over the banks
+    // row stride (floats): 16-byte aligned; PAD = 4 spreads the rows over the banks, PAD = 0 (CC = 4: 16 bytes per coarse
+    // point) is the dense form that still fits when the coarse set is large (m <= 12800)
+    constexpr int CCP = CC + PAD;
     extern __shared__ __align__(16) float tile[];  // [m][CCP]
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * CC;
@@ -239,19 +241,42 @@ three_interpolate_smem_kernel(int c, int m, int n, const float *__restrict__ poi
     }
 }
 
-template <int CC>
+// One channel per CTA for coarse sets beyond the tiled kernel (12800 < m <= 51200): the channel row is copied to shared
+// memory as it lies (coalesced), each point costs three LDS.32 and one streaming store.
+__global__ void __launch_bounds__(TS_THREADS, 2)
+three_interpolate_row_kernel(int c, int m, int n, const float *__restrict__ points, const int32_t *__restrict__ idx,
+                             const float *__restrict__ weight, float *__restrict__ out) {
+    extern __shared__ __align__(16) float tile[];  // [m]
+    const int b = blockIdx.z, ch = blockIdx.y;
+    const float *f = points + ((size_t)b * c + ch) * m;
+    for (int k = threadIdx.x; k < m; k += TS_THREADS) tile[k] = __ldg(f + k);
+    __syncthreads();
+    float *ob = out + ((size_t)b * c + ch) * n;
+    const int32_t *idb = idx + (size_t)b * n * 3;
+    const float *wb = weight + (size_t)b * n * 3;
+    const int per = (n + gridDim.x - 1) / gridDim.x;
+    const int i0 = blockIdx.x * per, i1 = min(n, i0 + per);
+    for (int i = i0 + threadIdx.x; i < i1; i += TS_THREADS) {
+        const int32_t *id = idb + (size_t)i * 3;
+        const float *w = wb + (size_t)i * 3;
+        const float a0 = tile[id[0]], a1 = tile[id[1]], a2 = tile[id[2]];
+        __stcs(ob + i, __fmaf_rn(w[2], a2, __fmaf_rn(w[0], a0, __fmul_rn(w[1], a1))));
+    }
+}
+
+template <int CC, int PAD = 4>
 int launch_interp_smem(int b, int c, int m, int n, const float *points, const int32_t *idx, const float *weight, float *out,
                        cudaStream_t s) {
     const int chunks = ceil_div(c, CC);
-    const size_t smem = (size_t)m * (CC + 4) * sizeof(float);
+    const size_t smem = (size_t)m * (CC + PAD) * sizeof(float);
     const int per_sm = smem <= 72 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1);
     // split the points of a (cloud, channel chunk) until the grid gives two full waves, but keep at least 2*m points
     // per CTA so the staging stays a small part of its work
     int nsplit = 1;
     while ((long long)nsplit * chunks * b < 2ll * per_sm * sm_count() && n / (nsplit + 1) >= 2 * m) ++nsplit;
-    PN2_CUDA(cudaFuncSetAttribute(three_interpolate_smem_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PN2_CUDA(cudaFuncSetAttribute(three_interpolate_smem_kernel<CC, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nsplit, chunks, b);
-    three_interpolate_smem_kernel<CC><<<grid, TS_THREADS, smem, s>>>(c, m, n, points, idx, weight, out);
+    three_interpolate_smem_kernel<CC, PAD><<<grid, TS_THREADS, smem, s>>>(c, m, n, points, idx, weight, out);
     PN2_LAUNCH_OK("three_interpolate");
     return PN2_OK;
 }
@@ -330,6 +355,18 @@ extern "C" int pn2_three_interpolate(int b, int c, int m, int n, const float *po
         if ((long long)m * 36 <= one && c >= 32) return launch_interp_smem<32>(b, c, m, n, points, idx, weight, out, st);
         if ((long long)m * 20 <= one && c >= 16) return launch_interp_smem<16>(b, c, m, n, points, idx, weight, out, st);
         if ((long long)m * 12 <= one) return launch_interp_smem<8>(b, c, m, n, points, idx, weight, out, st);
+        // large coarse sets: dense 4-channel tiles (m <= 12800), then one channel row per CTA (m <= 51200)
+        if ((long long)m * 4 <= one) return launch_interp_smem<4, 0>(b, c, m, n, points, idx, weight, out, st);
+        if ((long long)m <= one && c <= 65535) {
+            const size_t smem = (size_t)m * sizeof(float);
+            const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+            int nsplit = 1;
+            while ((long long)nsplit * c * b < 2ll * per_sm * sm_count() && n / (nsplit + 1) >= 2 * m) ++nsplit;
+            PN2_CUDA(cudaFuncSetAttribute(three_interpolate_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            three_interpolate_row_kernel<<<dim3(nsplit, c, b), TS_THREADS, smem, st>>>(c, m, n, points, idx, weight, out);
+            PN2_LAUNCH_OK("three_interpolate");
+            return PN2_OK;
+        }
     }
     dim3 grid(ceil_div(n, TI_THREADS), ceil_div(c, TI_CH), b);
     three_interpolate_kernel<<<grid, TI_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, points, idx, weight, out);

@@ -189,7 +189,8 @@ def test_group_bit_exact_and_grad(cuda, B, C, N, P, S):
         np.testing.assert_array_equal(out.detach().cpu().numpy(), ref_cuda.grouping_operation(dev(f, cuda), dev(idx, cuda)).cpu().numpy())
 
 
-@pytest.mark.parametrize("B,C,m,n", [(2, 128, 1024, 8192), (2, 256, 64, 256), (1, 7, 50, 33), (2, 512, 16, 64)])
+@pytest.mark.parametrize("B,C,m,n", [(2, 128, 1024, 8192), (2, 256, 64, 256), (1, 7, 50, 33), (2, 512, 16, 64),
+                                     (1, 70, 8192, 32768), (1, 66, 15000, 30002), (2, 33, 6000, 12001)])  # large coarse sets
 def test_three_interpolate_and_grad(cuda, B, C, m, n):
     rng = np.random.default_rng(C + m + n)
     f = rng.standard_normal((B, C, m)).astype(np.float32)
