@@ -1100,14 +1100,16 @@ Plan make_plan_capped(const pn2_mlp *mlp, int nblk_cap) {
     while (P.tmem_cols < nmax) P.tmem_cols *= 2;
     P.bias_floats = boff;
     P.fits = false;
-    // Ring depth: prefer the deepest ring that still lets TWO CTAs share an SM (their phases overlap); fall back
-    // to whatever fits one CTA.
+    // Residency first (as many CTAs per SM as TMEM and the 4-CTA register budget allow), then the deepest ring that still
+    // fits: a 2-stage ring of 128-row tiles holds one 128x128 layer just like 4 stages of 64-row tiles, with half the
+    // MMAs and barrier hand-offs (fp1+head 133.5 -> 127.9 us).
     const size_t fixed = 1024 + (size_t)P.a_bytes + TC_TAIL_BYTES + (size_t)boff * 4;
     int best = 0;
-    for (int s = MAX_STAGES; s >= 2 && !best; --s)
-        if (2 * (fixed + (size_t)s * P.stage_bytes) <= TC_SMEM_LIMIT + 1024) best = s;
-    for (int s = MAX_STAGES; s >= 2 && !best; --s)
-        if (fixed + (size_t)s * P.stage_bytes <= TC_SMEM_LIMIT) best = s;
+    int cmax = 512 / P.tmem_cols;
+    if (cmax > 4) cmax = 4;
+    for (int c = cmax; c >= 1 && !best; --c)
+        for (int s = MAX_STAGES; s >= 2 && !best; --s)
+            if ((size_t)c * (fixed + (size_t)s * P.stage_bytes + 1024) <= TC_SMEM_LIMIT + 1024) best = s;
     if (best) {
         P.stages = best;
         P.smem_bytes = fixed + (size_t)best * P.stage_bytes;
