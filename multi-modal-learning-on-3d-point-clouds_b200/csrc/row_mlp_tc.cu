@@ -582,9 +582,12 @@ __device__ __forceinline__ void coop_gather_bf16(const TcParams &p, const RowPre
 // Two instantiations: fp32 gathered features (lean: 4 CTAs/SM) and bf16 gathered features (3 CTAs/SM).
 template <bool kInBf16>
 __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel(const __grid_constant__ TcParams p) {
-    extern __shared__ unsigned char smem_raw[];
-    // 1024-byte alignment for the 128B-swizzled operand tiles
-    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the 128B-swizzled operand tiles.  The alignment is REQUESTED on the declaration (no manual
+    // round-up through an integer: that hid the address space from the compiler, which then emitted generic LD.E / ST.E
+    // for every shared-memory access of the gather and the epilogues) and verified once.
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     unsigned char *a_buf = smem;
     unsigned char *w_ring = smem + p.a_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(w_ring + (size_t)p.stages * p.stage_bytes);
