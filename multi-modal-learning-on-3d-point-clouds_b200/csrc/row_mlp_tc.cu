@@ -521,19 +521,20 @@ template <int U>
 __device__ __forceinline__ void coop_gather_bf16(const TcParams &p, const RowPre &pre, unsigned char *a, int warp, int lane,
                                                  int c8_begin, int c8_from, int c8_to) {
     const bool sa = p.mode == MODE_SA;
-    const __nv_bfloat16 *b0 = reinterpret_cast<const __nv_bfloat16 *>(sa ? (const void *)p.feat : (const void *)p.feat2);
-    const size_t Dm = sa ? p.d : p.d2;
+    // rows are addressed in 16-byte units with 32-bit row index x 32-bit pitch (one IMAD.WIDE.U32 per row pointer)
+    const uint4 *base = reinterpret_cast<const uint4 *>(sa ? (const void *)p.feat : (const void *)p.feat2) + c8_from;
+    const uint32_t pitch = (uint32_t)(sa ? p.d : p.d2) >> 3;
     const bool fp3 = !sa && p.fp_m != 1;
     const int nc = c8_to - c8_from;  // power of two, >= 4
     const int lg = 31 - __clz(nc);
     const int my0 = pre.ok ? pre.i0 : -1, my1 = pre.i1, my2 = pre.i2;
-    for (int base = 0; base < 32 * nc; base += 32 * U) {
+    for (int base_item = 0; base_item < 32 * nc; base_item += 32 * U) {
         uint4 q0[U], q1[U], q2[U];
         float w0[U], w1[U], w2[U];
         int rw[U], ch[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int item = base + 32 * u + lane;
+            const int item = base_item + 32 * u + lane;
             rw[u] = item >> lg;
             ch[u] = item & (nc - 1);
             const int s0 = __shfl_sync(0xffffffffu, my0, rw[u]);
@@ -547,12 +548,12 @@ __device__ __forceinline__ void coop_gather_bf16(const TcParams &p, const RowPre
                 w1[u] = __shfl_sync(0xffffffffu, pre.b, rw[u]);
                 w2[u] = __shfl_sync(0xffffffffu, pre.c, rw[u]);
                 if (s0 >= 0) {
-                    q0[u] = __ldg(reinterpret_cast<const uint4 *>(b0 + (size_t)s0 * Dm) + c8_from + ch[u]);
-                    q1[u] = __ldg(reinterpret_cast<const uint4 *>(b0 + (size_t)s1 * Dm) + c8_from + ch[u]);
-                    q2[u] = __ldg(reinterpret_cast<const uint4 *>(b0 + (size_t)s2 * Dm) + c8_from + ch[u]);
+                    q0[u] = __ldg(base + (size_t)((unsigned long long)(uint32_t)s0 * pitch) + ch[u]);
+                    q1[u] = __ldg(base + (size_t)((unsigned long long)(uint32_t)s1 * pitch) + ch[u]);
+                    q2[u] = __ldg(base + (size_t)((unsigned long long)(uint32_t)s2 * pitch) + ch[u]);
                 }
             } else if (s0 >= 0) {
-                q0[u] = __ldg(reinterpret_cast<const uint4 *>(b0 + (size_t)s0 * Dm) + c8_from + ch[u]);
+                q0[u] = __ldg(base + (size_t)((unsigned long long)(uint32_t)s0 * pitch) + ch[u]);
             }
         }
 #pragma unroll
@@ -579,9 +580,10 @@ __device__ __forceinline__ void coop_gather_bf16(const TcParams &p, const RowPre
     }
 }
 
-// Two instantiations: fp32 gathered features (lean: 4 CTAs/SM) and bf16 gathered features (3 CTAs/SM).
+// Two instantiations (kernels below): fp32 gathered features (lean: 80 registers, 4 CTAs/SM) and bf16 gathered features
+// (96 registers, 3 CTAs/SM).
 template <bool kInBf16>
-__global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel(const __grid_constant__ TcParams p) {
+__device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
     // 1024-byte alignment for the 128B-swizzled operand tiles.  The alignment is REQUESTED on the declaration (no manual
     // round-up through an integer: that hid the address space from the compiler, which then emitted generic LD.E / ST.E
     // for every shared-memory access of the gather and the epilogues) and verified once.
@@ -1012,6 +1014,14 @@ __global__ void __launch_bounds__(TC_THREADS, kInBf16 ? 3 : 4) row_mlp_tc_kernel
     if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// Entry points.  fp32 features: 80 registers, 4 CTAs/SM.  bf16 features: 96 registers (a few spilled words) is what
+// 3 CTAs x 6 warps allow -- the 18 warps spread 5/5/4/4 over the four 16 K-register partitions (__maxnreg__(112) removes
+// the spills and drops to 2 CTAs/SM: fp1+head 120 -> 164 us); blocks that shared memory or TMEM limit to <= 2 CTAs/SM
+// anyway use the un-spilled build.
+__global__ void __launch_bounds__(TC_THREADS, 4) row_mlp_tc_kernel_f32(const __grid_constant__ TcParams p) { row_mlp_tc_body<false>(p); }
+__global__ void __launch_bounds__(TC_THREADS, 3) row_mlp_tc_kernel_bf16(const __grid_constant__ TcParams p) { row_mlp_tc_body<true>(p); }
+__global__ void __launch_bounds__(TC_THREADS, 2) row_mlp_tc_kernel_bf16_wide(const __grid_constant__ TcParams p) { row_mlp_tc_body<true>(p); }
+
 // ---- weight packing -----------------------------------------------------------------------------------
 // Packed image of one layer: for nb in n-blocks, for kb in k-blocks: a [nblk rows x 64 bf16] tile, row n at n*128 B,
 // its 16-byte chunk c stored at position c ^ (n & 7) (128B swizzle), zero padded.  `perm_split` > 0 rotates the
@@ -1204,19 +1214,14 @@ int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, c
     p.kchunk = P.kchunk;
     p.thin = P.thin;
     p.tiles = tiles;
-    if (p.in_bf16)
-        PN2_CUDA(cudaFuncSetAttribute(row_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    else
-        PN2_CUDA(cudaFuncSetAttribute(row_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    // persistent grid: as many CTAs as can be resident (shared memory, 512 TMEM columns, threads), at most one per tile
+    // persistent grid: as many CTAs as can be resident (shared memory, 512 TMEM columns, registers), at most one per tile
     int per_sm = ctas_per_sm(P);
-    if (p.in_bf16 && per_sm > 3) per_sm = 3;  // register budget of the bf16-input instantiation
+    if (p.in_bf16 && per_sm > 3) per_sm = 3;  // register budget of the bf16-input build
+    void (*kernel)(TcParams) = !p.in_bf16 ? row_mlp_tc_kernel_f32 : (per_sm <= 2 ? row_mlp_tc_kernel_bf16_wide : row_mlp_tc_kernel_bf16);
+    PN2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
     long long grid = (long long)per_sm * sm_count();
     if (grid > tiles) grid = tiles;
-    if (p.in_bf16)
-        row_mlp_tc_kernel<true><<<(unsigned)grid, TC_THREADS, P.smem_bytes, s>>>(p);
-    else
-        row_mlp_tc_kernel<false><<<(unsigned)grid, TC_THREADS, P.smem_bytes, s>>>(p);
+    kernel<<<(unsigned)grid, TC_THREADS, P.smem_bytes, s>>>(p);
     PN2_LAUNCH_OK("row_mlp_tc_kernel");
     return PN2_OK;
 }
