@@ -259,6 +259,21 @@ def op_rooflines(device, batch, pk):
         byts = bb * (4 * M * K + 4 * C * min(N, M * K) + 4 * C * M * K)
         out["group_points_b%d_c%d_n%d_m%d_k%d" % (bb, C, N, M, K)] = {"ms": ms, "gbs": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / pk["hbm_gbs"]}
         del f, idx
+    # multi-view lifting (BASELINE config 3 shapes): V views of 128 x 32 x 41 feature maps onto 8192 points per scene
+    from pn2_b200 import scenes as _sc
+    from pn2_b200.projection import lift_views
+    pts_np = x[:, :, :3].cpu().numpy()
+    for V in (3, 5):
+        mv = [_sc.multiview_inputs(7000 + i, pts_np[i], V, 128) for i in range(batch)]
+        feats = torch.from_numpy(np.stack([m[0] for m in mv])).to(device)
+        depth = torch.from_numpy(np.stack([m[1] for m in mv])).to(device)
+        poses = torch.from_numpy(np.stack([m[2] for m in mv]).astype(np.float32)).to(device)
+        for red in ("max", "first"):
+            ms = t_ms(lambda: lift_views(xyz, feats, depth, poses, _sc.SCANNET_INTRINSIC, 0.1, 4.0, _sc.SCANNET_IMAGE_DIMS, 0.05, reduce=red))
+            byts = batch * (12 * NPOINTS + V * (4 * 32 * 41 + 64) + 4 * 128 * min(V * 32 * 41, V * NPOINTS) + 4 * 128 * NPOINTS)
+            out["lift_views_v%d_%s" % (V, red)] = {"ms": ms, "scenes_per_s": batch / ms * 1e3, "gbs": byts / ms / 1e6,
+                                                   "frac_hbm": byts / ms / 1e6 / pk["hbm_gbs"]}
+        del feats, depth, poses
     ms = t_ms(lambda: pu.ball_query(0.1, 32, xyz, new_xyz))
     out["ball_query_r0.1_k32_grid"] = {"ms": ms, "note": "grid build + query; brute force (first version) 0.345 ms"}
     return out

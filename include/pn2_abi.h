@@ -89,6 +89,14 @@ int pn2_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out
 #define PN2_REDUCE_MAX 0   /* F.max_pool1d over views, model/pointnet2multiview.py:39 */
 #define PN2_REDUCE_FIRST 1 /* first view, later views fill all-zero columns, :93-98 */
 
+/* Per-view parameters of the lifting in one launch (utils/projection.py:25-95 and :178, ~25 torch ops per view in the
+ * reference): c2w (num_views,4,4) camera-to-world poses; cam_corners = HOST pointer to 8x3 floats, the camera-space
+ * frustum corners depth_to_skeleton(u,v,d) for (u,v) in (0,0),(W-1,0),(W-1,H-1),(0,H-1) x d in (depth_min, depth_max)
+ * -> w2c (num_views,4,4) = inverse pose (fp64 adjugate, rounded once), corner2 / corner4 (num_views,3), normals
+ * (num_views,6,3), the inputs of pn2_lift_views / pn2_frustum_count. */
+int pn2_lift_setup(int num_views, const float *c2w, const float *cam_corners, float *w2c, float *corner2, float *corner4,
+                   float *normals, void *stream);
+
 /* One launch for a whole batch of B clouds x V views: frustum test, projection, nearest-pixel
  * (round-half-even) lookup, bounds + depth test, feature fetch and view reduction.
  *   points (B,N,3); feats (B,V,C,H,W); depth (B,V,H,W); w2c (B,V,4,4) = inverse(camera_to_world);

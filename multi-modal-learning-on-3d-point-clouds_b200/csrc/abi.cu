@@ -20,6 +20,24 @@ int set_error(int status, const char *fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+cudaError_t scratch_alloc(void **ptr, size_t bytes, cudaStream_t stream) {
+    static std::atomic<unsigned long long> configured{0};  // bit per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_relaxed) & bit)) {
+        cudaMemPool_t pool;
+        e = cudaDeviceGetDefaultMemPool(&pool, dev);
+        if (e != cudaSuccess) return e;
+        unsigned long long keep = ~0ull;
+        e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) return e;
+        configured.fetch_or(bit, std::memory_order_relaxed);
+    }
+    return cudaMallocAsync(ptr, bytes, stream);
+}
+
 int sm_count() {
     static int cached = 0;
     if (!cached) {

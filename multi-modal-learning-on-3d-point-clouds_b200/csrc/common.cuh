@@ -11,6 +11,9 @@ namespace pn2 {
 int set_error(int status, const char *fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
+// Stream-ordered scratch (cudaMallocAsync).  The first call on a device raises the pool's release threshold so that the
+// memory stays in the pool between calls instead of going back to the driver at every synchronisation.
+cudaError_t scratch_alloc(void **ptr, size_t bytes, cudaStream_t stream);
 
 #define PN2_REQUIRE(cond, ...)                                             \
     do {                                                                   \

@@ -138,6 +138,243 @@ lift_views_kernel(int n, int nv, int c, int h, int w, const float *__restrict__ 
     }
 }
 
+// ---- per-view parameters in one launch ------------------------------------------------------------------------
+// The reference derives them per (scene, view) with ~25 small torch ops (utils/projection.py:25-95, 178): inverse of the
+// pose, eight frustum corners = pose x camera-space corners, six plane normals = cross products of corner differences.
+// One thread per view here.  The inverse is evaluated in fp64 (adjugate) and rounded once -- torch.inverse is an fp32 LU
+// whose low bits depend on the backend, so agreement is to ~1 ulp, not bitwise; corners and normals are fp32 with one
+// rounding per operation.
+struct CamCorners {
+    float p[8][3];  // depth_to_skeleton of the four image corners at depth_min (0-3) and depth_max (4-7), utils/projection.py:37-44
+};
+
+__global__ void lift_setup_kernel(int nviews, const float *__restrict__ c2w_all, CamCorners cam, float *__restrict__ w2c_all,
+                                  float *__restrict__ corner2, float *__restrict__ corner4, float *__restrict__ normals) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nviews) return;
+    const float *m = c2w_all + (size_t)t * 16;
+    double a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = (double)m[k];
+    // general 4x4 inverse by the adjugate (2x2 sub-determinants)
+    const double s0 = a[0] * a[5] - a[4] * a[1], s1 = a[0] * a[6] - a[4] * a[2], s2 = a[0] * a[7] - a[4] * a[3];
+    const double s3 = a[1] * a[6] - a[5] * a[2], s4 = a[1] * a[7] - a[5] * a[3], s5 = a[2] * a[7] - a[6] * a[3];
+    const double c5 = a[10] * a[15] - a[14] * a[11], c4 = a[9] * a[15] - a[13] * a[11], c3 = a[9] * a[14] - a[13] * a[10];
+    const double c2 = a[8] * a[15] - a[12] * a[11], c1 = a[8] * a[14] - a[12] * a[10], c0 = a[8] * a[13] - a[12] * a[9];
+    const double inv = 1.0 / (s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0);
+    float *w = w2c_all + (size_t)t * 16;
+    w[0] = (float)((a[5] * c5 - a[6] * c4 + a[7] * c3) * inv);
+    w[1] = (float)((-a[1] * c5 + a[2] * c4 - a[3] * c3) * inv);
+    w[2] = (float)((a[13] * s5 - a[14] * s4 + a[15] * s3) * inv);
+    w[3] = (float)((-a[9] * s5 + a[10] * s4 - a[11] * s3) * inv);
+    w[4] = (float)((-a[4] * c5 + a[6] * c2 - a[7] * c1) * inv);
+    w[5] = (float)((a[0] * c5 - a[2] * c2 + a[3] * c1) * inv);
+    w[6] = (float)((-a[12] * s5 + a[14] * s2 - a[15] * s1) * inv);
+    w[7] = (float)((a[8] * s5 - a[10] * s2 + a[11] * s1) * inv);
+    w[8] = (float)((a[4] * c4 - a[5] * c2 + a[7] * c0) * inv);
+    w[9] = (float)((-a[0] * c4 + a[1] * c2 - a[3] * c0) * inv);
+    w[10] = (float)((a[12] * s4 - a[13] * s2 + a[15] * s0) * inv);
+    w[11] = (float)((-a[8] * s4 + a[9] * s2 - a[11] * s0) * inv);
+    w[12] = (float)((-a[4] * c3 + a[5] * c1 - a[6] * c0) * inv);
+    w[13] = (float)((a[0] * c3 - a[1] * c1 + a[2] * c0) * inv);
+    w[14] = (float)((-a[12] * s3 + a[13] * s1 - a[14] * s0) * inv);
+    w[15] = (float)((a[8] * s3 - a[9] * s1 + a[10] * s0) * inv);
+    // world-space corners: rows 0..2 of pose x (x, y, z, 1)
+    float cw[8][3];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            cw[k][r] = __fadd_rn(__fmaf_rn(m[4 * r + 2], cam.p[k][2], __fmaf_rn(m[4 * r + 1], cam.p[k][1], __fmul_rn(m[4 * r], cam.p[k][0]))),
+                                 m[4 * r + 3]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        corner2[(size_t)t * 3 + r] = cw[2][r];
+        corner4[(size_t)t * 3 + r] = cw[4][r];
+    }
+    // inward normals (utils/projection.py:66-93): cross(c[a1] - c[a0], c[b1] - c[b0])
+    const int A0[6] = {0, 1, 2, 3, 0, 5}, A1[6] = {3, 2, 3, 0, 1, 6}, B0[6] = {0, 1, 2, 3, 0, 5}, B1[6] = {1, 5, 6, 7, 4, 4};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        float u[3], v[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            u[r] = __fsub_rn(cw[A1[k]][r], cw[A0[k]][r]);
+            v[r] = __fsub_rn(cw[B1[k]][r], cw[B0[k]][r]);
+        }
+        float *nk = normals + (size_t)t * 18 + 3 * k;
+        nk[0] = __fsub_rn(__fmul_rn(u[1], v[2]), __fmul_rn(u[2], v[1]));
+        nk[1] = __fsub_rn(__fmul_rn(u[2], v[0]), __fmul_rn(u[0], v[2]));
+        nk[2] = __fsub_rn(__fmul_rn(u[0], v[1]), __fmul_rn(u[1], v[0]));
+    }
+}
+
+// ---- staged path (the default): project once, then stream the feature maps through shared memory ----------------
+// The single-kernel form above fetches every (point, view, channel) value as its own 32-byte sector from a channel-major
+// map (stride H*W floats between channels): 8x read amplification and, measured, 4 % of the HBM roofline.  Staged:
+//   lift_nonzero_kernel  (REDUCE_FIRST only) flags, per (cloud, view, pixel), whether the C-channel column is non-zero;
+//   lift_project_kernel  projects every point into every view once -> pix (b,v,n), count, and for REDUCE_FIRST the view
+//                        each point takes its column from (first visible view with a non-zero column);
+//   lift_gather_kernel   one CTA per (cloud, chunk of CH channels): the chunk's slab of ALL views (V x CH x H*W floats,
+//                        contiguous per view) is copied to shared memory with coalesced 128-bit loads, then every point
+//                        reads its pixels from the slab and the warp writes 32 consecutive points per channel.
+// Feature maps are read once (twice for REDUCE_FIRST), the output is written once, both coalesced.
+__global__ void __launch_bounds__(256)
+lift_nonzero_kernel(int c, int hw, const float *__restrict__ feats, unsigned char *__restrict__ nz) {
+    const int px = blockIdx.x * 256 + threadIdx.x;
+    if (px >= hw) return;
+    const size_t bv = blockIdx.y;
+    const float *f = feats + bv * c * hw + px;
+    bool any = false;
+    for (int ch = 0; ch < c; ++ch) any = any || (__ldg(f + (size_t)ch * hw) != 0.f);
+    nz[bv * hw + px] = any ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(LV_THREADS)
+lift_project_kernel(int n, int nv, int h, int w, const float *__restrict__ points, const float *__restrict__ depth,
+                    const float *__restrict__ w2c, const float *__restrict__ corner2, const float *__restrict__ corner4,
+                    const float *__restrict__ normals, float fx, float fy, float cx, float cy, float dmin, float dmax, float acc,
+                    const unsigned char *__restrict__ nz, int32_t *__restrict__ pix_out, signed char *__restrict__ sel,
+                    int32_t *__restrict__ count) {
+    __shared__ ViewParams vps[LV_MAXV];
+    __shared__ int vcount[LV_MAXV];
+    const int b = blockIdx.y;
+    const int hw = h * w;
+    if (threadIdx.x < nv) {
+        const size_t bv = (size_t)b * nv + threadIdx.x;
+        ViewParams &vp = vps[threadIdx.x];
+        for (int k = 0; k < 12; ++k) vp.w2c[k] = w2c[bv * 16 + k];
+        for (int k = 0; k < 3; ++k) {
+            vp.c2[k] = corner2[bv * 3 + k];
+            vp.c4[k] = corner4[bv * 3 + k];
+        }
+        for (int k = 0; k < 18; ++k) vp.nrm[k] = normals[bv * 18 + k];
+        vcount[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * LV_THREADS + threadIdx.x;
+    if (i < n) {
+        const float *p = points + ((size_t)b * n + i) * 3;
+        const float px = p[0], py = p[1], pz = p[2];
+        int chosen = -1;
+        for (int v = 0; v < nv; ++v) {
+            const size_t bv = (size_t)b * nv + v;
+            const int pix = project_point(px, py, pz, vps[v], fx, fy, cx, cy, w, h, depth + bv * hw, dmin, dmax, acc);
+            pix_out[bv * n + i] = pix;
+            if (count && pix >= 0) atomicAdd(&vcount[v], 1);
+            // first view, then only views that fill an all-zero column (model/pointnet2multiview.py:93-98)
+            if (sel && chosen < 0 && pix >= 0 && nz[bv * hw + pix]) chosen = v;
+        }
+        if (sel) sel[(size_t)b * n + i] = (signed char)chosen;
+    }
+    if (count) {
+        __syncthreads();
+        if (threadIdx.x < nv && vcount[threadIdx.x]) atomicAdd(count + (size_t)b * nv + threadIdx.x, vcount[threadIdx.x]);
+    }
+}
+
+constexpr int LG_THREADS = 512;
+
+template <int CH>
+__global__ void __launch_bounds__(LG_THREADS)
+lift_gather_kernel(int n, int nv, int c, int hw, const float *__restrict__ feats, const int32_t *__restrict__ pix,
+                   const signed char *__restrict__ sel, float *__restrict__ out) {
+    extern __shared__ __align__(16) float slab[];  // [nv][CH][hw]
+    const int b = blockIdx.y;
+    const int c0 = blockIdx.x * CH;
+    const int cc = min(CH, c - c0);
+    for (int v = 0; v < nv; ++v) {
+        const float *src = feats + (((size_t)b * nv + v) * c + c0) * hw;  // cc * hw contiguous floats
+        float *dst = slab + (size_t)v * CH * hw;
+        const int total = cc * hw;
+        if (((uintptr_t)src & 15) == 0 && (total & 3) == 0 && ((CH * hw) & 3) == 0) {
+            for (int e = threadIdx.x; e < total / 4; e += LG_THREADS)
+                reinterpret_cast<float4 *>(dst)[e] = __ldcs(reinterpret_cast<const float4 *>(src) + e);
+        } else {
+            for (int e = threadIdx.x; e < total; e += LG_THREADS) dst[e] = __ldcs(src + e);
+        }
+    }
+    __syncthreads();
+    float *o = out + ((size_t)b * c + c0) * n;
+    const int32_t *pb = pix + (size_t)b * nv * n;
+    if ((n & 3) == 0 && ((uintptr_t)o & 15) == 0 && ((uintptr_t)pb & 15) == 0) {
+        // four consecutive points per thread: 128-bit pixel-index loads and 128-bit streaming stores per channel
+        const int n4 = n >> 2;
+        for (int i4 = threadIdx.x; i4 < n4; i4 += LG_THREADS) {
+            float r[CH][4];
+#pragma unroll
+            for (int q = 0; q < CH; ++q) r[q][0] = r[q][1] = r[q][2] = r[q][3] = 0.f;
+            if (sel) {
+                const char4 sv = *reinterpret_cast<const char4 *>(sel + (size_t)b * n + 4 * i4);
+                const int vs[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (vs[k] >= 0) {
+                        const float *f = slab + (size_t)vs[k] * CH * hw + pb[(size_t)vs[k] * n + 4 * i4 + k];
+#pragma unroll
+                        for (int q = 0; q < CH; ++q) r[q][k] = f[q * hw];
+                    }
+            } else {
+                // F.max_pool1d over the stacked per-view maps: invisible views contribute zeros
+                for (int v = 0; v < nv; ++v) {
+                    const int4 pv = *(reinterpret_cast<const int4 *>(pb + (size_t)v * n) + i4);
+                    const int ps[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float *f = slab + (size_t)v * CH * hw + (ps[k] >= 0 ? ps[k] : 0);
+#pragma unroll
+                        for (int q = 0; q < CH; ++q) {
+                            const float x = ps[k] >= 0 ? f[q * hw] : 0.f;
+                            r[q][k] = v == 0 ? x : fmaxf(r[q][k], x);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < CH; ++q)
+                if (q < cc) __stcs(reinterpret_cast<float4 *>(o + (size_t)q * n) + i4, make_float4(r[q][0], r[q][1], r[q][2], r[q][3]));
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < n; i += LG_THREADS) {
+        float r[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) r[q] = 0.f;
+        if (sel) {
+            const int v = sel[(size_t)b * n + i];
+            if (v >= 0) {
+                const float *f = slab + (size_t)v * CH * hw + pb[(size_t)v * n + i];
+#pragma unroll
+                for (int q = 0; q < CH; ++q) r[q] = f[q * hw];
+            }
+        } else {
+            for (int v = 0; v < nv; ++v) {
+                const int p = pb[(size_t)v * n + i];
+                const float *f = slab + (size_t)v * CH * hw + (p >= 0 ? p : 0);
+#pragma unroll
+                for (int q = 0; q < CH; ++q) {
+                    const float x = p >= 0 ? f[q * hw] : 0.f;
+                    r[q] = v == 0 ? x : fmaxf(r[q], x);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < CH; ++q)
+            if (q < cc) __stcs(o + (size_t)q * n + i, r[q]);
+    }
+}
+
+template <int CH>
+int launch_lift_gather(int b, int n, int nv, int c, int hw, const float *feats, const int32_t *pix, const signed char *sel, float *out,
+                       cudaStream_t s) {
+    const size_t smem = (size_t)nv * CH * hw * sizeof(float);
+    PN2_CUDA(cudaFuncSetAttribute(lift_gather_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(c, CH), b);
+    lift_gather_kernel<CH><<<grid, LG_THREADS, smem, s>>>(n, nv, c, hw, feats, pix, sel, out);
+    PN2_LAUNCH_OK("lift_gather_kernel");
+    return PN2_OK;
+}
+
 // Best-view selection of the ScanNet loader (data_utils/ScanNetDataLoader.py:87-105, 260-278): how many of the N crop
 // points fall inside the frustum of EACH of the scene's P camera poses.  The reference calls points_in_frustum_cpu
 // (utils/projection.py:132-164) once per pose file on the CPU in fp64; here all P x N tests are one launch, in fp64
@@ -198,6 +435,20 @@ extern "C" int pn2_frustum_count(int n, int num_poses, const float *points, cons
     return PN2_OK;
 }
 
+extern "C" int pn2_lift_setup(int num_views, const float *c2w, const float *cam_corners, float *w2c, float *corner2, float *corner4,
+                              float *normals, void *stream) {
+    using namespace pn2;
+    PN2_REQUIRE(num_views >= 0, "lift_setup: bad dims");
+    if (num_views == 0) return PN2_OK;
+    PN2_REQUIRE(c2w && cam_corners && w2c && corner2 && corner4 && normals, "lift_setup: null pointer");
+    CamCorners cam;
+    for (int k = 0; k < 8; ++k)
+        for (int r = 0; r < 3; ++r) cam.p[k][r] = cam_corners[3 * k + r];
+    lift_setup_kernel<<<ceil_div(num_views, 128), 128, 0, (cudaStream_t)stream>>>(num_views, c2w, cam, w2c, corner2, corner4, normals);
+    PN2_LAUNCH_OK("lift_setup_kernel");
+    return PN2_OK;
+}
+
 extern "C" int pn2_lift_views(int b, int n, int v, int c, int h, int w, const float *points, const float *feats,
                               const float *depth, const float *w2c, const float *corner2, const float *corner4,
                               const float *normals, const float *intr, float depth_min, float depth_max,
@@ -209,8 +460,46 @@ extern "C" int pn2_lift_views(int b, int n, int v, int c, int h, int w, const fl
     if (b == 0 || n == 0) return PN2_OK;
     PN2_REQUIRE(points && depth && w2c && corner2 && corner4 && normals && intr && ((feats && out) || c == 0), "lift_views: null pointer");
     PN2_REQUIRE(b <= 65535, "lift_views: b exceeds the grid limit");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int hw = h * w;
+    // staged path when a slab of all views fits shared memory for at least one channel (ENet-sized maps: 4-8 channels)
+    const size_t per_ch = (size_t)v * hw * sizeof(float);
+    const int chunk = c == 0 ? 0 : (8 * per_ch <= 100 * 1024 ? 8 : 4 * per_ch <= 100 * 1024 ? 4 : 2 * per_ch <= 200 * 1024 ? 2 : per_ch <= 200 * 1024 ? 1 : -1);
+    if (chunk >= 0 && ceil_div(c, chunk > 0 ? chunk : 1) <= 65535) {
+        const bool first = reduce == PN2_REDUCE_FIRST && c > 0;
+        const size_t pix_bytes = ((size_t)b * v * n * sizeof(int32_t) + 255) / 256 * 256;
+        const size_t sel_bytes = first ? ((size_t)b * n + 255) / 256 * 256 : 0;
+        const size_t nz_bytes = first ? ((size_t)b * v * hw + 255) / 256 * 256 : 0;
+        unsigned char *scratch = nullptr;
+        PN2_CUDA(scratch_alloc((void **)&scratch, (pix ? 0 : pix_bytes) + sel_bytes + nz_bytes + 256, s));
+        unsigned char *cur = scratch;
+        int32_t *pixbuf = pix;
+        if (!pixbuf) {
+            pixbuf = (int32_t *)cur;
+            cur += pix_bytes;
+        }
+        signed char *sel = first ? (signed char *)cur : nullptr;
+        cur += sel_bytes;
+        unsigned char *nz = first ? cur : nullptr;
+        if (first) {
+            lift_nonzero_kernel<<<dim3(ceil_div(hw, 256), b * v), 256, 0, s>>>(c, hw, feats, nz);
+            PN2_LAUNCH_OK("lift_nonzero_kernel");
+        }
+        lift_project_kernel<<<dim3(ceil_div(n, LV_THREADS), b), LV_THREADS, 0, s>>>(n, v, h, w, points, depth, w2c, corner2, corner4, normals,
+                                                                                  intr[0], intr[1], intr[2], intr[3], depth_min, depth_max,
+                                                                                  accuracy, nz, pixbuf, sel, count);
+        PN2_LAUNCH_OK("lift_project_kernel");
+        int st = PN2_OK;
+        if (chunk == 8) st = launch_lift_gather<8>(b, n, v, c, hw, feats, pixbuf, sel, out, s);
+        else if (chunk == 4) st = launch_lift_gather<4>(b, n, v, c, hw, feats, pixbuf, sel, out, s);
+        else if (chunk == 2) st = launch_lift_gather<2>(b, n, v, c, hw, feats, pixbuf, sel, out, s);
+        else if (chunk == 1) st = launch_lift_gather<1>(b, n, v, c, hw, feats, pixbuf, sel, out, s);
+        PN2_CUDA(cudaFreeAsync(scratch, s));
+        return st;
+    }
+    // feature maps too large for a shared-memory slab: one kernel, per-element gathers
     dim3 grid(ceil_div(n, LV_THREADS), b);
-    lift_views_kernel<<<grid, LV_THREADS, 0, (cudaStream_t)stream>>>(n, v, c, h, w, points, feats, depth, w2c, corner2, corner4,
+    lift_views_kernel<<<grid, LV_THREADS, 0, s>>>(n, v, c, h, w, points, feats, depth, w2c, corner2, corner4,
                                                                      normals, intr[0], intr[1], intr[2], intr[3], depth_min,
                                                                      depth_max, accuracy, reduce, out, pix, count);
     PN2_LAUNCH_OK("lift_views");

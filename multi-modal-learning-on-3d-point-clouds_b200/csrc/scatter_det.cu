@@ -97,7 +97,7 @@ extern "C" int pn2_inverse_index(int b, int n, long long j, const int32_t *idx, 
                                              (int32_t *)nullptr, (int)total, 0, end_bit, s));
     const size_t key_bytes = ((size_t)total * sizeof(uint32_t) + 255) / 256 * 256;
     unsigned char *scratch = nullptr;  // [keys in | keys out | positions in | cub temp]
-    PN2_CUDA(cudaMallocAsync((void **)&scratch, 3 * key_bytes + tmp_bytes, s));
+    PN2_CUDA(scratch_alloc((void **)&scratch, 3 * key_bytes + tmp_bytes, s));
     uint32_t *keys_in = (uint32_t *)scratch, *keys_out = (uint32_t *)(scratch + key_bytes);
     int32_t *pos_in = (int32_t *)(scratch + 2 * key_bytes);
     const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);

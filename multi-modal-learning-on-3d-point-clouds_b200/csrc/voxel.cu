@@ -184,7 +184,7 @@ extern "C" int pn2_voxel_first_index(int b, int n, const float *xyz, const unsig
                                              (const int32_t *)nullptr, (int32_t *)nullptr, (int)total, 0, end_bit, s));
     const size_t kb = ((size_t)total * 8 + 255) / 256 * 256, vb = ((size_t)total * 4 + 255) / 256 * 256;
     unsigned char *scratch = nullptr;  // [keys in | keys out | vals in | vals out | cub temp]
-    PN2_CUDA(cudaMallocAsync((void **)&scratch, 2 * kb + 2 * vb + tmp_bytes, s));
+    PN2_CUDA(scratch_alloc((void **)&scratch, 2 * kb + 2 * vb + tmp_bytes, s));
     unsigned long long *k_in = (unsigned long long *)scratch, *k_out = (unsigned long long *)(scratch + kb);
     int32_t *v_in = (int32_t *)(scratch + 2 * kb), *v_out = (int32_t *)(scratch + 2 * kb + vb);
     voxel_keys_kernel<<<b, VX_THREADS, 0, s>>>(n, xyz, mask, res, k_in, v_in, nvox);

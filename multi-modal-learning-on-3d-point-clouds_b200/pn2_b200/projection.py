@@ -56,6 +56,30 @@ def frustum_normals(corners):
                        dim=-2)
 
 
+def view_params(camera_to_world, intrinsic, depth_min, depth_max, image_dims):
+    """camera_to_world (..., 4, 4) cuda -> (w2c (..., 4, 4), corner2 (..., 3), corner4 (..., 3), normals (..., 6, 3)):
+    everything the lifting / frustum tests need per view, in ONE launch (pn2_lift_setup) instead of the ~25 torch ops of
+    utils/projection.py:25-95 + torch.inverse (:178).  The inverse is an fp64 adjugate rounded once, so it agrees with
+    torch.inverse to ~1 ulp rather than bitwise (see csrc/lift.cu)."""
+    _lib.require_cuda(camera_to_world)
+    c2w = camera_to_world.to(torch.float32).contiguous()
+    lead = c2w.shape[:-2]
+    nv = c2w.numel() // 16
+    W, H = image_dims
+    cam = []
+    for d in (depth_min, depth_max):
+        for (u, v) in ((0, 0), (W - 1, 0), (W - 1, H - 1), (0, H - 1)):
+            cam += _skeleton(intrinsic, u, v, d)  # Python floats, rounded to fp32 below as torch.Tensor(...) does
+    cam = (ctypes.c_float * 24)(*cam)
+    w2c_c = torch.empty((nv, 16), dtype=torch.float32, device=c2w.device)
+    c2_c = torch.empty((nv, 3), dtype=torch.float32, device=c2w.device)
+    c4_c = torch.empty((nv, 3), dtype=torch.float32, device=c2w.device)
+    nrm_c = torch.empty((nv, 18), dtype=torch.float32, device=c2w.device)
+    with torch.cuda.device(c2w.device):
+        _lib.call("pn2_lift_setup", nv, ptr(c2w), cam, ptr(w2c_c), ptr(c2_c), ptr(c4_c), ptr(nrm_c), _lib.stream_ptr(c2w.device))
+    return w2c_c.view(*lead, 4, 4), c2_c.view(*lead, 3), c4_c.view(*lead, 3), nrm_c.view(*lead, 6, 3)
+
+
 def lift_views(points, feats, depth, camera_to_world, intrinsic, depth_min, depth_max, image_dims, accuracy,
                reduce="max", return_pixels=False):
     """Fused lifting for a batch.
@@ -71,12 +95,7 @@ def lift_views(points, feats, depth, camera_to_world, intrinsic, depth_min, dept
     if [W, H] != [int(image_dims[0]), int(image_dims[1])]:
         raise _lib.Pn2Error("image_dims [W, H] = %s does not match the feature maps (H=%d, W=%d)" % (list(image_dims), H, W))
     dev = points.device
-    c2w = camera_to_world.to(torch.float32)
-    w2c = torch.inverse(c2w).contiguous()                      # as the reference (:178)
-    corners = frustum_corners(intrinsic, depth_min, depth_max, image_dims, c2w)
-    normals = frustum_normals(corners).contiguous()
-    corner2 = corners[..., 2, :3].contiguous()
-    corner4 = corners[..., 4, :3].contiguous()
+    w2c, corner2, corner4, normals = view_params(camera_to_world, intrinsic, depth_min, depth_max, image_dims)
     intr = (ctypes.c_float * 4)(float(intrinsic[0][0]), float(intrinsic[1][1]), float(intrinsic[0][2]), float(intrinsic[1][2]))
     out = torch.empty((B, C, N), dtype=torch.float32, device=dev)
     pix = torch.empty((B, V, N), dtype=torch.int32, device=dev) if return_pixels else None
@@ -97,11 +116,8 @@ def frustum_counts(points, camera_to_world, intrinsic, depth_min, depth_max, ima
     One launch for all poses of a scene; replaces the loader's per-pose-file loop over points_in_frustum_cpu
     (data_utils/ScanNetDataLoader.py:91-97)."""
     _lib.require_cuda(points, camera_to_world)
-    c2w = camera_to_world.to(torch.float32)
-    corners = frustum_corners(intrinsic, depth_min, depth_max, image_dims, c2w)
-    normals = frustum_normals(corners).contiguous()
-    c2, c4 = corners[..., 2, :3].contiguous(), corners[..., 4, :3].contiguous()
-    P, N = c2w.shape[0], points.shape[0]
+    _, c2, c4, normals = view_params(camera_to_world, intrinsic, depth_min, depth_max, image_dims)
+    P, N = camera_to_world.shape[0], points.shape[0]
     counts = torch.zeros((P,), dtype=torch.int32, device=points.device)
     points = points.contiguous()
     with torch.cuda.device(points.device):

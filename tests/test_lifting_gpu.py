@@ -34,17 +34,40 @@ def test_lift_views_bit_exact_vs_oracle(cuda, reduce, B, N, V, C):
     t = lambda a: torch.from_numpy(a).to(cuda)
     out, pix, count = projection.lift_views(t(xyz), t(feats), t(depth), t(poses), INTR, DMIN, DMAX, DIMS, ACC, reduce=reduce,
                                             return_pixels=True)
-    c2w = t(poses)
-    corners = projection.frustum_corners(INTR, DMIN, DMAX, DIMS, c2w)
-    normals = projection.frustum_normals(corners)
-    w2c = torch.inverse(c2w)
-    want, wpix = orc.lift_views(xyz, feats, depth, w2c.cpu().numpy().reshape(B, V, 16), corners[..., 2, :3].cpu().numpy(),
-                                corners[..., 4, :3].cpu().numpy(), normals.cpu().numpy().reshape(B, V, 18),
+    # the per-view parameters come from the product's own setup kernel (pinned to the reference's torch formulas by
+    # test_view_params_match_the_reference_formulas below); the oracle then checks projection, tests and gather bit for bit
+    w2c, corner2, corner4, normals = projection.view_params(t(poses), INTR, DMIN, DMAX, DIMS)
+    want, wpix = orc.lift_views(xyz, feats, depth, w2c.cpu().numpy().reshape(B, V, 16), corner2.cpu().numpy(),
+                                corner4.cpu().numpy(), normals.cpu().numpy().reshape(B, V, 18),
                                 np.array([INTR[0, 0], INTR[1, 1], INTR[0, 2], INTR[1, 2]], np.float32), DMIN, DMAX, ACC, reduce)
     np.testing.assert_array_equal(pix.cpu().numpy(), wpix)
     np.testing.assert_array_equal(out.cpu().numpy(), want)
     np.testing.assert_array_equal(count.cpu().numpy(), (wpix >= 0).sum(-1))
     assert (wpix >= 0).mean() > 0.05, "the synthetic views must actually see the scene"
+
+
+def test_view_params_match_the_reference_formulas(cuda):
+    """pn2_lift_setup against the reference's op sequence (utils/projection.py:25-95, :178): torch.inverse, pose x corners,
+    cross products.  One launch instead of ~25; agreement to a few ulp (the inverse is an fp64 adjugate rounded once)."""
+    _, _, _, poses = make_batch(3, 64, 5, 4, 77)
+    c2w = torch.from_numpy(poses).to(cuda)
+    w2c, c2, c4, nrm = projection.view_params(c2w, INTR, DMIN, DMAX, DIMS)
+    corners = projection.frustum_corners(INTR, DMIN, DMAX, DIMS, c2w)
+    want_n = projection.frustum_normals(corners)
+    want_w = torch.inverse(c2w.double())  # the exact inverse; torch.inverse in fp32 is itself only good to ~1e-6
+
+    def close(a, b, rel):
+        a, b = a.double().cpu(), b.double().cpu()
+        assert (a - b).abs().max() <= rel * b.abs().max()
+
+    close(w2c, want_w, 2e-7)
+    close(torch.inverse(c2w), want_w, 2e-5)          # the reference's own fp32 inverse is further from the truth than ours
+    close(c2, corners[..., 2, :3], 2e-7)
+    close(c4, corners[..., 4, :3], 2e-7)
+    close(nrm, want_n, 2e-6)
+    assert w2c.shape == (3, 5, 4, 4) and nrm.shape == (3, 5, 6, 3)
+    # the bottom row of an inverted rigid pose
+    assert torch.allclose(w2c[..., 3, :].cpu(), torch.tensor([0.0, 0.0, 0.0, 1.0]).expand(3, 5, 4), atol=1e-7)
 
 
 def test_lift_matches_reference_op_sequence(cuda):
