@@ -250,30 +250,65 @@ class _MultiviewStackBase(nn.Module):
         relus = [True] * len(self.fp1.mlp_convs) + [True, False]
         return self._head_fold.get(convs, bns, relus)
 
-    def forward_fused(self, xyz, image_features):
+    def _blocks(self):
+        mods = [self.sa1_geo, self.sa1_feat, self.sa2_geo, self.sa2_feat, self.sa3, self.sa4]
+        out = []
+        for m in mods:
+            out += [m.folded(i) for i in range(len(m.radius_list))] if hasattr(m, "radius_list") else [m.folded()]
+        return out + [self.fp4.folded(), self.fp3.folded(), self.fp2.folded(), self._fp1_with_head()]
+
+    def can_fuse_labels(self):
+        return get_mlp_precision() == "bf16" and self._fp1_with_head().bf16_ok() and self.conv2.out_channels <= 256
+
+    def forward_fused(self, xyz, image_features, labels=False):
         """Channel-last fused path; the two level-1/level-2 branches share ONE sampling and ball query each
-        (the reference recomputes them on identical coordinates, model/pointnet2multiview.py:104-107)."""
-        xyz_cl, img_cl = to_channel_last(xyz), to_channel_last(image_features)
-        geo1 = self._geometry(self.sa1_geo, xyz_cl)
-        l1_xyz, l1g = self.sa1_geo.forward_cl(xyz_cl, None, geometry=geo1)
-        _, l1f = self.sa1_feat.forward_cl(xyz_cl, img_cl, geometry=geo1)
+        (the reference recomputes them on identical coordinates, model/pointnet2multiview.py:104-107).  As in
+        PointNet2SemSeg.forward_fused: one cell list of the input cloud serves the level-0 ball queries, the 3-NN of fp1
+        and the processing order of its rows; activations between tensor-core blocks travel as bf16."""
+        xyz_cl = to_channel_last(xyz)
+        act = torch.bfloat16 if (get_mlp_precision() == "bf16" and all(b.bf16_ok() for b in self._blocks())) else torch.float32
+        # the lifted features are rounded to bf16 for the MMA operand anyway: converting while transposing is bit-identical
+        img_cl = image_features.permute(0, 2, 1).to(act).contiguous() if act == torch.bfloat16 else to_channel_last(image_features)
+        n0 = xyz_cl.shape[1]
+        radii0 = self.sa1_geo.radius_list if hasattr(self.sa1_geo, "radius_list") else [self.sa1_geo.radius]
+        g0 = SpatialGrid(xyz_cl, 1.01 * max(radii0)) if 2048 <= n0 <= grid_max_points() else None
+        geo1 = self._geometry(self.sa1_geo, xyz_cl, g0)
+        l1_xyz, l1g = self.sa1_geo.forward_cl(xyz_cl, None, geometry=geo1, out_dtype=act)
+        _, l1f = self.sa1_feat.forward_cl(xyz_cl, img_cl, geometry=geo1, out_dtype=act)
         geo2 = self._geometry(self.sa2_geo, l1_xyz)
-        l2_xyz, l2g = self.sa2_geo.forward_cl(l1_xyz, l1g, geometry=geo2)
-        _, l2f = self.sa2_feat.forward_cl(l1_xyz, l1f, geometry=geo2)
+        l2_xyz, l2g = self.sa2_geo.forward_cl(l1_xyz, l1g, geometry=geo2, out_dtype=act)
+        _, l2f = self.sa2_feat.forward_cl(l1_xyz, l1f, geometry=geo2, out_dtype=act)
         l2 = torch.cat((l2g, l2f), dim=2)
-        l3_xyz, l3 = self.sa3.forward_cl(l2_xyz, l2)
-        l4_xyz, l4 = self.sa4.forward_cl(l3_xyz, l3)
-        l3 = self.fp4.forward_cl(l3_xyz, l4_xyz, l3, l4)
-        l2 = self.fp3.forward_cl(l2_xyz, l3_xyz, l2, l3)
-        l1 = self.fp2.forward_cl(l1_xyz, l2_xyz, l1g, l2)
-        return self.fp1.forward_cl(xyz_cl, l1_xyz, None, l1, mlp=self._fp1_with_head())
+        l3_xyz, l3 = self.sa3.forward_cl(l2_xyz, l2, out_dtype=act)
+        l4_xyz, l4 = self.sa4.forward_cl(l3_xyz, l3, out_dtype=act)
+        l3 = self.fp4.forward_cl(l3_xyz, l4_xyz, l3, l4, out_dtype=act)
+        l2 = self.fp3.forward_cl(l2_xyz, l3_xyz, l2, l3, out_dtype=act)
+        l1 = self.fp2.forward_cl(l1_xyz, l2_xyz, l1g, l2, out_dtype=act)
+        nnw = None
+        if g0 is not None and 512 <= l1_xyz.shape[1] <= grid_max_points():
+            nnw = SpatialGrid(l1_xyz, 0.0).three_nn(xyz_cl, query_order=g0.order)
+        return self.fp1.forward_cl(xyz_cl, l1_xyz, None, l1, mlp=self._fp1_with_head(), nn_weights=nnw,
+                                   row_order=g0.order if g0 is not None else None,
+                                   out_dtype=torch.uint8 if labels else torch.float32)
+
+    def predict(self, xyz, image_features):
+        """Per-point class predictions (B, N) uint8; see PointNet2SemSeg.predict."""
+        if _fusable(self, xyz, image_features) and self.can_fuse_labels():
+            return self.forward_fused(xyz, image_features, labels=True)
+        logits = self.forward(xyz, image_features)
+        classes = torch.arange(logits.shape[-1], device=logits.device)
+        return torch.where(logits == logits.max(dim=-1, keepdim=True).values, classes, logits.shape[-1]).min(dim=-1).values.to(torch.uint8)
 
     @staticmethod
-    def _geometry(sa, xyz_cl):
+    def _geometry(sa, xyz_cl, grid=None):
         _, new_xyz = fps_gather_cl(xyz_cl, sa.npoint)
+
+        def query(r, k):
+            return grid.ball_query(r, k, new_xyz) if grid is not None else pointnet2_utils.ball_query(r, k, xyz_cl, new_xyz)
+
         if hasattr(sa, "radius_list"):
-            return new_xyz, [pointnet2_utils.ball_query(r, k, xyz_cl, new_xyz) for r, k in zip(sa.radius_list, sa.nsample_list)]
-        return new_xyz, pointnet2_utils.ball_query(sa.radius, sa.nsample, xyz_cl, new_xyz)
+            return new_xyz, [query(r, k) for r, k in zip(sa.radius_list, sa.nsample_list)]
+        return new_xyz, query(sa.radius, sa.nsample)
 
     def forward(self, xyz, image_features):
         """xyz (B, 3, N), image_features (B, 128, N) (lifted 2-D features) -> (B, N, num_classes)"""

@@ -435,7 +435,7 @@ class PointNetSetAbstractionMsg(nn.Module):
     def folded(self, i):
         return self._folds[i].get(self.conv_blocks[i], self.bn_blocks[i], [True] * len(self.conv_blocks[i]))
 
-    def forward_cl(self, xyz_cl, feat_cl, geometry=None):
+    def forward_cl(self, xyz_cl, feat_cl, geometry=None, out_dtype=torch.float32):
         """geometry = (new_xyz, [ball_idx per scale]) to share sampling / queries between modules."""
         if geometry is None:
             _, new_xyz = fps_gather_cl(xyz_cl, self.npoint)
@@ -444,7 +444,7 @@ class PointNetSetAbstractionMsg(nn.Module):
             new_xyz, idxs = geometry
         mlps = [self.folded(i) for i in range(len(self.radius_list))]
         B = xyz_cl.shape[0]
-        out = torch.empty((B, self.npoint, sum(m.cout for m in mlps)), dtype=torch.float32, device=xyz_cl.device)
+        out = torch.empty((B, self.npoint, sum(m.cout for m in mlps)), dtype=out_dtype, device=xyz_cl.device)
         off = 0
         for idx, mlp in zip(idxs, mlps):
             # features first, centred xyz last (reference :157); scales concatenated in order (:170)
