@@ -258,12 +258,15 @@ __global__ void __launch_bounds__(T, 1)
 fps_cluster_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__restrict__ idx_all,
                    float *__restrict__ new_xyz_all) {
     constexpr int NW = T / 32;
-    constexpr int G = T * C;          // threads per cloud
-    static_assert(G == 1024 && NW * C == 32, "cluster FPS assumes 1024 threads and 32 warp records per cloud");
+    constexpr int G = T * C;          // threads per cloud: 1024 (C = 4) or 2048 (C = 8: large sweeps, half the points per thread)
+    constexpr int NREC = NW * C;      // warp records per round
+    constexpr int QS = G / 1024;      // thread g owns k = g + i*G: k mod 1024 = g mod 1024, k / 1024 = QS*i + g / 1024
+    constexpr int SB = NREC == 32 ? 5 : 6;  // bits of the record slot below q in the tie key
+    static_assert((G == 1024 || G == 2048) && (NREC == 32 || NREC == 64), "cluster FPS: 4 or 8 CTAs of 256 threads per cloud");
     extern __shared__ float smem[];
     float *sx = smem, *sy = smem + T * P, *sz = smem + 2 * T * P;
-    __shared__ __align__(16) uint4 rec[2][32];   // {dist bits, ~tie key, x bits, y bits}
-    __shared__ float rec_z[2][32];
+    __shared__ __align__(16) uint4 rec[2][NREC];   // {dist bits, ~tie key, x bits, y bits}
+    __shared__ float rec_z[2][NREC];
     __shared__ __align__(8) unsigned long long mbar[2];
 
     const uint32_t rank = cluster_ctarank();
@@ -287,11 +290,12 @@ fps_cluster_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__r
         sy[i * T + tl] = y[i];
         sz[i * T + tl] = z[i];
     }
-    // Tie key of the cluster kernel: (bitrev10(g) << 22) | (i << 5) | slot.  The slot (= g / 32, the record index of
-    // this warp) is a function of g, so appending it below i does not change the order; it lets the receiver find
-    // the winning record without a ballot.
+    // Tie key of the cluster kernel: (bitrev10(g mod 1024) << 22) | (q << SB) | slot with q = k / 1024 = QS*i + g / 1024.
+    // The slot (= g / 32, the record index of this warp) is a function of g, so appending it below q does not change
+    // the order; it lets the receiver find the winning record without a ballot.
     const int my_slot = (int)rank * NW + warp;
-    const uint32_t inv_base = 0xFFFFFFFFu - (((__brev((uint32_t)g) >> 22) << QB) | (uint32_t)my_slot);
+    const uint32_t inv_base =
+        0xFFFFFFFFu - (((__brev((uint32_t)(g & 1023)) >> 22) << QB) | ((uint32_t)(g >> 10) << SB) | (uint32_t)my_slot);
     if (tl == 0) {
         const uint32_t b0 = (uint32_t)__cvta_generic_to_shared(&mbar[0]);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b0), "r"(1));
@@ -311,20 +315,19 @@ fps_cluster_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__r
     const uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(&rec[0][0]);
     const uint32_t recz_base = (uint32_t)__cvta_generic_to_shared(&rec_z[0][0]);
     const uint32_t bar_base = (uint32_t)__cvta_generic_to_shared(&mbar[0]);
-    // remote addresses of this warp's record slot / z slot / barrier in every CTA of the cluster (parity 0)
-    uint32_t ra[C], rz[C], rb[C];
-#pragma unroll
-    for (int d = 0; d < C; ++d) {
-        ra[d] = map_to_cta(rec_base + (uint32_t)my_slot * 16u, (uint32_t)d);
-        rz[d] = map_to_cta(recz_base + (uint32_t)my_slot * 4u, (uint32_t)d);
-        rb[d] = map_to_cta(bar_base, (uint32_t)d);
-    }
+    // lane d < C delivers this warp's record to CTA d: remote addresses of the warp's record slot / z slot and of the
+    // barrier in THAT CTA (parity 0).  All C deliveries of a round leave in one instruction instead of a 2C-store loop
+    // in the winning lane.
+    const uint32_t dest = (uint32_t)lane < (uint32_t)C ? (uint32_t)lane : 0u;
+    const uint32_t my_ra = map_to_cta(rec_base + (uint32_t)my_slot * 16u, dest);
+    const uint32_t my_rz = map_to_cta(recz_base + (uint32_t)my_slot * 4u, dest);
+    const uint32_t my_rb = map_to_cta(bar_base, dest);
 
     for (int j = 1; j < m; ++j) {
         const int par = j & 1;
-        // arm this round's barrier: one local arrival + 32 records x 20 bytes delivered by st.async
+        // arm this round's barrier: one local arrival + NREC records x 20 bytes delivered by st.async
         if (tl == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_base + (uint32_t)par * 8u), "r"(32 * 20)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_base + (uint32_t)par * 8u), "r"(NREC * 20)
                          : "memory");
         // update the running minima, then a pairwise (log-depth) in-thread arg-max; on ties the lower i wins
         update_min<P>(x, y, z, tm, x1, y1, z1);
@@ -347,26 +350,28 @@ fps_cluster_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__r
         }
         const float best = bv[0];
         const int besti = bi[0];
-        const uint32_t hi = __float_as_uint(best), lo = inv_base - ((uint32_t)besti << 5);
+        const uint32_t hi = __float_as_uint(best), lo = inv_base - ((uint32_t)(QS * besti) << SB);
         uint32_t whi = hi, wlo = lo;
         warp_argmax(whi, wlo);
-        if (hi == whi && lo == wlo) {
-            // the warp's winning lane delivers (key, coordinates) to every CTA; completion is counted on that
-            // CTA's barrier (st.async + complete_tx: no fences, no block barrier)
-            const float cx = sx[besti * T + tl], cy = sy[besti * T + tl], cz = sz[besti * T + tl];
-#pragma unroll
-            for (int d = 0; d < C; ++d) {
+        {
+            // the winning lane's coordinates are broadcast, then lanes 0..C-1 deliver (key, coordinates) to one CTA each;
+            // completion is counted on that CTA's barrier (st.async + complete_tx: no fences, no block barrier)
+            const int wl = __ffs(__ballot_sync(0xffffffffu, hi == whi && lo == wlo)) - 1;
+            const float cx = __shfl_sync(0xffffffffu, sx[besti * T + tl], wl);
+            const float cy = __shfl_sync(0xffffffffu, sy[besti * T + tl], wl);
+            const float cz = __shfl_sync(0xffffffffu, sz[besti * T + tl], wl);
+            if (lane < C) {
                 asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
-                                 ra[d] + (uint32_t)par * 512u),
-                             "r"(whi), "r"(wlo), "r"(__float_as_uint(cx)), "r"(__float_as_uint(cy)), "r"(rb[d] + (uint32_t)par * 8u)
+                                 my_ra + (uint32_t)par * (NREC * 16u)),
+                             "r"(whi), "r"(wlo), "r"(__float_as_uint(cx)), "r"(__float_as_uint(cy)), "r"(my_rb + (uint32_t)par * 8u)
                              : "memory");
                 asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(
-                                 rz[d] + (uint32_t)par * 128u),
-                             "r"(__float_as_uint(cz)), "r"(rb[d] + (uint32_t)par * 8u)
+                                 my_rz + (uint32_t)par * (NREC * 4u)),
+                             "r"(__float_as_uint(cz)), "r"(my_rb + (uint32_t)par * 8u)
                              : "memory");
             }
         }
-        // wait until all 32 records of this round are in OUR shared memory
+        // wait until all NREC records of this round are in OUR shared memory
         {
             const uint32_t bar = bar_base + (uint32_t)par * 8u;
             const uint32_t parity = (uint32_t)((j - 1) >> 1) & 1u;  // each barrier is used every other round
@@ -383,15 +388,22 @@ fps_cluster_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__r
         }
         const uint2 key = *reinterpret_cast<const uint2 *>(&rec[par][lane]);
         uint32_t ghi = key.x, glo = key.y;
+        if (NREC == 64) {  // two records per lane: keep the larger (dist, ~tie key) pair
+            const uint2 k2 = *reinterpret_cast<const uint2 *>(&rec[par][lane + 32]);
+            if (k2.x > ghi || (k2.x == ghi && k2.y > glo)) {
+                ghi = k2.x;
+                glo = k2.y;
+            }
+        }
         warp_argmax(ghi, glo);
         const uint32_t tie = 0xFFFFFFFFu - glo;
-        const int src = (int)(tie & 31u);
+        const int src = (int)(tie & (uint32_t)(NREC - 1));
         const uint4 win = rec[par][src];  // broadcast read of the winning record
         x1 = __uint_as_float(win.z);
         y1 = __uint_as_float(win.w);
         z1 = rec_z[par][src];
         if (g == 0) {
-            const int k = (int)((tie & QMASK) >> 5) * 1024 + (int)(__brev(tie >> QB) >> 22);
+            const int k = (int)((tie & QMASK) >> SB) * 1024 + (int)(__brev(tie >> QB) >> 22);
             idx[j] = k;
             if (new_xyz) {
                 new_xyz[3 * j] = x1; new_xyz[3 * j + 1] = y1; new_xyz[3 * j + 2] = z1;
@@ -512,9 +524,9 @@ int launch_few(int b, int n, int m, const float *xyz, int32_t *idx, float *new_x
     return PN2_OK;
 }
 
-template <int P>
+template <int P, int C = 4>
 int launch_cluster(int b, int n, int m, const float *xyz, int32_t *idx, float *new_xyz, cudaStream_t s) {
-    constexpr int T = 256, C = 4;
+    constexpr int T = 256;
     const size_t smem = (size_t)3 * T * P * sizeof(float);
     if (smem > 40 * 1024)
         PN2_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<T, P, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -588,13 +600,19 @@ int fps_impl(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, f
     const bool cluster_ok = (long long)b * 4 <= sm_count();
     const bool use_cluster = n > 8192 || mode == PN2_FPS_CLUSTER || (mode == PN2_FPS_AUTO && n > 4096 && cluster_ok);
     if (use_cluster) {
+        // large sweeps: 8 CTAs per cloud (half the points per thread) while the clusters still fit the GPU in one wave
         if (n <= 2048) return launch_cluster<2>(b, n, m, xyz, idx, new_xyz, s);
         if (n <= 4096) return launch_cluster<4>(b, n, m, xyz, idx, new_xyz, s);
         if (n <= 8192) return launch_cluster<8>(b, n, m, xyz, idx, new_xyz, s);
         if (n <= 16384) return launch_cluster<16>(b, n, m, xyz, idx, new_xyz, s);
         if (n <= 24576) return launch_cluster<24>(b, n, m, xyz, idx, new_xyz, s);
         if (n <= 32768) return launch_cluster<32>(b, n, m, xyz, idx, new_xyz, s);
-        if (n <= 49152) return launch_cluster<48>(b, n, m, xyz, idx, new_xyz, s);  // e.g. a raw 35k-point lidar sweep
+        if (n <= 36864) return launch_cluster<36>(b, n, m, xyz, idx, new_xyz, s);  // a raw ~35k-point lidar sweep: no padded slots
+        if (n <= 40960) return launch_cluster<40>(b, n, m, xyz, idx, new_xyz, s);
+        if (n <= 49152) return launch_cluster<48>(b, n, m, xyz, idx, new_xyz, s);
+        // 8 CTAs per cloud keep clouds of up to 65536 points on chip.  (For smaller clouds the 8-CTA exchange costs more
+        // than the halved per-thread work saves: 16 sweeps x 34720 points 1789 -> 1483 sweeps/s, so 4 CTAs stay the default.)
+        if (n <= 65536) return launch_cluster<32, 8>(b, n, m, xyz, idx, new_xyz, s);
     } else if (mode == 4) {
         if (n <= 2048) return launch_reg<1024, 2>(b, n, m, xyz, idx, new_xyz, s);
         if (n <= 4096) return launch_reg<1024, 4>(b, n, m, xyz, idx, new_xyz, s);

@@ -210,16 +210,39 @@ class PointNet2Backbone(nn.Module):
         self.fp1 = PointNetFeaturePropagation(128, [128, 128, 128])
 
     def forward_fused(self, xyz, points):
-        """-> (B, N, 128) channel-last"""
+        """-> (B, N, 128) channel-last.  Cell lists serve the ball queries (clouds up to grid_max_points()), every 3-NN
+        whose coarse set has >= 512 points, and the processing order of fp1's rows; activations between tensor-core
+        blocks travel as bf16."""
         xyz_cl, feat_cl = to_channel_last(xyz), to_channel_last(points)
-        l1_xyz, l1 = self.sa1.forward_cl(xyz_cl, feat_cl)
-        l2_xyz, l2 = self.sa2.forward_cl(l1_xyz, l1)
-        l3_xyz, l3 = self.sa3.forward_cl(l2_xyz, l2)
-        l4_xyz, l4 = self.sa4.forward_cl(l3_xyz, l3)
-        l3 = self.fp4.forward_cl(l3_xyz, l4_xyz, l3, l4)
-        l2 = self.fp3.forward_cl(l2_xyz, l3_xyz, l2, l3)
-        l1 = self.fp2.forward_cl(l1_xyz, l2_xyz, l1, l2)
-        return self.fp1.forward_cl(xyz_cl, l1_xyz, None, l1)
+        sas = [self.sa1, self.sa2, self.sa3, self.sa4]
+        fps_ = [self.fp4, self.fp3, self.fp2, self.fp1]
+        blocks = [m.folded() for m in sas + fps_]
+        act = torch.bfloat16 if (get_mlp_precision() == "bf16" and all(b.bf16_ok() for b in blocks)) else torch.float32
+        levels, feats, grids = [xyz_cl], [feat_cl], {}
+        for i, sa in enumerate(sas):
+            cur = levels[-1]
+            if 2048 <= cur.shape[1] <= grid_max_points():
+                grids[i] = SpatialGrid(cur, 1.01 * sa.radius)
+            _, new_xyz = fps_gather_cl(cur, sa.npoint)
+            ball = (grids[i].ball_query(sa.radius, sa.nsample, new_xyz) if i in grids
+                    else pointnet2_utils.ball_query(sa.radius, sa.nsample, cur, new_xyz))
+            _, out = sa.forward_cl(cur, feats[-1], geometry=(new_xyz, ball), out_dtype=act)
+            levels.append(new_xyz)
+            feats.append(out)
+        up = feats[4]
+        for j, fp in enumerate(fps_):  # fine level 3, 2, 1, 0
+            lvl = 3 - j
+            fine, coarse = levels[lvl], levels[lvl + 1]
+            order = grids[lvl].order if lvl in grids else None
+            nnw = None
+            # lidar sweeps are far from uniform (rings, dense near the sensor): the cell-list search only beats the
+            # brute-force scan from ~2048 coarse points (0.68 vs 1.23 ms at 34720 x 4096; 0.14 vs 0.07 ms at 4096 x 1024)
+            if 2048 <= coarse.shape[1] <= grid_max_points():
+                nnw = SpatialGrid(coarse, 0.0).three_nn(fine, query_order=order)
+            skip = feats[lvl] if lvl > 0 else None
+            up = fp.forward_cl(fine, coarse, skip, up, nn_weights=nnw, row_order=order if lvl == 0 else None,
+                               out_dtype=act if lvl > 0 else torch.float32)
+        return up
 
     def forward(self, xyz, points):
         if _fusable(self, xyz, points):
