@@ -32,6 +32,42 @@ __device__ __forceinline__ int cell_coord(float p, float o, float inv_h, int dim
     return (int)v;
 }
 
+// Cell size and grid dimensions from the bounding box of a cloud.
+__device__ GridMeta make_meta(const float (&lo)[3], const float (&hi)[3], float h, int n) {
+    // h <= 0: pick the cell from the bounding box so that a cell holds about one point
+    float hh = h;
+    if (!(hh > 0.f)) {
+        float e0 = hi[0] - lo[0], e1 = hi[1] - lo[1], e2 = hi[2] - lo[2];
+        const float emax = fmaxf(e0, fmaxf(e1, e2)), emin = fminf(e0, fminf(e1, e2));
+        const float emid = e0 + e1 + e2 - emax - emin;
+        if (emin < 0.05f * emax)
+            hh = sqrtf(fmaxf(emax * fmaxf(emid, 1e-6f * emax), 1e-30f) / (float)n);  // (nearly) planar cloud
+        else
+            hh = cbrtf(e0 * e1 * e2 / (float)n);
+        hh = fmaxf(hh, 1e-6f);
+    }
+    // grow the cell until the dense table fits; a larger cell only adds candidates, never loses one
+    int d[3];
+    for (int iter = 0; iter < 64; ++iter) {
+        const float inv = 1.0f / hh;
+        long long cells = 1;
+        for (int a = 0; a < 3; ++a) {
+            float e = (hi[a] - lo[a]) * inv;
+            e = fminf(e, (float)(GRID_MAX_DIM - 1));
+            d[a] = (int)e + 1;
+            cells *= d[a];
+        }
+        if (cells <= GRID_MAX_CELLS) break;
+        hh *= 1.26f;
+    }
+    GridMeta m;
+    m.ox = lo[0]; m.oy = lo[1]; m.oz = lo[2];
+    m.inv_h = 1.0f / hh;
+    m.dx = d[0]; m.dy = d[1]; m.dz = d[2];
+    m.ncells = d[0] * d[1] * d[2];
+    return m;
+}
+
 // One CTA per cloud: bounding box, cell of every point, bitonic sort of (cell, index), dense cell-start table.
 __global__ void __launch_bounds__(1024, 1)
 grid_build_kernel(int n, float h, const float *__restrict__ xyz_all, float4 *__restrict__ sorted_all,
@@ -75,36 +111,7 @@ grid_build_kernel(int n, float h, const float *__restrict__ xyz_all, float4 *__r
                 hi[a] = fmaxf(hi[a], red[3 + a][w]);
             }
         }
-        // h <= 0: pick the cell from the bounding box so that a cell holds about one point
-        float hh = h;
-        if (!(hh > 0.f)) {
-            float e0 = hi[0] - lo[0], e1 = hi[1] - lo[1], e2 = hi[2] - lo[2];
-            const float emax = fmaxf(e0, fmaxf(e1, e2)), emin = fminf(e0, fminf(e1, e2));
-            const float emid = e0 + e1 + e2 - emax - emin;
-            if (emin < 0.05f * emax)
-                hh = sqrtf(fmaxf(emax * fmaxf(emid, 1e-6f * emax), 1e-30f) / (float)n);  // (nearly) planar cloud
-            else
-                hh = cbrtf(e0 * e1 * e2 / (float)n);
-            hh = fmaxf(hh, 1e-6f);
-        }
-        // grow the cell until the dense table fits; a larger cell only adds candidates, never loses one
-        int d[3];
-        for (int iter = 0; iter < 64; ++iter) {
-            const float inv = 1.0f / hh;
-            long long cells = 1;
-            for (int a = 0; a < 3; ++a) {
-                float e = (hi[a] - lo[a]) * inv;
-                e = fminf(e, (float)(GRID_MAX_DIM - 1));
-                d[a] = (int)e + 1;
-                cells *= d[a];
-            }
-            if (cells <= GRID_MAX_CELLS) break;
-            hh *= 1.26f;
-        }
-        sm.ox = lo[0]; sm.oy = lo[1]; sm.oz = lo[2];
-        sm.inv_h = 1.0f / hh;
-        sm.dx = d[0]; sm.dy = d[1]; sm.dz = d[2];
-        sm.ncells = d[0] * d[1] * d[2];
+        sm = make_meta(lo, hi, h, n);
         meta_all[b] = sm;
     }
     __syncthreads();
@@ -149,6 +156,118 @@ grid_build_kernel(int n, float h, const float *__restrict__ xyz_all, float4 *__r
             if (order) order[i] = k;
         }
     }
+}
+
+// ---- clouds beyond the single-CTA sort (GRID_MAX_N < n <= GRID_MAX_N_LARGE): counting sort by cell -----------------
+// bounding box + meta (one CTA per cloud), per-cell counts (atomics), exclusive scan of the <= 65536 counts (one CTA per
+// cloud), scatter through per-cell cursors.  The order of the points INSIDE a cell is whatever the atomics produce; the
+// query kernels re-establish the reference's ordering explicitly (rank by index, lexicographic (d, idx)), so their
+// results do not depend on it.
+constexpr int GRID_MAX_N_LARGE = 1 << 18;
+
+__global__ void __launch_bounds__(1024, 1)
+grid_meta_kernel(int n, float h, const float *__restrict__ xyz_all, GridMeta *__restrict__ meta_all) {
+    __shared__ float red[6][32];
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float *xyz = xyz_all + (size_t)b * n * 3;
+    float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int k = t; k < n; k += 1024) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = xyz[3 * k + a];
+            mn[a] = fminf(mn[a], v);
+            mx[a] = fmaxf(mx[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        if (lane == 0) {
+            red[a][warp] = mn[a];
+            red[3 + a][warp] = mx[a];
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = red[a][0];
+            hi[a] = red[3 + a][0];
+            for (int w = 1; w < 32; ++w) {
+                lo[a] = fminf(lo[a], red[a][w]);
+                hi[a] = fmaxf(hi[a], red[3 + a][w]);
+            }
+        }
+        meta_all[b] = make_meta(lo, hi, h, n);
+    }
+}
+
+__device__ __forceinline__ int cell_of(const GridMeta &g, const float *p) {
+    const int cx = cell_coord(p[0], g.ox, g.inv_h, g.dx);
+    const int cy = cell_coord(p[1], g.oy, g.inv_h, g.dy);
+    const int cz = cell_coord(p[2], g.oz, g.inv_h, g.dz);
+    return cx + g.dx * (cy + g.dy * cz);
+}
+
+__global__ void __launch_bounds__(256)
+grid_count_kernel(int n, const float *__restrict__ xyz_all, const GridMeta *__restrict__ meta_all, int32_t *__restrict__ cursor_all) {
+    const int b = blockIdx.y, k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= n) return;
+    const GridMeta g = meta_all[b];
+    atomicAdd(cursor_all + (size_t)b * (GRID_MAX_CELLS + 1) + cell_of(g, xyz_all + ((size_t)b * n + k) * 3), 1);
+}
+
+// exclusive scan of the per-cell counts -> cell_start[0..ncells]; the cursors restart at the cell starts
+__global__ void __launch_bounds__(1024, 1)
+grid_scan_kernel(int n, const GridMeta *__restrict__ meta_all, int32_t *__restrict__ cursor_all, int32_t *__restrict__ cell_start_all) {
+    __shared__ int wsum[32];
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int ncells = meta_all[b].ncells;
+    int32_t *cursor = cursor_all + (size_t)b * (GRID_MAX_CELLS + 1);
+    int32_t *cell_start = cell_start_all + (size_t)b * (GRID_MAX_CELLS + 1);
+    const int per = (ncells + 1023) / 1024;
+    const int c0 = t * per, c1 = min(ncells, c0 + per);
+    int local = 0;
+    for (int c = c0; c < c1; ++c) local += cursor[c];
+    int incl = local;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = wsum[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        wsum[lane] = v;
+    }
+    __syncthreads();
+    int run = incl - local + (warp > 0 ? wsum[warp - 1] : 0);
+    for (int c = c0; c < c1; ++c) {
+        const int cnt = cursor[c];
+        cell_start[c] = run;
+        cursor[c] = run;
+        run += cnt;
+    }
+    if (t == 0) cell_start[ncells] = n;
+}
+
+__global__ void __launch_bounds__(256)
+grid_scatter_kernel(int n, const float *__restrict__ xyz_all, const GridMeta *__restrict__ meta_all, int32_t *__restrict__ cursor_all,
+                    float4 *__restrict__ sorted_all, int32_t *__restrict__ order_all) {
+    const int b = blockIdx.y, k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= n) return;
+    const GridMeta g = meta_all[b];
+    const float *p = xyz_all + ((size_t)b * n + k) * 3;
+    const int pos = atomicAdd(cursor_all + (size_t)b * (GRID_MAX_CELLS + 1) + cell_of(g, p), 1);
+    sorted_all[(size_t)b * n + pos] = make_float4(p[0], p[1], p[2], __int_as_float(k));
+    if (order_all) order_all[(size_t)b * n + pos] = k;
 }
 
 // ---- ball query ------------------------------------------------------------------------------------------
@@ -288,7 +407,12 @@ three_nn_grid_kernel(int n, int m, const float *__restrict__ unknown_all, const 
     const int cx = cell_coord(ux, g.ox, g.inv_h, g.dx), cy = cell_coord(uy, g.oy, g.inv_h, g.dy),
               cz = cell_coord(uz, g.oz, g.inv_h, g.dz);
     bool done = false;
-    for (int ring = 1; ring <= 2 && !done; ++ring) {
+    // rings 1, 2, then doubling while a block is still much cheaper than the brute-force scan (row look-ups + points
+    // grow with the block; in flat or very non-uniform clouds -- lidar sweeps -- the third neighbour is often further
+    // than two cells away, and a 9 x 9 x dz block costs a few dozen row look-ups against m distance tests)
+    for (int ring = 1; !done; ring = ring < 2 ? 2 : 2 * ring) {
+        const long long rows = (long long)min(2 * ring + 1, g.dy) * min(2 * ring + 1, g.dz);
+        if (ring > 2 && (rows * 8 > m || ring > 64)) break;
         t.d1 = t.d2 = t.d3 = INF;
         t.i1 = t.i2 = t.i3 = 0x7fffffff;
         const int x0 = max(cx - ring, 0), x1 = min(cx + ring, g.dx - 1);
@@ -351,18 +475,40 @@ three_nn_grid_kernel(int n, int m, const float *__restrict__ unknown_all, const 
 }  // namespace
 }  // namespace pn2
 
-extern "C" int pn2_grid_max_points(void) { return pn2::GRID_MAX_N; }
+extern "C" int pn2_grid_max_points(void) { return pn2::GRID_MAX_N_LARGE; }
 extern "C" int pn2_grid_table_stride(void) { return pn2::GRID_MAX_CELLS + 1; }
 
 extern "C" int pn2_grid_build(int b, int n, const float *xyz, float cell, float *sorted, int32_t *cell_start, int32_t *order,
                               float *meta, void *stream) {
     using namespace pn2;
     PN2_REQUIRE(b >= 0 && n >= 1, "grid_build: bad dims b=%d n=%d", b, n);
-    if (n > GRID_MAX_N) return set_error(PN2_ERR_UNSUPPORTED, "grid_build: at most %d points per cloud (got %d)", GRID_MAX_N, n);
+    if (n > GRID_MAX_N_LARGE)
+        return set_error(PN2_ERR_UNSUPPORTED, "grid_build: at most %d points per cloud (got %d)", GRID_MAX_N_LARGE, n);
     PN2_REQUIRE(cell == cell, "grid_build: cell size is NaN (pass <= 0 for automatic)");
     if (b == 0) return PN2_OK;
     PN2_REQUIRE(xyz && sorted && cell_start && meta, "grid_build: null pointer");
     PN2_REQUIRE((((uintptr_t)sorted) & 15) == 0, "grid_build: sorted must be 16-byte aligned");
+    if (n > GRID_MAX_N) {
+        // counting sort by cell (several CTAs per cloud); per-cell cursors live in stream-ordered scratch
+        PN2_REQUIRE(b <= 65535, "grid_build: b exceeds the grid limit");
+        cudaStream_t s = (cudaStream_t)stream;
+        const size_t bytes = (size_t)b * (GRID_MAX_CELLS + 1) * sizeof(int32_t);
+        int32_t *cursor = nullptr;
+        PN2_CUDA(scratch_alloc((void **)&cursor, bytes, s));
+        PN2_CUDA(cudaMemsetAsync(cursor, 0, bytes, s));
+        GridMeta *gm = reinterpret_cast<GridMeta *>(meta);
+        grid_meta_kernel<<<b, 1024, 0, s>>>(n, cell, xyz, gm);
+        PN2_LAUNCH_OK("grid_meta_kernel");
+        const dim3 pts(ceil_div(n, 256), b);
+        grid_count_kernel<<<pts, 256, 0, s>>>(n, xyz, gm, cursor);
+        PN2_LAUNCH_OK("grid_count_kernel");
+        grid_scan_kernel<<<b, 1024, 0, s>>>(n, gm, cursor, cell_start);
+        PN2_LAUNCH_OK("grid_scan_kernel");
+        grid_scatter_kernel<<<pts, 256, 0, s>>>(n, xyz, gm, cursor, reinterpret_cast<float4 *>(sorted), order);
+        PN2_LAUNCH_OK("grid_scatter_kernel");
+        PN2_CUDA(cudaFreeAsync(cursor, s));
+        return PN2_OK;
+    }
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
     const size_t smem = (size_t)np2 * sizeof(uint32_t);

@@ -245,7 +245,9 @@ def test_aliases_and_query_and_group(cuda):
 
 GRID_BQ = [("uniform", 1, 32768, 256, 0.03, 32, 1.01), ("uniform", 1, 16384, 512, 0.04, 32, 1.01), ("scannet", 2, 8192, 1024, 0.1, 32, 1.01), ("scannet", 2, 8192, 1024, 0.2, 32, 1.01), ("dup", 2, 4096, 300, 0.1, 16, 1.5),
            ("lattice", 1, 3000, 100, 0.25, 64, 1.01), ("uniform", 1, 2500, 40, 10.0, 128, 1.01), ("uniform", 2, 5000, 300, 0.05, 16, 1.01),
-           ("dup", 2, 1024, 256, 0.3, 32, 1.01), ("uniform", 1, 700, 64, 0.3, 200, 0.3), ("scannet", 1, 8192, 512, 0.8, 32, 1.01)]
+           ("dup", 2, 1024, 256, 0.3, 32, 1.01), ("uniform", 1, 700, 64, 0.3, 200, 0.3), ("scannet", 1, 8192, 512, 0.8, 32, 1.01),
+           # beyond the single-CTA sort: counting sort by cell (order inside a cell unspecified, results identical)
+           ("uniform", 2, 34720, 300, 0.03, 32, 1.01), ("dup", 1, 40000, 200, 0.05, 16, 1.01), ("uniform", 1, 70000, 128, 0.02, 32, 1.5)]
 
 
 @pytest.mark.parametrize("kind,B,N,M,r,K,cellf", GRID_BQ)
@@ -264,7 +266,8 @@ def test_grid_ball_query_bit_exact(cuda, kind, B, N, M, r, K, cellf):
 
 
 GRID_NN = [("scannet", 2, 8192, 1024, 0.1), ("scannet", 2, 8192, 1024, 0.0), ("uniform", 2, 3000, 600, 0.0), ("lattice", 2, 900, 500, 0.3),
-           ("dup", 2, 2000, 700, 0.05), ("uniform", 1, 500, 2, 0.0), ("uniform", 1, 400, 5000, 0.02), ("scannet", 1, 4096, 64, 0.0)]
+           ("dup", 2, 2000, 700, 0.05), ("uniform", 1, 500, 2, 0.0), ("uniform", 1, 400, 5000, 0.02), ("scannet", 1, 4096, 64, 0.0),
+           ("uniform", 1, 1500, 40000, 0.0)]  # a known set beyond the single-CTA sort
 
 
 @pytest.mark.parametrize("kind,B,n,m,cell", GRID_NN)
