@@ -481,14 +481,14 @@ def run_ours(args):
                                           "tcgen05 MLP over %d rows)" % (B * NPOINTS),
                                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                                 # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full at batch 32
-                                # (profiles/r1_tc_mlp_v4_ncu_full_summary.csv, last row); the 22 MB of logits stay in L2
-                                "traffic": 19.12e6 if B == 32 else None,
+                                # (profiles/r1_tc_mlp_v5_ncu_full_summary.csv, last row); the 22 MB of logits stay in L2
+                                "traffic": 19.14e6 if B == 32 else None,
                                 "algorithmic_bytes": B * NPOINTS * (12 + 12 + 24 + 4 * NUM_CLASSES) + B * 1024 * 128 * 2,
                                 "ms": ms, "share_of_step_one_at_a_time": ms / (serial_ms / args.steps),
                                 "peak_source": pk["source"] + " bf16 sustained (kernel timed inside eager steps, alone on the GPU)",
                                 "note": "largest full-GPU kernel of the step; its 128-row tiles are a latency chain (gather -> 5 x [MMA, "
                                         "TMEM epilogue]) overlapped only across the 3 CTAs of an SM, not tensor bound "
-                                        "(ncu: tensor pipe 14 % active, issue slots 40 %, l1tex 44 %)"}
+                                        "(ncu: tensor pipe 16 % active, issue slots 40 %, l1tex 43 %)"}
         if world == 1 and not args.no_extras:
             line["kernels"] = op_rooflines(device, B, pk)
             line["ref_gpu"] = time_ref_gpu(model, device, B)
