@@ -236,7 +236,7 @@ int pn2_label_counts(int b, int n, int num_classes, const int32_t *select, const
 /* ---- tuning ---- */
 /* Kernel policy of furthest point sampling for 4096 < n <= 8192 points per cloud.  Process-wide; read when a launch is
  * issued (or captured into a CUDA graph).  The sampled indices are identical under every policy.
- *   PN2_FPS_AUTO     a 4-CTA cluster per cloud while 4*b CTAs fit the GPU (lowest latency of a single batch: 0.45 ms for
+ *   PN2_FPS_AUTO     a 4-CTA cluster per cloud while 4*b CTAs fit the GPU (lowest latency of a single batch: 0.43 ms for
  *                    8192 -> 1024), else ONE_CTA;
  *   PN2_FPS_ONE_CTA  one 256-thread CTA per cloud (0.54 ms): it occupies b SMs instead of 4*b, which is what counts when
  *                    several batches are in flight (measured: 44.2 k -> 52.2 k scenes/s at the time, profiles/README.md);
