@@ -4,7 +4,7 @@
  * multi-view 2D->3D feature lifting of
  * ChengnanYu/Multi-modal-Learning-on-3D-Point-Clouds.
  *
- * Conventions (mirroring the reference's launcher seam, utils/src/*_gpu.h):
+ * Conventions (mirroring the reference's launcher seam, the *_gpu.h files under utils/src):
  *   - every pointer is a DEVICE pointer into memory the caller owns; outputs
  *     are caller-allocated; nothing is retained between calls;
  *   - tensors are dense, row-major, fp32 / int32 exactly as the reference's;

@@ -2,22 +2,27 @@
 // operands, fp32 accumulation in TMEM).  Same operator contract as row_mlp.cu (the fp32 path); outputs
 // agree with it within bf16 rounding (2e-2 relative, BASELINE.json north_star; measured ~4e-3).
 //
-// PERSISTENT CTAs (3-4 per SM) walk tiles of 128 rows (= UMMA M); barriers, TMEM and biases are set up once.
+// PERSISTENT CTAs (2-4 per SM) walk tiles of 128 rows (= UMMA M); barriers, TMEM and biases are set up once.
 // For every layer
 //     D[128 x N] (TMEM, fp32) = A[128 x K] (smem, bf16, K-major, 128B swizzle) * W[N x K]^T (smem, same layout)
 //   * A of layer 0 is written by the gather (grouped features + centred xyz, or 3-NN interpolation + skip rows),
 //     in CHUNKS of whole 64-column k-blocks: the MMAs of a chunk accumulate into TMEM while the buffer is refilled,
-//     so inputs of any width stream through a 32-64 KB operand buffer (fp4's 768 / 1536 channels included);
+//     so inputs of any width stream through a 32-64 KB operand buffer (fp4's 768 / 1536 channels included).  A last
+//     k-block of only 16 columns (the xyz / colour tail) lives in its own 4 KB un-swizzled region and rides with the
+//     last chunk.  bf16 feature rows are gathered warp-cooperatively (consecutive lanes = consecutive 16 bytes of one
+//     source row); the index-level loads of tile i+1 are issued while the layers of tile i run;
 //   * A of layer l+1 is written by the epilogue of layer l straight from TMEM (tcgen05.ld, bias, ReLU, bf16 pack --
 //     packed f32x2 / bf16x2 math) into the SAME buffer: all MMAs of a layer are committed before its epilogue runs;
 //   * W arrives as pre-swizzled tiles (packed once by pn2_mlp_pack_bf16; 64/128/256 rows chosen for residency)
 //     through a 2-4-stage ring of bulk-async copies (cp.async.bulk = TMA unit, mbarrier complete_tx) that runs ahead
 //     across layer AND tile boundaries;
-//   * tcgen05.mma is issued by ONE thread; the final max over nsample is a CREDUX per column inside each epilogue
-//     warp (TMEM lane == row, so warp w holds exactly the 32 samples of one centroid when nsample = 32);
-//   * activations that only travel between such blocks are read / written as bf16 (PN2_FLAG_*): a gathered 16-byte
-//     load is then a whole operand chunk (SA: pure copy), halving gather traffic; FP rows can be processed in a
-//     spatially sorted order (row_perm) so neighbouring rows share their three coarse rows in L1.
+//   * tcgen05.mma is issued by one elected lane of a warp that walks the schedule in uniform control flow;
+//   * SA blocks compute their LAST layer transposed (D^T = W A^T: channels on TMEM lanes, the 128 samples on columns),
+//     so the max over nsample is a register-local tree and bias + ReLU are applied once per group; FP blocks store rows
+//     with 128-bit stores, or only the arg-max of the row (PN2_FLAG_OUT_ARGMAX);
+//   * activations that only travel between such blocks are read / written as bf16 (PN2_FLAG_*), halving gather
+//     traffic; FP rows can be processed in a spatially sorted order (row_perm) so neighbouring rows share their three
+//     coarse rows in L1.
 // Warp roles: 0-3 gather + epilogue (TMEM lanes 32w..32w+31), 4 weight producer, 5 TMEM alloc + MMA issue.
 // Measured behaviour and the experiments behind these choices: profiles/README.md.
 #include <cuda_bf16.h>
@@ -598,9 +603,8 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
     // phases ahead of a waiting warp); then the TMEM base slot, exchange, biases
     const int S = p.stages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 8);
-    float *xchg = reinterpret_cast<float *>(tmem_slot + 4);  // SA: [4 warps][32] maxima for nsample > 32
-    long long *srow = reinterpret_cast<long long *>(xchg);   // FP: destination row of each tile row (-1 = past the end)
-    float *sbias = xchg + 4 * 32 * 2;                        // all layers' biases, zero padded to npad
+    long long *srow = reinterpret_cast<long long *>(tmem_slot + 4);       // FP: destination row of each tile row (-1 = past the end)
+    float *sbias = reinterpret_cast<float *>(srow) + 4 * 32 * 2;          // all layers' biases, zero padded to npad
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + MAX_STAGES);
@@ -1060,7 +1064,7 @@ struct Plan {
 };
 
 constexpr size_t TC_SMEM_LIMIT = 227 * 1024;
-constexpr int TC_TAIL_BYTES = (2 * MAX_STAGES + 8) * 8 + 16 + 4 * 32 * 8;  // barriers, TMEM slot, exchange / row table (+ biases)
+constexpr int TC_TAIL_BYTES = (2 * MAX_STAGES + 8) * 8 + 16 + 4 * 32 * 8;  // barriers, TMEM slot, row table (+ biases)
 
 Plan make_plan_capped(const pn2_mlp *mlp, int nblk_cap) {
     Plan P = {};
