@@ -46,6 +46,26 @@ def test_abi_version_and_error_string_without_gpu():
     assert lib.pn2_furthest_point_sampling(0, 8, 4, None, None, None, None) == 0  # empty batch: no-op
 
 
+def test_argument_validation_of_the_wider_entry_points_without_gpu():
+    """Same for the entry points added around the nine operators: bad arguments are refused with a message before any
+    CUDA call; empty batches are no-ops."""
+    from pn2_b200 import _lib
+    lib = _lib.load()
+    err = lib.pn2_last_error
+    assert lib.pn2_label_counts(2, 8, 0, None, None, None, None, None, None, None) == 1 and b"classes" in err()
+    assert lib.pn2_label_counts(2, 8, 21, None, None, None, None, None, None, None) == 1 and b"null pointer" in err()
+    assert lib.pn2_label_counts(0, 8, 21, None, None, None, None, None, None, None) == 0
+    assert lib.pn2_voxel_first_index(2, 8, None, None, ctypes.c_float(0.0), None, None, None, None, None) == 1 and b"res" in err()
+    assert lib.pn2_voxel_first_index(0, 8, None, None, ctypes.c_float(0.02), None, None, None, None, None) == 0
+    assert lib.pn2_inverse_index(1, 0, 4, None, None, None, None) == 1 and b"bad dims" in err()
+    assert lib.pn2_scatter_rows_det(1, 4, 8, 10, 3, None, None, None, None, None, None) == 1 and b"multiple of div" in err()
+    assert lib.pn2_scatter_rows_det(1, 4, 8, 9, 2, None, None, None, None, None, None) == 1 and b"div" in err()
+    assert lib.pn2_lift_setup(3, None, None, None, None, None, None, None) == 1 and b"null pointer" in err()
+    assert lib.pn2_lift_setup(0, None, None, None, None, None, None, None) == 0
+    assert lib.pn2_grid_build(1, (1 << 18) + 1, None, ctypes.c_float(0.1), None, None, None, None, None) == 2 and b"at most" in err()
+    assert lib.pn2_grid_max_points() == 1 << 18
+
+
 def test_fps_policy_switch_returns_previous_value():
     from pn2_b200 import _lib
     lib = _lib.load()
