@@ -32,7 +32,13 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=4)
     ap.add_argument("--npoints", type=int, default=8192)
     ap.add_argument("--model", default="msg", choices=["msg", "ssg"])
+    ap.add_argument("--deterministic", action="store_true",
+                    help="bit-reproducible training: fixed-order backwards of gather / grouping / interpolation "
+                         "(pn2_scatter_rows_det) and torch's deterministic algorithms")
     args = ap.parse_args()
+    if args.deterministic:
+        os.environ.setdefault("CUBLAS_WORKSPACE_CONFIG", ":4096:8")
+        torch.use_deterministic_algorithms(True, warn_only=True)  # pn2_b200.pointnet2_utils follows this switch
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -55,7 +61,8 @@ def main():
         target = (pts[:, :, 2].clamp(0, 2.69) / 2.7 * 20).long() + 1
         target[torch.rand(target.shape, generator=g).to(device) < 0.05] = 0
         weights = torch.ones_like(target, dtype=torch.float32)
-        second = torch.randn(B, 128, N, device=device) if args.model == "msg" else pts[:, :, 3:].permute(0, 2, 1).contiguous()
+        second = (torch.randn(B, 128, N, generator=g).to(device) if args.model == "msg"
+                  else pts[:, :, 3:].permute(0, 2, 1).contiguous())
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
@@ -70,8 +77,9 @@ def main():
     t = torch.tensor([sum(t_steps[2:]) / max(len(t_steps) - 2, 1)], dtype=torch.float64, device=device)
     sharding.max_over_ranks(t)
     if rank == 0:
-        print("model=%s world=%d batch/gpu=%d npoints=%d  step %.1f ms  -> %.1f scenes/s   loss %.4f -> %.4f" % (
-            args.model, world, B, N, float(t) * 1e3, world * B / float(t), losses[0], losses[-1]))
+        print("model=%s world=%d batch/gpu=%d npoints=%d  step %.1f ms  -> %.1f scenes/s   loss %.4f -> %.9f%s" % (
+            args.model, world, B, N, float(t) * 1e3, world * B / float(t), losses[0], losses[-1],
+            "  (deterministic)" if args.deterministic else ""))
     if world > 1:
         dist.destroy_process_group()
 
