@@ -250,6 +250,8 @@ int pn2_set_fps_policy(int policy);
 void pn2_debug_set_fps_mode(int mode);
 /* The next pn2_*_bf16 launch on this thread records clock64() phase stamps of CTA 0 into buf (>= 512 int64, device; MMA issuer stamps from [256]). */
 void pn2_debug_set_tc_timestamps(long long *buf);
+/* Caps the resident CTAs per SM of the tensor-core MLP kernel (bench.py --tc-max-ctas; default 8 = no cap). */
+void pn2_debug_set_tc_max_ctas(int n);
 
 #ifdef __cplusplus
 }

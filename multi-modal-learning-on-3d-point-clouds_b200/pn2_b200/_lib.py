@@ -70,6 +70,7 @@ _OTHER = {
     "pn2_set_fps_policy": ([_c_int], _c_int),
     "pn2_debug_set_fps_mode": ([_c_int], None),
     "pn2_debug_set_tc_timestamps": ([_vp], None),
+    "pn2_debug_set_tc_max_ctas": ([_c_int], None),
     "pn2_mlp_pack_bf16_size": ([ctypes.POINTER(Pn2Mlp)], ctypes.c_longlong),
 }
 
