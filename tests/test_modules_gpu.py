@@ -65,7 +65,8 @@ def scene_batch(B, N, seed, D):
 
 
 SA_CASES = [(512, 0.1, 32, 3, [32, 32, 64], 2048), (128, 0.2, 32, 64, [64, 64, 128], 512), (16, 0.8, 32, 256, [256, 256, 512], 64),
-            (64, 0.4, 16, 0, [16, 32], 300), (40, 0.3, 64, 5, [24, 21], 1000), (8, 0.5, 128, 2, [8], 700)]
+            (64, 0.4, 16, 0, [16, 32], 300), (40, 0.3, 64, 5, [24, 21], 1000), (8, 0.5, 128, 2, [8], 700),
+            (32, 0.3, 8, 4, [16, 40], 500), (16, 0.5, 1, 3, [8, 8], 200), (24, 0.4, 2, 13, [32, 160], 400)]
 
 
 @pytest.mark.parametrize("npoint,radius,nsample,D,mlp,N", SA_CASES)
