@@ -589,6 +589,7 @@ int fps_impl(int b, int n, int m, const float *xyz, float *temp, int32_t *idx, f
         case 512: return launch_reg_small<512>(b, n, m, xyz, idx, new_xyz, s);
         default: break;
     }
+    if (n == 1024 && fps_force_mode() != 4) return launch_few<256, 1>(b, n, m, xyz, idx, new_xyz, s);  // 4 points per thread
     if (n <= 1024) return launch_reg<1024, 1>(b, n, m, xyz, idx, new_xyz, s);
     // 1024 < n <= 8192.  One CTA per cloud = the 256-thread kernel (fps_few_kernel): 0.12 / 0.17 / 0.54 ms for
     // 2048->512 / 4096->512 / 8192->1024, faster than both alternatives up to 4096 points.  At 4096 < n <= 8192 the
