@@ -233,6 +233,16 @@ int pn2_voxel_first_index(int b, int n, const float *xyz, const unsigned char *m
 int pn2_label_counts(int b, int n, int num_classes, const int32_t *select, const int32_t *count, const unsigned char *mask,
                      const long long *target, const unsigned char *pred, long long *out, void *stream);
 
+/* ---- proposal layer of the nuScenes detector ----
+ * model/pointmaskrcnn.py:233-288 iou_spheres: spheres (x, y, z, r), 16-byte aligned rows -> iou (m,n) fp32, every
+ * operation rounded to fp32 in the reference's order. */
+int pn2_sphere_iou(int m, int n, const float *spheres_a, const float *spheres_b, float *iou, void *stream);
+/* model/pointmaskrcnn.py:290-321 nms, b independent problems of up to n <= 4096 spheres (count_in (b) int32 or NULL = n
+ * each): visit by descending score (equal scores: lower index first), keep a sphere and drop every later one whose IoU
+ * with it is > threshold.  keep (b,n) int32 = kept indices in selection order, padded with -1; count_out (b) int32. */
+int pn2_sphere_nms(int b, int n, const float *spheres, const float *scores, const int32_t *count_in, float threshold,
+                   int32_t *keep, int32_t *count_out, void *stream);
+
 /* ---- tuning ---- */
 /* Kernel policy of furthest point sampling for 4096 < n <= 8192 points per cloud.  Process-wide; read when a launch is
  * issued (or captured into a CUDA graph).  The sampled indices are identical under every policy.

@@ -42,6 +42,8 @@ _SIGNATURES = {
     "pn2_three_nn": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "pn2_three_interpolate": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "pn2_three_interpolate_grad": [_c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
+    "pn2_sphere_iou": [_c_int, _c_int, _vp, _vp, _vp, _vp],
+    "pn2_sphere_nms": [_c_int, _c_int, _vp, _vp, _vp, _c_float, _vp, _vp, _vp],
     "pn2_lift_setup": [_c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pn2_voxel_first_index": [_c_int, _c_int, _vp, _vp, _c_float, _vp, _vp, _vp, _vp, _vp],
     "pn2_label_counts": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

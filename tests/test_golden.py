@@ -58,3 +58,21 @@ def test_pc_util_restatement_matches_reference(name):
     np.testing.assert_array_equal(uvlabel, gold[name + "/uvlabel"])
     np.testing.assert_array_equal(nvox, gold[name + "/nvox"])
     assert uvidx.dtype == np.float32  # the reference computes the voxel index in float32
+
+
+# ---- proposal-layer geometry: golden vectors from the reference's own iou_spheres / nms (torch on the CPU) ----
+RPN_NPZ = os.path.join(HERE, "golden", "rpn_r1.npz")
+spec_rpn = importlib.util.spec_from_file_location("make_golden_rpn", os.path.join(HERE, "golden", "make_golden_rpn.py"))
+mgr = importlib.util.module_from_spec(spec_rpn)
+spec_rpn.loader.exec_module(mgr)
+
+
+@pytest.mark.parametrize("name", list(mgr.CASES))
+def test_rpn_restatement_matches_reference(name):
+    from oracle import rpn_ref
+    gold = np.load(RPN_NPZ)
+    spheres, scores = mgr.rpn_inputs(name)
+    iou = rpn_ref.iou_spheres(spheres, spheres)
+    np.testing.assert_allclose(iou, gold[name + "/iou"], rtol=2e-6, atol=1e-7)  # torch.norm's summation order is its own
+    assert ((iou > 0) == (gold[name + "/iou"] > 0)).all()
+    np.testing.assert_array_equal(rpn_ref.nms(spheres, scores, mgr.CASES[name][2]), gold[name + "/keep"])
