@@ -42,13 +42,14 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks / throttle reasons; only samples that arrive between begin() and end() are used.
-    Started well before the timed region (nvidia-smi needs a few hundred ms to come up)."""
+    """Samples nvidia-smi SM clocks / throttle reasons; only samples that arrive inside a begin()..end() window are used
+    (one window per timed region: the device-resident leg and the end-to-end legs).  Started well before the first
+    timed region (nvidia-smi needs a few hundred ms to come up)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index, period_ms=20):
-        self.rows, self.proc, self.t0, self.t1 = [], None, None, None
+        self.rows, self.proc, self.windows = [], None, []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", str(period_ms)], stdout=subprocess.PIPE,
@@ -68,10 +69,10 @@ class ClockSampler:
             time.sleep(0.02)
 
     def begin(self):
-        self.t0 = time.perf_counter()
+        self.windows.append([time.perf_counter(), None])
 
     def end(self):
-        self.t1 = time.perf_counter()
+        self.windows[-1][1] = time.perf_counter()
 
     def close(self):
         if self.proc is not None:
@@ -82,7 +83,7 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, r in self.rows:
-            if self.t0 is None or ts < self.t0 or ts > (self.t1 or ts) + 0.03:
+            if not any(a <= ts <= (b if b is not None else ts) + 0.03 for a, b in self.windows):
                 continue
             try:
                 sm.append(float(r[0]))
@@ -368,7 +369,6 @@ def run_ours(args):
         b.record()
         barrier()
         clocks.end()
-        clocks.close()
         total_ms = a.elapsed_time(b)
         launches = _lib.launch_count() - launches0
         if graphed is not None:
@@ -428,7 +428,9 @@ def run_ours(args):
             return a.elapsed_time(b)
 
         # (1) the reference protocol: the full fp32 logits come back (train_scannet_semseg.py:204 `pred.cpu().numpy()`)
+        clocks.begin()
         e2e_ms = run_e2e(pipe, graphed, (B, NPOINTS, NUM_CLASSES), torch.float32, model)
+        clocks.end()
         # (2) predict(): the arg-max the evaluation loop takes from those logits, fused into the head kernel; 1 byte per point
         e2e_lab_ms = 0.0
         if model.can_fuse_labels() and not args.no_graph:
@@ -441,7 +443,10 @@ def run_ours(args):
                     graphed_l.run(devs[i % n_rot][:, :3], devs[i % n_rot][:, 3:])
             if pipe_l is not None:
                 pipe_l.join()
+            clocks.begin()
             e2e_lab_ms = run_e2e(pipe_l, graphed_l, (B, NPOINTS), torch.uint8, model.predict)
+            clocks.end()
+        clocks.close()
 
     t = torch.tensor([total_ms, e2e_ms, e2e_lab_ms], dtype=torch.float64, device=device)
     if world > 1:
