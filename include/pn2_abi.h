@@ -262,6 +262,9 @@ void pn2_debug_set_fps_mode(int mode);
 void pn2_debug_set_tc_timestamps(long long *buf);
 /* Caps the resident CTAs per SM of the tensor-core MLP kernel (bench.py --tc-max-ctas; default 8 = no cap). */
 void pn2_debug_set_tc_max_ctas(int n);
+/* Kernel choice of pn2_three_interpolate: 0 automatic, 1 tiled kernels only, 32 the lane-along-channel kernel wherever it
+ * applies, + 256 for its 256-thread form (two CTAs per SM).  scripts/interp_sweep.py. */
+void pn2_debug_set_interp_mode(int mode);
 
 #ifdef __cplusplus
 }

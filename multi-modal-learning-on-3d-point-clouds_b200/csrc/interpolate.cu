@@ -11,6 +11,8 @@
 // read once (the reference re-reads them for every channel) and the stores of a warp are coalesced.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace pn2 {
 namespace {
 
@@ -149,6 +151,7 @@ three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points, 
 // the stores of a warp coalesced along n.  HBM sees the coarse features once per CTA slice, idx/weight once per channel
 // chunk, and the output once.
 constexpr int TS_THREADS = 256;
+constexpr int LC_GRAN = 64;  // points per warp granule of the lane-along-channel kernel
 
 template <int CC, int PAD>
 __global__ void __launch_bounds__(TS_THREADS, 3)
@@ -281,6 +284,182 @@ int launch_interp_smem(int b, int c, int m, int n, const float *points, const in
     return PN2_OK;
 }
 
+// Lane-along-channel kernel (coarse sets up to ~1500 points with 32 channels per tile).
+//
+// The tiled kernel above spends its shared-memory wavefronts on bank conflicts: each lane reads 16 bytes of its OWN random
+// coarse row, so the 8 lanes of a quarter warp collide in the 8 four-bank groups (ncu: 5.2 M conflict wavefronts of 8.6 M,
+// LSU data pipe 91 % busy while active; profiles/r1_hbm_ops_ncu_full_summary.csv).  Here the LPR = CC/4 lanes of a group
+// read the CC channels of ONE coarse row (for CC = 32 a quarter warp reads one whole 128-byte row: conflict free whatever
+// the indices are).  A group owns EIGHT CONSECUTIVE points of a granule (one per step) and keeps its 4 channels x 8 points
+// in registers; chunk q of a row holds the channels q, q + LPR, q + 2 LPR, q + 3 LPR.  Rows are XOR-swizzled by (k >> 2) so
+// that the transposing stage is conflict free as well.  idx / weight travel through a per-warp record buffer ({k0,k1,k2,-}
+// {w0,w1,w2,-} per point: two LDS.128 per step, broadcast inside a group, slots XOR-swizzled by the group number so the
+// groups fall into different banks); the next granule's records are fetched while the current one is computed.
+// Each channel's 8 points of a group leave as one 256-bit store (a full 32-byte sector).
+// Persistent CTAs: the (cloud, channel tile, granule) space is cut into gridDim.x contiguous ranges, so a CTA stages at
+// most two tiles more than it has whole (cloud, tile) pairs and there is no partial last wave.
+
+// Transposing stage: tile4[k][q ^ ((k >> 2) & (LPR - 1))] = channels q + LPR * {0,1,2,3} of coarse point k (zero beyond nc).
+// Vector form: an item = four consecutive points of four channel rows (four coalesced 128-bit loads) -> four swizzled
+// 16-byte chunks; a thread issues the loads of four items before the first store, so 16 loads are in flight per thread.
+template <int LPR, int T>
+__device__ __forceinline__ void lac_stage_tile(float4 *tile4, const float *__restrict__ f, int m, int nc, int tid) {
+    if ((m & 3) == 0 && ((uintptr_t)f & 15) == 0) {
+        const int m4 = m >> 2;
+        const int items = LPR * m4;
+        for (int base = 0; base < items; base += 4 * T) {
+            float4 r[4][4];
+            int cqs[4], is[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int it = base + u * T + tid;
+                const int cq = it / m4, i = it - cq * m4;
+                cqs[u] = cq;
+                is[u] = i;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    r[u][e] = it < items && cq + LPR * e < nc ? __ldg(reinterpret_cast<const float4 *>(f + (size_t)(cq + LPR * e) * m) + i)
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (base + u * T + tid >= items) continue;
+                float4 *d = tile4 + (size_t)(4 * is[u]) * LPR + (cqs[u] ^ (is[u] & (LPR - 1)));
+                d[0] = make_float4(r[u][0].x, r[u][1].x, r[u][2].x, r[u][3].x);
+                d[LPR] = make_float4(r[u][0].y, r[u][1].y, r[u][2].y, r[u][3].y);
+                d[2 * LPR] = make_float4(r[u][0].z, r[u][1].z, r[u][2].z, r[u][3].z);
+                d[3 * LPR] = make_float4(r[u][0].w, r[u][1].w, r[u][2].w, r[u][3].w);
+            }
+        }
+    } else {
+        for (int cq = 0; cq < LPR; ++cq)
+            for (int k = tid; k < m; k += T) {
+                float4 v;
+                v.x = cq < nc ? __ldg(f + (size_t)cq * m + k) : 0.f;
+                v.y = cq + LPR < nc ? __ldg(f + (size_t)(cq + LPR) * m + k) : 0.f;
+                v.z = cq + 2 * LPR < nc ? __ldg(f + (size_t)(cq + 2 * LPR) * m + k) : 0.f;
+                v.w = cq + 3 * LPR < nc ? __ldg(f + (size_t)(cq + 3 * LPR) * m + k) : 0.f;
+                tile4[(size_t)k * LPR + (cq ^ ((k >> 2) & (LPR - 1)))] = v;
+            }
+    }
+}
+
+template <int CC, int T>
+__global__ void __launch_bounds__(T, 512 / T)
+three_interpolate_lac_kernel(int c, int m, int n, int chunks, int gpp, long long total_gran,
+                             const float *__restrict__ points, const int32_t *__restrict__ idx,
+                             const float *__restrict__ weight, float *__restrict__ out) {
+    constexpr int LPR = CC / 4;    // lanes per coarse row = lanes per group
+    constexpr int PPI = 32 / LPR;  // groups per warp
+    constexpr int GRAN = LC_GRAN;  // points per warp granule
+    constexpr int RUNS = GRAN / (8 * PPI);  // eight-point runs per group and granule
+    constexpr int WARPS = T / 32;
+    constexpr int FPL = GRAN / 32;  // records fetched per lane
+    extern __shared__ __align__(16) float4 lac_smem[];
+    float4 *tile4 = lac_smem;                                            // [m][LPR]
+    int4 *rec_i = reinterpret_cast<int4 *>(lac_smem + (size_t)m * LPR);  // [WARPS][GRAN]
+    float4 *rec_w = reinterpret_cast<float4 *>(rec_i + WARPS * GRAN);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int j = lane % LPR, g = lane / LPR;
+    int4 *my_i = rec_i + warp * GRAN;
+    float4 *my_w = rec_w + warp * GRAN;
+
+    long long gq = total_gran * blockIdx.x / gridDim.x;
+    const long long gq_end = total_gran * (blockIdx.x + 1) / gridDim.x;
+    while (gq < gq_end) {
+        const int pair = (int)(gq / gpp);
+        const int gi0 = (int)(gq - (long long)pair * gpp);
+        const long long seg_end = min(gq_end, (long long)(pair + 1) * gpp);
+        const int gi1 = gi0 + (int)(seg_end - gq);
+        gq = seg_end;
+        const int bb = pair / chunks, c0 = (pair - bb * chunks) * CC;
+        const int nc = min(CC, c - c0);
+        const int32_t *idb = idx + (size_t)bb * n * 3;
+        const float *wb = weight + (size_t)bb * n * 3;
+        float *ob = out + ((size_t)bb * c + c0) * n;
+        int rk[FPL][3];
+        float rw[FPL][3];
+        auto fetch = [&](int gi) {
+#pragma unroll
+            for (int h = 0; h < FPL; ++h) {
+                const int p = gi * GRAN + lane + 32 * h;
+                const bool ok = gi < gi1 && p < n;
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    rk[h][e] = ok ? __ldg(idb + (size_t)p * 3 + e) : 0;
+                    rw[h][e] = ok ? __ldg(wb + (size_t)p * 3 + e) : 0.f;
+                }
+            }
+        };
+        fetch(gi0 + warp);  // in flight during the stage
+        __syncthreads();    // every warp is done with the previous tile
+        lac_stage_tile<LPR, T>(tile4, points + ((size_t)bb * c + c0) * m, m, nc, tid);
+        __syncthreads();
+        for (int gi = gi0 + warp; gi < gi1; gi += WARPS) {
+            __syncwarp();  // the previous granule's steps have read their records
+#pragma unroll
+            for (int h = 0; h < FPL; ++h) {
+                const int q = lane + 32 * h;
+                const int slot = q ^ ((q >> 3) & (PPI - 1));
+                my_i[slot] = make_int4(rk[h][0], rk[h][1], rk[h][2], 0);
+                my_w[slot] = make_float4(rw[h][0], rw[h][1], rw[h][2], 0.f);
+            }
+            __syncwarp();
+            fetch(gi + WARPS);
+#pragma unroll
+            for (int run = 0; run < RUNS; ++run) {
+                // the group's eight points, within the granule (the PPI groups of a warp own consecutive runs)
+                const int q0 = 8 * PPI * run + 8 * g;
+                float acc[4][8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int slot = (q0 + s) ^ (g & (PPI - 1));
+                    const int4 kk = my_i[slot];
+                    const float4 ww = my_w[slot];
+                    const float4 a0 = tile4[(size_t)kk.x * LPR + (j ^ ((kk.x >> 2) & (LPR - 1)))];
+                    const float4 a1 = tile4[(size_t)kk.y * LPR + (j ^ ((kk.y >> 2) & (LPR - 1)))];
+                    const float4 a2 = tile4[(size_t)kk.z * LPR + (j ^ ((kk.z >> 2) & (LPR - 1)))];
+                    // the reference's contraction (K8): fma(w2, f2, fma(w0, f0, rn(w1 * f1)))
+                    acc[0][s] = __fmaf_rn(ww.z, a2.x, __fmaf_rn(ww.x, a0.x, __fmul_rn(ww.y, a1.x)));
+                    acc[1][s] = __fmaf_rn(ww.z, a2.y, __fmaf_rn(ww.x, a0.y, __fmul_rn(ww.y, a1.y)));
+                    acc[2][s] = __fmaf_rn(ww.z, a2.z, __fmaf_rn(ww.x, a0.z, __fmul_rn(ww.y, a1.z)));
+                    acc[3][s] = __fmaf_rn(ww.z, a2.w, __fmaf_rn(ww.x, a0.w, __fmul_rn(ww.y, a1.w)));
+                }
+                const int p = gi * GRAN + q0;  // element u of the lane's chunk is channel j + LPR * u
+                if (p < n) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (j + LPR * u < nc)
+                            asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ob + (size_t)(j + LPR * u) * n + p),
+                                         "f"(acc[u][0]), "f"(acc[u][1]), "f"(acc[u][2]), "f"(acc[u][3]), "f"(acc[u][4]),
+                                         "f"(acc[u][5]), "f"(acc[u][6]), "f"(acc[u][7])
+                                         : "memory");
+                }
+            }
+        }
+    }
+}
+
+int g_interp_mode = 0;  // developer knob (pn2_debug_set_interp_mode): 0 auto, 1 tiled kernels only, 32 the lane-along-channel
+                        // kernel wherever it applies (+ 256: 256-thread CTAs, two per SM)
+
+inline size_t lac_smem_bytes(int m, int cc, int threads) { return (size_t)m * cc * 4 + (size_t)(threads / 32) * LC_GRAN * 32; }
+inline bool lac_fits(int m, int cc, int threads) { return (512 / threads) * (lac_smem_bytes(m, cc, threads) + 1024) <= 233472; }
+
+template <int CC, int T>
+int launch_interp_lac(int b, int c, int m, int n, const float *points, const int32_t *idx, const float *weight, float *out,
+                      cudaStream_t s) {
+    const int chunks = ceil_div(c, CC);
+    const int gpp = ceil_div(n, LC_GRAN);
+    const long long total = (long long)b * chunks * gpp;
+    const size_t smem = lac_smem_bytes(m, CC, T);
+    const int grid = (int)std::min<long long>((long long)(512 / T) * sm_count(), std::max<long long>(1, total / (T / 32)));
+    PN2_CUDA(cudaFuncSetAttribute(three_interpolate_lac_kernel<CC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    three_interpolate_lac_kernel<CC, T><<<grid, T, smem, s>>>(c, m, n, chunks, gpp, total, points, idx, weight, out);
+    PN2_LAUNCH_OK("three_interpolate");
+    return PN2_OK;
+}
+
 // grad_points[b,c,idx_j] += grad_out[b,c,i] * w_j   (interpolate_gpu.cu:120-142)
 __global__ void __launch_bounds__(TI_THREADS)
 three_interpolate_grad_kernel(int c, int n, int m, const float *__restrict__ grad_out, const int32_t *__restrict__ idx,
@@ -308,6 +487,8 @@ three_interpolate_grad_kernel(int c, int n, int m, const float *__restrict__ gra
 
 }  // namespace
 }  // namespace pn2
+
+extern "C" void pn2_debug_set_interp_mode(int mode) { pn2::g_interp_mode = mode; }
 
 extern "C" int pn2_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int32_t *idx,
                             void *stream) {
@@ -342,6 +523,20 @@ extern "C" int pn2_three_interpolate(int b, int c, int m, int n, const float *po
     if (b == 0 || c == 0 || n == 0) return PN2_OK;
     PN2_REQUIRE(points && idx && weight && out, "three_interpolate: null pointer");
     PN2_REQUIRE(b <= 65535 && ceil_div(c, TI_CH) <= 65535, "three_interpolate: b or c exceeds the grid limits");
+    if (g_interp_mode != 1 && (n & 7) == 0 && ((uintptr_t)out & 31) == 0) {
+        // lane-along-channel kernel (three_interpolate_lac_kernel): 256-bit stores need 32-byte aligned rows.  Measured
+        // (scripts/interp_sweep.py): 4 % faster than the tiled kernel at the fp1 shape (b 32, c 128, m 1024, n 8192), 20-25 %
+        // at m <= 256; slower when there is too little work for one CTA per SM.
+        cudaStream_t st = (cudaStream_t)stream;
+        const bool forced = (g_interp_mode & 255) == 32;
+        const int threads = forced ? ((g_interp_mode & 256) ? 256 : 512) : (lac_fits(m, 32, 256) ? 256 : 512);
+        const long long granules = (long long)b * ceil_div(c, 32) * ceil_div(n, LC_GRAN);
+        const bool wanted = forced || (c >= 32 && n >= 2 * m && (m <= 512 || granules >= 16ll * sm_count()));
+        if (wanted && lac_fits(m, 32, threads)) {
+            if (threads == 512) return launch_interp_lac<32, 512>(b, c, m, n, points, idx, weight, out, st);
+            return launch_interp_lac<32, 256>(b, c, m, n, points, idx, weight, out, st);
+        }
+    }
     // upsampling (n >> m) with a coarse set that fits in shared memory: stage it (three_interpolate_smem_kernel)
     if (n >= 2 * m && (long long)b * c >= 64) {
         // prefer a tile that lets two CTAs share an SM (one stages while the other streams), else the widest that fits

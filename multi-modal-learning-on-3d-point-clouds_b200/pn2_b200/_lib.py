@@ -73,6 +73,7 @@ _OTHER = {
     "pn2_debug_set_fps_mode": ([_c_int], None),
     "pn2_debug_set_tc_timestamps": ([_vp], None),
     "pn2_debug_set_tc_max_ctas": ([_c_int], None),
+    "pn2_debug_set_interp_mode": ([_c_int], None),
     "pn2_mlp_pack_bf16_size": ([ctypes.POINTER(Pn2Mlp)], ctypes.c_longlong),
 }
 

@@ -212,6 +212,33 @@ def test_three_interpolate_and_grad(cuda, B, C, m, n):
         np.testing.assert_array_equal(out.detach().cpu().numpy(), ref)
 
 
+# every kernel choice of pn2_three_interpolate (pn2_debug_set_interp_mode: tiled kernels, the lane-along-channel kernel in its
+# 512- and 256-thread forms, automatic) against the oracle and the reference's kernel, bit for bit; shapes cover a partial
+# last channel tile (100, 37 channels), a partial last granule (n = 8200), a coarse set that is not a multiple of 4
+# (scalar stage), a single coarse point and two (cloud, tile) pairs inside one CTA's range
+@pytest.mark.parametrize("B,C,m,n", [(4, 128, 1024, 8192), (3, 100, 1023, 8200), (5, 37, 700, 4104), (2, 128, 1, 512),
+                                     (16, 64, 256, 1024), (40, 32, 64, 256), (2, 96, 1500, 30000)])
+def test_three_interpolate_kernel_choices(cuda, B, C, m, n):
+    from pn2_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(B + C + m + n)
+    f = rng.standard_normal((B, C, m)).astype(np.float32)
+    idx = rng.integers(0, m, (B, n, 3)).astype(np.int32)
+    w = rng.random((B, n, 3)).astype(np.float32)
+    w /= w.sum(-1, keepdims=True)
+    want = orc.three_interpolate(f, idx, w)
+    ft, it, wt = dev(f, cuda), dev(idx, cuda), dev(w, cuda)
+    try:
+        for mode in (1, 32, 32 | 256, 0):
+            lib.pn2_debug_set_interp_mode(mode)
+            got = pu.three_interpolate(ft, it, wt).cpu().numpy()
+            np.testing.assert_array_equal(got, want, err_msg="mode %d" % mode)
+    finally:
+        lib.pn2_debug_set_interp_mode(0)
+    if ref_cuda.available():
+        np.testing.assert_array_equal(ref_cuda.three_interpolate(ft, it, wt).cpu().numpy(), want)
+
+
 def test_aliases_and_query_and_group(cuda):
     xyz = clouds("scannet", 2, 2048, 21)
     x = dev(xyz, cuda)
