@@ -263,7 +263,8 @@ void pn2_debug_set_tc_timestamps(long long *buf);
 /* Caps the resident CTAs per SM of the tensor-core MLP kernel (bench.py --tc-max-ctas; default 8 = no cap). */
 void pn2_debug_set_tc_max_ctas(int n);
 /* Kernel choice of pn2_three_interpolate: 0 automatic, 1 tiled kernels only, 32 the lane-along-channel kernel wherever it
- * applies, + 256 for its 256-thread form (two CTAs per SM).  scripts/interp_sweep.py. */
+ * applies (+ 256 / 4096 / 512: 256 / 768 / 1024 threads per CTA instead of 512; + 1024: no stores, + 2048: no row reads --
+ * bisect probes, results are then meaningless).  scripts/interp_sweep.py. */
 void pn2_debug_set_interp_mode(int mode);
 
 #ifdef __cplusplus

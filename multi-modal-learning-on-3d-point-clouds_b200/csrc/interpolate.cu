@@ -151,7 +151,7 @@ three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points, 
 // the stores of a warp coalesced along n.  HBM sees the coarse features once per CTA slice, idx/weight once per channel
 // chunk, and the output once.
 constexpr int TS_THREADS = 256;
-constexpr int LC_GRAN = 64;  // points per warp granule of the lane-along-channel kernel
+constexpr int LC_GRAN = 32;  // points per warp granule of the lane-along-channel kernel
 
 template <int CC, int PAD>
 __global__ void __launch_bounds__(TS_THREADS, 3)
@@ -284,20 +284,24 @@ int launch_interp_smem(int b, int c, int m, int n, const float *points, const in
     return PN2_OK;
 }
 
-// Lane-along-channel kernel (coarse sets up to ~1500 points with 32 channels per tile).
+// Lane-along-channel kernel (32 channels per tile, coarse sets up to ~1400 points).
 //
 // The tiled kernel above spends its shared-memory wavefronts on bank conflicts: each lane reads 16 bytes of its OWN random
 // coarse row, so the 8 lanes of a quarter warp collide in the 8 four-bank groups (ncu: 5.2 M conflict wavefronts of 8.6 M,
-// LSU data pipe 91 % busy while active; profiles/r1_hbm_ops_ncu_full_summary.csv).  Here the LPR = CC/4 lanes of a group
-// read the CC channels of ONE coarse row (for CC = 32 a quarter warp reads one whole 128-byte row: conflict free whatever
-// the indices are).  A group owns EIGHT CONSECUTIVE points of a granule (one per step) and keeps its 4 channels x 8 points
-// in registers; chunk q of a row holds the channels q, q + LPR, q + 2 LPR, q + 3 LPR.  Rows are XOR-swizzled by (k >> 2) so
-// that the transposing stage is conflict free as well.  idx / weight travel through a per-warp record buffer ({k0,k1,k2,-}
-// {w0,w1,w2,-} per point: two LDS.128 per step, broadcast inside a group, slots XOR-swizzled by the group number so the
-// groups fall into different banks); the next granule's records are fetched while the current one is computed.
-// Each channel's 8 points of a group leave as one 256-bit store (a full 32-byte sector).
+// LSU data pipe 91 % busy while active; profiles/r1_hbm_ops_ncu_full_summary.csv).  Here the LPR = CC/4 = 8 lanes of a
+// group read the 32 channels of ONE coarse row: a quarter warp reads one whole 128-byte row, conflict free whatever the
+// indices are.  A group owns EIGHT CONSECUTIVE points of a 32-point granule (one per step) and keeps its 4 channels x 8
+// points in registers; chunk q of a row holds the channels q, q + 8, q + 16, q + 24.  Rows are XOR-swizzled by (k >> 2) so
+// that the transposing stage is conflict free as well.
+// idx / weight: each warp keeps LC_DEPTH granules in flight in a cp.async ring (the 384 + 384 bytes of a granule as they lie
+// in global memory); a step reads its point's six words with broadcast LDS.32.
+// Stores: a 256-bit store is issued a quarter warp at a time and costs one LSU wavefront per distinct 128-byte line, so
+// the accumulators are first exchanged by shuffles (same register in every lane, no selects) until the lanes of a
+// quarter hold contiguous bytes of a channel row; a quarter then writes two whole lines (stores: 20 -> 8 us of the fp1 shape).
 // Persistent CTAs: the (cloud, channel tile, granule) space is cut into gridDim.x contiguous ranges, so a CTA stages at
 // most two tiles more than it has whole (cloud, tile) pairs and there is no partial last wave.
+// `probe` (developer bisect, pn2_debug_set_interp_mode bits 10 / 11): 1 = no stores, 2 = no row reads.  At the fp1 shape
+// (45 us): stores 8 us, row reads 6 us, the rest (stage 2 x 128 KB per CTA, ring, arithmetic, shuffles) 31 us.
 
 // Transposing stage: tile4[k][q ^ ((k >> 2) & (LPR - 1))] = channels q + LPR * {0,1,2,3} of coarse point k (zero beyond nc).
 // Vector form: an item = four consecutive points of four channel rows (four coalesced 128-bit loads) -> four swizzled
@@ -307,11 +311,12 @@ __device__ __forceinline__ void lac_stage_tile(float4 *tile4, const float *__res
     if ((m & 3) == 0 && ((uintptr_t)f & 15) == 0) {
         const int m4 = m >> 2;
         const int items = LPR * m4;
-        for (int base = 0; base < items; base += 4 * T) {
-            float4 r[4][4];
-            int cqs[4], is[4];
+        constexpr int NB = T >= 768 ? 2 : 4;  // items per thread and batch
+        for (int base = 0; base < items; base += NB * T) {
+            float4 r[NB][4];
+            int cqs[NB], is[NB];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < NB; ++u) {
                 const int it = base + u * T + tid;
                 const int cq = it / m4, i = it - cq * m4;
                 cqs[u] = cq;
@@ -322,7 +327,7 @@ __device__ __forceinline__ void lac_stage_tile(float4 *tile4, const float *__res
                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < NB; ++u) {
                 if (base + u * T + tid >= items) continue;
                 float4 *d = tile4 + (size_t)(4 * is[u]) * LPR + (cqs[u] ^ (is[u] & (LPR - 1)));
                 d[0] = make_float4(r[u][0].x, r[u][1].x, r[u][2].x, r[u][3].x);
@@ -344,25 +349,29 @@ __device__ __forceinline__ void lac_stage_tile(float4 *tile4, const float *__res
     }
 }
 
+constexpr int LC_DEPTH = 4;  // granules of idx / weight in flight per warp (cp.async ring)
+
 template <int CC, int T>
-__global__ void __launch_bounds__(T, 512 / T)
+__global__ void __launch_bounds__(T, T <= 256 ? 2 : 1)
 three_interpolate_lac_kernel(int c, int m, int n, int chunks, int gpp, long long total_gran,
                              const float *__restrict__ points, const int32_t *__restrict__ idx,
-                             const float *__restrict__ weight, float *__restrict__ out) {
+                             const float *__restrict__ weight, float *__restrict__ out, int probe) {
     constexpr int LPR = CC / 4;    // lanes per coarse row = lanes per group
     constexpr int PPI = 32 / LPR;  // groups per warp
     constexpr int GRAN = LC_GRAN;  // points per warp granule
     constexpr int RUNS = GRAN / (8 * PPI);  // eight-point runs per group and granule
     constexpr int WARPS = T / 32;
-    constexpr int FPL = GRAN / 32;  // records fetched per lane
+    constexpr int SLOT_WORDS = GRAN * 6;  // 3 indices then 3 weights per point, as they lie in global memory
     extern __shared__ __align__(16) float4 lac_smem[];
-    float4 *tile4 = lac_smem;                                            // [m][LPR]
-    int4 *rec_i = reinterpret_cast<int4 *>(lac_smem + (size_t)m * LPR);  // [WARPS][GRAN]
-    float4 *rec_w = reinterpret_cast<float4 *>(rec_i + WARPS * GRAN);
+    float4 *tile4 = lac_smem;  // [m][LPR]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int j = lane % LPR, g = lane / LPR;
-    int4 *my_i = rec_i + warp * GRAN;
-    float4 *my_w = rec_w + warp * GRAN;
+    int32_t *ring = reinterpret_cast<int32_t *>(lac_smem + (size_t)m * LPR) + (size_t)warp * LC_DEPTH * SLOT_WORDS;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    const char *tile_bytes = reinterpret_cast<const char *>(tile4);
+    const int j16 = j << 4;
+    // byte offset of a lane's chunk of coarse row k (swizzle included)
+    auto row_off = [&](int k) { return (((k * LPR) | ((k >> 2) & (LPR - 1))) << 4) ^ j16; };
 
     long long gq = total_gran * blockIdx.x / gridDim.x;
     const long long gq_end = total_gran * (blockIdx.x + 1) / gridDim.x;
@@ -377,74 +386,99 @@ three_interpolate_lac_kernel(int c, int m, int n, int chunks, int gpp, long long
         const int32_t *idb = idx + (size_t)bb * n * 3;
         const float *wb = weight + (size_t)bb * n * 3;
         float *ob = out + ((size_t)bb * c + c0) * n;
-        int rk[FPL][3];
-        float rw[FPL][3];
-        auto fetch = [&](int gi) {
-#pragma unroll
-            for (int h = 0; h < FPL; ++h) {
-                const int p = gi * GRAN + lane + 32 * h;
-                const bool ok = gi < gi1 && p < n;
-#pragma unroll
-                for (int e = 0; e < 3; ++e) {
-                    rk[h][e] = ok ? __ldg(idb + (size_t)p * 3 + e) : 0;
-                    rw[h][e] = ok ? __ldg(wb + (size_t)p * 3 + e) : 0.f;
+        // granule gi -> ring slot: 12 * points bytes of idx and of weight, in 16-byte pieces (n % 8 == 0: whole pieces)
+        auto issue = [&](int gi, int slot) {
+            if (gi < gi1) {
+                const int p0 = gi * GRAN;
+                const int pieces = min(GRAN, n - p0) * 3 / 4;
+                const uint32_t dst = ring_s + (uint32_t)slot * SLOT_WORDS * 4;
+                for (int q = lane; q < pieces; q += 32) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * 16), "l"(idb + (size_t)p0 * 3 + q * 4) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + GRAN * 12 + q * 16), "l"(wb + (size_t)p0 * 3 + q * 4)
+                                 : "memory");
                 }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        fetch(gi0 + warp);  // in flight during the stage
-        __syncthreads();    // every warp is done with the previous tile
+        __syncwarp();  // the warp has consumed every slot of the previous segment
+#pragma unroll
+        for (int d = 0; d < LC_DEPTH - 1; ++d) issue(gi0 + warp + d * WARPS, d);  // in flight during the stage
+        __syncthreads();  // every warp is done with the previous tile
         lac_stage_tile<LPR, T>(tile4, points + ((size_t)bb * c + c0) * m, m, nc, tid);
         __syncthreads();
+        int slot = 0;
         for (int gi = gi0 + warp; gi < gi1; gi += WARPS) {
-            __syncwarp();  // the previous granule's steps have read their records
-#pragma unroll
-            for (int h = 0; h < FPL; ++h) {
-                const int q = lane + 32 * h;
-                const int slot = q ^ ((q >> 3) & (PPI - 1));
-                my_i[slot] = make_int4(rk[h][0], rk[h][1], rk[h][2], 0);
-                my_w[slot] = make_float4(rw[h][0], rw[h][1], rw[h][2], 0.f);
-            }
-            __syncwarp();
-            fetch(gi + WARPS);
+            __syncwarp();  // the slot refilled below was read in the previous iteration
+            issue(gi + (LC_DEPTH - 1) * WARPS, slot == 0 ? LC_DEPTH - 1 : slot - 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(LC_DEPTH - 1) : "memory");
+            __syncwarp();  // every lane's pieces of this granule have landed
+            const int32_t *ri = ring + slot * SLOT_WORDS;
+            const float *rw = reinterpret_cast<const float *>(ri + GRAN * 3);
+            slot = slot == LC_DEPTH - 1 ? 0 : slot + 1;
 #pragma unroll
             for (int run = 0; run < RUNS; ++run) {
                 // the group's eight points, within the granule (the PPI groups of a warp own consecutive runs)
                 const int q0 = 8 * PPI * run + 8 * g;
+                const int pw = gi * GRAN + 8 * PPI * run;  // the warp's 8 * PPI points of this run
                 float acc[4][8];
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const int slot = (q0 + s) ^ (g & (PPI - 1));
-                    const int4 kk = my_i[slot];
-                    const float4 ww = my_w[slot];
-                    const float4 a0 = tile4[(size_t)kk.x * LPR + (j ^ ((kk.x >> 2) & (LPR - 1)))];
-                    const float4 a1 = tile4[(size_t)kk.y * LPR + (j ^ ((kk.y >> 2) & (LPR - 1)))];
-                    const float4 a2 = tile4[(size_t)kk.z * LPR + (j ^ ((kk.z >> 2) & (LPR - 1)))];
-                    // the reference's contraction (K8): fma(w2, f2, fma(w0, f0, rn(w1 * f1)))
-                    acc[0][s] = __fmaf_rn(ww.z, a2.x, __fmaf_rn(ww.x, a0.x, __fmul_rn(ww.y, a1.x)));
-                    acc[1][s] = __fmaf_rn(ww.z, a2.y, __fmaf_rn(ww.x, a0.y, __fmul_rn(ww.y, a1.y)));
-                    acc[2][s] = __fmaf_rn(ww.z, a2.z, __fmaf_rn(ww.x, a0.z, __fmul_rn(ww.y, a1.z)));
-                    acc[3][s] = __fmaf_rn(ww.z, a2.w, __fmaf_rn(ww.x, a0.w, __fmul_rn(ww.y, a1.w)));
-                }
-                const int p = gi * GRAN + q0;  // element u of the lane's chunk is channel j + LPR * u
-                if (p < n) {
+                for (int u = 0; u < 4; ++u)
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (j + LPR * u < nc)
-                            asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ob + (size_t)(j + LPR * u) * n + p),
-                                         "f"(acc[u][0]), "f"(acc[u][1]), "f"(acc[u][2]), "f"(acc[u][3]), "f"(acc[u][4]),
-                                         "f"(acc[u][5]), "f"(acc[u][6]), "f"(acc[u][7])
-                                         : "memory");
+                    for (int s = 0; s < 8; ++s) acc[u][s] = 0.f;
+                if (pw + 8 * g < n) {  // n % 8 == 0: a group's run is whole or absent (its ring words may be stale)
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const int k0 = ri[3 * (q0 + s)], k1 = ri[3 * (q0 + s) + 1], k2 = ri[3 * (q0 + s) + 2];
+                        const float w0 = rw[3 * (q0 + s)], w1 = rw[3 * (q0 + s) + 1], w2 = rw[3 * (q0 + s) + 2];
+                        float4 a0, a1, a2;
+                        if (probe & 2) {
+                            a0 = a1 = a2 = make_float4(__int_as_float(k0), __int_as_float(k1), __int_as_float(k2), w0);
+                        } else {
+                            a0 = *reinterpret_cast<const float4 *>(tile_bytes + row_off(k0));
+                            a1 = *reinterpret_cast<const float4 *>(tile_bytes + row_off(k1));
+                            a2 = *reinterpret_cast<const float4 *>(tile_bytes + row_off(k2));
+                        }
+                        // the reference's contraction (K8): fma(w2, f2, fma(w0, f0, rn(w1 * f1)))
+                        acc[0][s] = __fmaf_rn(w2, a2.x, __fmaf_rn(w0, a0.x, __fmul_rn(w1, a1.x)));
+                        acc[1][s] = __fmaf_rn(w2, a2.y, __fmaf_rn(w0, a0.y, __fmul_rn(w1, a1.y)));
+                        acc[2][s] = __fmaf_rn(w2, a2.z, __fmaf_rn(w0, a0.z, __fmul_rn(w1, a1.z)));
+                        acc[3][s] = __fmaf_rn(w2, a2.w, __fmaf_rn(w0, a0.w, __fmul_rn(w1, a1.w)));
+                    }
+                }
+                // Element u of lane (g, j) is channel j + LPR * u of the points 8 g .. 8 g + 7.  A 256-bit store is issued a
+                // quarter warp at a time, so the lanes of a QUARTER have to cover contiguous bytes: for store u, lane
+                // (Q, l) takes over channel LPR * u + 2 Q + (l >> 2), points 8 (l & 3) .. + 7, from lane (g = l & 3,
+                // j = 2 Q + (l >> 2)) -- eight shuffles of the same register in every lane, no selects; a quarter then
+                // writes two whole 128-byte lines.
+                static_assert(CC == 32, "the store transpose is written for eight lanes per row");
+                const int l = lane & 7, Q = lane >> 3;
+                const int src = (l & 3) * 8 + 2 * Q + (l >> 2);
+                const int prun = pw + 8 * (l & 3);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float v[8];
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) v[s] = __shfl_sync(0xffffffffu, acc[u][s], src);
+                    const int ch = LPR * u + 2 * Q + (l >> 2);
+                    if (ch < nc && prun < n && (!(probe & 1) || v[0] + v[7] == 12345.678f))
+                        asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ob + (size_t)ch * n + prun), "f"(v[0]),
+                                     "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                                     : "memory");
                 }
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 int g_interp_mode = 0;  // developer knob (pn2_debug_set_interp_mode): 0 auto, 1 tiled kernels only, 32 the lane-along-channel
-                        // kernel wherever it applies (+ 256: 256-thread CTAs, two per SM)
+                        // kernel wherever it applies (+ 256: 256-thread CTAs, two per SM; + 4096 / 512: 768 / 1024 threads;
+                        // + 1024 / 2048: probe bits)
 
-inline size_t lac_smem_bytes(int m, int cc, int threads) { return (size_t)m * cc * 4 + (size_t)(threads / 32) * LC_GRAN * 32; }
-inline bool lac_fits(int m, int cc, int threads) { return (512 / threads) * (lac_smem_bytes(m, cc, threads) + 1024) <= 233472; }
+inline size_t lac_smem_bytes(int m, int cc, int threads) {
+    return (size_t)m * cc * 4 + (size_t)(threads / 32) * LC_DEPTH * LC_GRAN * 24;
+}
+inline bool lac_fits(int m, int cc, int threads) { return (threads <= 256 ? 2 : 1) * (lac_smem_bytes(m, cc, threads) + 1024) <= 233472; }
 
 template <int CC, int T>
 int launch_interp_lac(int b, int c, int m, int n, const float *points, const int32_t *idx, const float *weight, float *out,
@@ -453,9 +487,9 @@ int launch_interp_lac(int b, int c, int m, int n, const float *points, const int
     const int gpp = ceil_div(n, LC_GRAN);
     const long long total = (long long)b * chunks * gpp;
     const size_t smem = lac_smem_bytes(m, CC, T);
-    const int grid = (int)std::min<long long>((long long)(512 / T) * sm_count(), std::max<long long>(1, total / (T / 32)));
+    const int grid = (int)std::min<long long>((long long)(T <= 256 ? 2 : 1) * sm_count(), std::max<long long>(1, total / (T / 32)));
     PN2_CUDA(cudaFuncSetAttribute(three_interpolate_lac_kernel<CC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    three_interpolate_lac_kernel<CC, T><<<grid, T, smem, s>>>(c, m, n, chunks, gpp, total, points, idx, weight, out);
+    three_interpolate_lac_kernel<CC, T><<<grid, T, smem, s>>>(c, m, n, chunks, gpp, total, points, idx, weight, out, (g_interp_mode >> 10) & 3);
     PN2_LAUNCH_OK("three_interpolate");
     return PN2_OK;
 }
@@ -523,16 +557,19 @@ extern "C" int pn2_three_interpolate(int b, int c, int m, int n, const float *po
     if (b == 0 || c == 0 || n == 0) return PN2_OK;
     PN2_REQUIRE(points && idx && weight && out, "three_interpolate: null pointer");
     PN2_REQUIRE(b <= 65535 && ceil_div(c, TI_CH) <= 65535, "three_interpolate: b or c exceeds the grid limits");
-    if (g_interp_mode != 1 && (n & 7) == 0 && ((uintptr_t)out & 31) == 0) {
-        // lane-along-channel kernel (three_interpolate_lac_kernel): 256-bit stores need 32-byte aligned rows.  Measured
-        // (scripts/interp_sweep.py): 4 % faster than the tiled kernel at the fp1 shape (b 32, c 128, m 1024, n 8192), 20-25 %
-        // at m <= 256; slower when there is too little work for one CTA per SM.
+    if (g_interp_mode != 1 && (n & 7) == 0 && ((uintptr_t)out & 31) == 0 && (((uintptr_t)idx | (uintptr_t)weight) & 15) == 0) {
+        // lane-along-channel kernel (three_interpolate_lac_kernel): 256-bit stores need 32-byte aligned rows, the cp.async ring
+        // 16-byte aligned idx / weight.  Measured (scripts/interp_sweep.py, profiles/r1_interp_sweep_lac.jsonl): fp1 shape (b 32,
+        // c 128, m 1024, n 8192) 57 -> 45 us = 53 % of HBM, 20-40 % faster at m <= 256; no gain with too little work per SM.
         cudaStream_t st = (cudaStream_t)stream;
         const bool forced = (g_interp_mode & 255) == 32;
-        const int threads = forced ? ((g_interp_mode & 256) ? 256 : 512) : (lac_fits(m, 32, 256) ? 256 : 512);
+        const int threads = forced ? ((g_interp_mode & 256) ? 256 : (g_interp_mode & 512) ? 1024 : (g_interp_mode & 4096) ? 768 : 512)
+                                   : (lac_fits(m, 32, 256) ? 256 : 512);
         const long long granules = (long long)b * ceil_div(c, 32) * ceil_div(n, LC_GRAN);
         const bool wanted = forced || (c >= 32 && n >= 2 * m && (m <= 512 || granules >= 16ll * sm_count()));
         if (wanted && lac_fits(m, 32, threads)) {
+            if (threads == 1024) return launch_interp_lac<32, 1024>(b, c, m, n, points, idx, weight, out, st);
+            if (threads == 768) return launch_interp_lac<32, 768>(b, c, m, n, points, idx, weight, out, st);
             if (threads == 512) return launch_interp_lac<32, 512>(b, c, m, n, points, idx, weight, out, st);
             return launch_interp_lac<32, 256>(b, c, m, n, points, idx, weight, out, st);
         }
