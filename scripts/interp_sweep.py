@@ -8,7 +8,8 @@ from pn2_b200 import _lib as L
 from pn2_b200 import pointnet2_utils as pu
 dev = torch.device("cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+_pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+PEAK = json.load(open(_pk))["hbm_gbs"] if os.path.exists(_pk) else 6650.0  # fallback: B200_PROFILING.md
 lib = L.load()
 
 
