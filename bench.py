@@ -303,6 +303,8 @@ def run_ours(args):
         import ctypes
         from pn2_b200 import _lib
         _lib.load().pn2_debug_set_tc_max_ctas(ctypes.c_int(args.tc_max_ctas))
+    from pn2_b200 import pointnet_util as _pu
+    _pu.set_mlp_precision(args.precision)  # the drop-in modules default to fp32 (1e-5 parity); the benchmark path is bf16
     model = build_model(device)
     # rotating inputs: 24 distinct batches = 151 MB of input (+ the activations they produce) > the 126 MB L2
     n_rot = 24
@@ -514,6 +516,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=32, help="scenes per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="shared-MLP arithmetic: bf16 tcgen05 tensor cores (2e-2, north_star) or fp32 FFMA (1e-5)")
     ap.add_argument("--pipeline", type=int, default=6, help="batches in flight (graph instances on separate streams)")
     ap.add_argument("--fps-mode", type=int, default=0, help="developer knob: 1 = one CTA per cloud, 2 = 4-CTA cluster per cloud")
     ap.add_argument("--tc-max-ctas", type=int, default=0, help="developer knob: cap resident CTAs/SM of the tensor-core MLP kernel")

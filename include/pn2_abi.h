@@ -148,6 +148,10 @@ int pn2_sa_mlp_max(int b, int n, int m, int k, int d, const float *xyz, const fl
 int pn2_fp_mlp(int b, int n, int m, int d1, int d2, const float *feat1, const float *feat2, const int32_t *idx,
                const float *weight, const pn2_mlp *mlp, float *out, void *stream);
 
+/* 1 if pn2_sa_mlp_max (nsample >= 1) / pn2_fp_mlp (nsample == 0) supports this stack fed with c0 input channels
+ * (layer count, nsample a power of two <= 128, widths within shared memory); 0 otherwise.  No CUDA call. */
+int pn2_mlp_fp32_supported(const pn2_mlp *mlp, int c0, int nsample);
+
 /* ---- the same two blocks on the tcgen05 tensor cores: bf16 operands, fp32 accumulation in TMEM ----
  * Outputs agree with the fp32 entry points within bf16 rounding (2e-2 relative).  Weights are packed once
  * (bf16, pre-swizzled UMMA tiles) with pn2_mlp_pack_bf16; biases are still read from `mlp`.

@@ -394,6 +394,21 @@ void copy_mlp(RowMlpParams &p, const pn2_mlp *mlp) {
 }  // namespace
 }  // namespace pn2
 
+// 1 when pn2_sa_mlp_max (nsample > 0) / pn2_fp_mlp (nsample == 0) can run this stack with `c0` input channels: the
+// callers (pn2_b200/pointnet_util.py::_fusable) use the reference's operator composition otherwise, so a module that
+// trains on the composed path never fails at eval time for its shape alone.
+extern "C" int pn2_mlp_fp32_supported(const pn2_mlp *mlp, int c0, int nsample) {
+    using namespace pn2;
+    if (!mlp || mlp->num_layers < 1 || mlp->num_layers > PN2_MAX_LAYERS || c0 < 1 || mlp->cin[0] != c0) return 0;
+    const int k = nsample;
+    if (k < 0 || (k > 0 && !(k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32 || k == 64 || k == 128))) return 0;
+    const int min_tr = k < 16 ? 16 : k;
+    const int cands[4] = {128, 64, 32, 16};
+    for (int i = 0; i < 4; ++i)
+        if (cands[i] >= min_tr && cands[i] % min_tr == 0 && make_layout(cands[i], c0, mlp).bytes <= SMEM_LIMIT) return 1;
+    return 0;
+}
+
 extern "C" int pn2_sa_mlp_max(int b, int n, int m, int k, int d, const float *xyz, const float *feat, const float *new_xyz,
                               const int32_t *idx, int order, const pn2_mlp *mlp, float *out, int out_stride,
                               int out_offset, void *stream) {

@@ -67,6 +67,7 @@ _OTHER = {
     "pn2_abi_version": ([], _c_int),
     "pn2_launch_count": ([], ctypes.c_uint64),
     "pn2_mlp_bf16_supported": ([ctypes.POINTER(Pn2Mlp)], _c_int),
+    "pn2_mlp_fp32_supported": ([ctypes.POINTER(Pn2Mlp), _c_int, _c_int], _c_int),
     "pn2_grid_max_points": ([], _c_int),
     "pn2_grid_table_stride": ([], _c_int),
     "pn2_set_fps_policy": ([_c_int], _c_int),
@@ -119,6 +120,26 @@ def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise Pn2Error("pn2_b200 operators need CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
+
+
+def check_f32(t, name="tensor", allow_bf16=False):
+    """The kernels read raw device pointers as contiguous fp32 (bf16 where stated): anything else would be reinterpreted
+    silently, so it is refused here -- the reference raises a dtype error in the same situation."""
+    if t is None:
+        return None
+    require_cuda(t)
+    if t.dtype != torch.float32 and not (allow_bf16 and t.dtype == torch.bfloat16):
+        raise Pn2Error("%s must be float32%s (got %s)" % (name, " or bfloat16" if allow_bf16 else "", t.dtype))
+    return t.contiguous()
+
+
+def check_i32(t, name="index tensor"):
+    if t is None:
+        return None
+    require_cuda(t)
+    if t.dtype != torch.int32:
+        raise Pn2Error("%s must be int32 (got %s)" % (name, t.dtype))
+    return t.contiguous()
 
 
 PROFILE = None  # developer profiling: list of (name, start_event, end_event) when enabled

@@ -10,6 +10,8 @@ torch.no_grad() the forward is 17 kernel launches (2 layout transposes, 4 x (FPS
 query, fused SA), 4 x (three_nn+weights, fused FP; the head is folded into the last FP block) -- the reference issues ~170
 (SURVEY.md 3.2).  Otherwise the reference's own composition runs (training / autograd).
 """
+import threading
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -37,8 +39,35 @@ class PointNet2SemSeg(nn.Module):
         self.conv2 = nn.Conv1d(128, num_classes, 1)
         self._head_fold = _FoldCache()
         self.timers = None  # bench.py: dict name -> [(start_event, end_event)] recorded on the current stream
-        self._streams = None
+        self._streams = {}  # device index -> (sampling stream, ball-query stream); shared by DataParallel replicas
+        self._streams_lock = threading.Lock()
         self.single_stream = False
+
+    def train(self, mode=True):
+        self._head_fold.clear()
+        return super().train(mode)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_streams"], state["_streams_lock"] = {}, None
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._streams_lock = threading.Lock()
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k == "_streams":
+                new.__dict__[k] = {}
+            elif k == "_streams_lock":
+                new.__dict__[k] = threading.Lock()
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
 
     @property
     def compute_dtype(self):
@@ -49,7 +78,7 @@ class PointNet2SemSeg(nn.Module):
         convs = list(self.fp1.mlp_convs) + [self.conv1, self.conv2]
         bns = list(self.fp1.mlp_bns) + [self.bn1, None]
         relus = [True] * len(self.fp1.mlp_convs) + [True, False]
-        return self._head_fold.get(convs, bns, relus)
+        return self._head_fold.get(self, convs, bns, relus)
 
     def forward_fused(self, xyz, points, labels=False):
         """xyz (B, 3, N), points (B, D, N) -> (B, N, num_classes), contiguous; labels=True -> (B, N) uint8 class
@@ -59,9 +88,11 @@ class PointNet2SemSeg(nn.Module):
         streams: FPS chain + 3-NN on one, ball queries on another; the fused SA/FP kernels follow on the caller's
         stream as their indices become ready.  No collective, no host synchronisation."""
         main = torch.cuda.current_stream(xyz.device)
-        if self._streams is None or self._streams[0].device != xyz.device:
-            self._streams = (torch.cuda.Stream(xyz.device), torch.cuda.Stream(xyz.device))
-        s_fps, s_bq = self._streams
+        with self._streams_lock:
+            pair = self._streams.get(xyz.device.index)
+            if pair is None:
+                pair = self._streams[xyz.device.index] = (torch.cuda.Stream(xyz.device), torch.cuda.Stream(xyz.device))
+        s_fps, s_bq = pair
         if self.single_stream:  # developer profiling: everything on the caller's stream
             s_fps = s_bq = main
         xyz_cl, feat_cl = to_channel_last(xyz), to_channel_last(points)
@@ -263,6 +294,10 @@ class _MultiviewStackBase(nn.Module):
 
     reduce = "max"
 
+    def train(self, mode=True):
+        self._head_fold.clear()
+        return super().train(mode)
+
     def _head(self, l0_points):
         x = self.drop1(F.relu(self.bn1(self.conv1(l0_points))))
         return self.conv2(x).permute(0, 2, 1)
@@ -271,7 +306,7 @@ class _MultiviewStackBase(nn.Module):
         convs = list(self.fp1.mlp_convs) + [self.conv1, self.conv2]
         bns = list(self.fp1.mlp_bns) + [self.bn1, None]
         relus = [True] * len(self.fp1.mlp_convs) + [True, False]
-        return self._head_fold.get(convs, bns, relus)
+        return self._head_fold.get(self, convs, bns, relus)
 
     def _blocks(self):
         mods = [self.sa1_geo, self.sa1_feat, self.sa2_geo, self.sa2_feat, self.sa3, self.sa4]

@@ -17,6 +17,7 @@ Two execution paths per module:
     kernels for the geometry, torch.nn for conv/BN -- with identical semantics.
 """
 import ctypes
+import threading
 from time import time
 
 import numpy as np
@@ -98,13 +99,15 @@ class FoldedMlp:
         return buf
 
 
-_PRECISION = "bf16"
+_PRECISION = "fp32"
 
 
 def set_mlp_precision(precision):
-    """Arithmetic of the fused shared-MLP kernels: "bf16" (tcgen05 tensor cores, fp32 accumulate; outputs within
-    2e-2 relative of fp32) or "fp32" (FFMA; within 1e-5 relative of the reference).  Returns the previous value.
-    Blocks whose widths do not fit the tensor-core kernel always run in fp32."""
+    """Arithmetic of the fused shared-MLP kernels: "fp32" (FFMA; within 1e-5 relative of the reference -- the default,
+    so a reference checkpoint loaded into these drop-in modules reproduces the reference's logits) or "bf16" (tcgen05
+    tensor cores, fp32 accumulate; outputs within 2e-2 relative of fp32; what bench.py and the throughput paths of
+    pn2_b200/models.py select explicitly).  Returns the previous value.  Blocks whose widths do not fit the tensor-core
+    kernel always run in fp32."""
     global _PRECISION
     if precision not in ("bf16", "fp32"):
         raise ValueError("precision must be 'bf16' or 'fp32'")
@@ -116,36 +119,82 @@ def get_mlp_precision():
     return _PRECISION
 
 
-def _param_key(mods):
+def _fold_key(convs, bns):
+    """Identity + version of exactly the tensors a fold reads (weights, biases, BatchNorm affine and running statistics)."""
     key = []
-    for m in mods:
-        for t in list(m.parameters()) + list(m.buffers()):
-            key.append((t.data_ptr(), t._version))
+    for conv, bn in zip(convs, bns):
+        ts = [conv.weight, conv.bias]
+        if bn is not None:
+            ts += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        for t in ts:
+            key.append(None if t is None else (t.data_ptr(), t._version, t.device.index))
     return tuple(key)
 
 
 class _FoldCache:
-    """Re-folds only when a parameter / running statistic changed (version counters)."""
+    """Folded weights of one conv/BN stack, re-folded only when a tensor it reads changed (version counters).
+
+    One entry per device, guarded by a lock: torch.nn.DataParallel replicas shallow-copy the module's __dict__, so every
+    per-device replica thread sees this same object.  Replicas themselves are never cached -- their parameters are fresh
+    broadcast copies whose (pointer, version) pairs the caching allocator recycles, which would make a stale hit possible
+    -- they fold on every call (a handful of tiny launches).  `module.train()` drops the entries.  The cache is dropped,
+    not copied, by pickling / deepcopy (the descriptor holds raw device pointers)."""
 
     def __init__(self):
-        self.key, self.value = None, None
+        self._lock = threading.Lock()
+        self._entries = {}
 
-    def get(self, convs, bns, relus):
-        mods = list(convs) + [b for b in bns if b is not None]
-        key = _param_key(mods)
-        if key != self.key:
-            self.value = FoldedMlp([fold_conv_bn(c, b) + (r,) for c, b, r in zip(convs, bns, relus)])
-            self.key = key
-        return self.value
+    def clear(self):
+        with self._lock:
+            self._entries.clear()
+
+    def get(self, owner, convs, bns, relus):
+        def fold():
+            return FoldedMlp([fold_conv_bn(c, b) + (r,) for c, b, r in zip(convs, bns, relus)])
+
+        if getattr(owner, "_is_replica", False):
+            return fold()
+        dev = convs[0].weight.device
+        key = _fold_key(convs, bns)
+        with self._lock:
+            hit = self._entries.get(dev)
+            if hit is not None and hit[0] == key:
+                return hit[1]
+        value = fold()
+        with self._lock:
+            self._entries[dev] = (key, value)
+        return value
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
+    def __deepcopy__(self, memo):
+        return _FoldCache()
+
+
+def _all_f32(*tensors):
+    return all(t is None or t.dtype == torch.float32 for t in tensors)
 
 
 def _fusable(module, *tensors):
+    """The fused kernels serve eval-mode, no-autograd calls on CUDA fp32 tensors with fp32 parameters; everything else
+    (training, autograd, half / double models or inputs) takes the reference's operator composition, where torch raises
+    the same dtype errors the reference would."""
     if module.training:
         return False
     if torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in tensors)
                                     or any(p.requires_grad for p in module.parameters())):
         return False
-    return all(t is None or t.is_cuda for t in tensors)
+    if not all(t is None or t.is_cuda for t in tensors) or not _all_f32(*tensors):
+        return False
+    return all(p.dtype == torch.float32 and p.is_cuda for p in module.parameters())
+
+
+def _fp32_supported(mlp, c0, nsample):
+    return bool(_lib.load().pn2_mlp_fp32_supported(ctypes.byref(mlp.desc), int(c0), int(nsample)))
 
 
 def to_channel_last(x):
@@ -153,7 +202,7 @@ def to_channel_last(x):
     if x is None:
         return None
     B, C, N = x.shape
-    x = x.contiguous()
+    x = _lib.check_f32(x, "channel-first tensor")
     out = torch.empty((B, N, C), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.call("pn2_transpose", B, C, N, ptr(x), ptr(out), _lib.stream_ptr(x.device))
@@ -163,7 +212,7 @@ def to_channel_last(x):
 def to_channel_first(x):
     """(B, N, C) -> contiguous (B, C, N)"""
     B, N, C = x.shape
-    x = x.contiguous()
+    x = _lib.check_f32(x, "channel-last tensor")
     out = torch.empty((B, C, N), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.call("pn2_transpose", B, N, C, ptr(x), ptr(out), _lib.stream_ptr(x.device))
@@ -193,6 +242,7 @@ class fps_policy:
 def fps_gather_cl(xyz_cl, npoint):
     """xyz (B, N, 3) -> (idx (B, npoint) int32, new_xyz (B, npoint, 3)); the sampler writes the picked
     coordinates itself, replacing gather_operation + two layout copies (model/pointnet_util.py:34-35)."""
+    xyz_cl = _lib.check_f32(xyz_cl, "xyz")
     B, N, _ = xyz_cl.shape
     idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz_cl.device)
     new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz_cl.device)
@@ -208,6 +258,7 @@ class SpatialGrid:
     scan, and a spatially coherent point order.  xyz (B, N, 3) with N <= grid_max_points(); cell <= 0 = automatic."""
 
     def __init__(self, xyz_cl, cell):
+        xyz_cl = _lib.check_f32(xyz_cl, "xyz")
         B, N, _ = xyz_cl.shape
         dev = xyz_cl.device
         self.xyz, self.B, self.N = xyz_cl, B, N
@@ -224,6 +275,7 @@ class SpatialGrid:
 
     def ball_query(self, radius, nsample, new_xyz_cl):
         """Bit-identical to pointnet2_utils.ball_query(radius, nsample, xyz, new_xyz); build with cell >= 1.01 * radius."""
+        new_xyz_cl = _lib.check_f32(new_xyz_cl, "new_xyz")
         M = new_xyz_cl.shape[1]
         idx = torch.empty((self.B, M, nsample), dtype=torch.int32, device=self.xyz.device)
         with torch.cuda.device(self.xyz.device):
@@ -234,6 +286,7 @@ class SpatialGrid:
     def three_nn(self, unknown_cl, query_order=None, want_dist2=False, want_weight=True):
         """3-NN of `unknown` (B, n, 3) in this (known) cloud -> (idx, weight) [or (idx, dist2)]; bit-identical to the
         brute-force kernels."""
+        unknown_cl, query_order = _lib.check_f32(unknown_cl, "unknown"), _lib.check_i32(query_order, "query_order")
         n = unknown_cl.shape[1]
         dev = self.xyz.device
         idx = torch.empty((self.B, n, 3), dtype=torch.int32, device=dev)
@@ -276,6 +329,8 @@ def _bf16_flags(block0, skip, out):
 def sa_mlp_max_cl(xyz_cl, feat_cl, new_xyz_cl, idx, order, mlp, out=None, out_offset=0, out_dtype=torch.float32):
     """Fused grouping + MLP + max.  Returns (B, M, cout) (or writes a channel slice of `out`).  bf16 feature / output
     tensors are accepted by the tensor-core path only (activations travelling between tensor-core blocks)."""
+    xyz_cl, new_xyz_cl, idx = _lib.check_f32(xyz_cl, "xyz"), _lib.check_f32(new_xyz_cl, "new_xyz"), _lib.check_i32(idx, "idx")
+    feat_cl = _lib.check_f32(feat_cl, "features", allow_bf16=True)
     B, N, _ = xyz_cl.shape
     M, K = idx.shape[1], idx.shape[2]
     D = 0 if feat_cl is None else feat_cl.shape[2]
@@ -298,6 +353,7 @@ def sa_mlp_max_cl(xyz_cl, feat_cl, new_xyz_cl, idx, order, mlp, out=None, out_of
 def three_nn_weights_cl(xyz1_cl, xyz2_cl):
     """-> idx (B, n, 3) int32, weight (B, n, 3): three_nn + sqrt + clamp + inverse-distance weights
     (model/pointnet_util.py:205-208) in one kernel."""
+    xyz1_cl, xyz2_cl = _lib.check_f32(xyz1_cl, "xyz1"), _lib.check_f32(xyz2_cl, "xyz2")
     B, n, _ = xyz1_cl.shape
     m = xyz2_cl.shape[1]
     idx = torch.empty((B, n, 3), dtype=torch.int32, device=xyz1_cl.device)
@@ -311,6 +367,8 @@ def three_nn_weights_cl(xyz1_cl, xyz2_cl):
 def fp_mlp_cl(feat1_cl, feat2_cl, idx, weight, mlp, n, row_order=None, out_dtype=torch.float32):
     """Fused 3-NN interpolation + skip concatenation + MLP.  -> (B, n, cout); with out_dtype=torch.uint8 -> (B, n)
     class predictions: arg-max over the output channels, fused into the last layer (tensor-core path only)."""
+    feat1_cl, feat2_cl = _lib.check_f32(feat1_cl, "feat1", allow_bf16=True), _lib.check_f32(feat2_cl, "feat2", allow_bf16=True)
+    idx, weight, row_order = _lib.check_i32(idx, "idx"), _lib.check_f32(weight, "weight"), _lib.check_i32(row_order, "row_order")
     B, m, D2 = feat2_cl.shape
     D1 = 0 if feat1_cl is None else feat1_cl.shape[2]
     if out_dtype == torch.uint8:
@@ -384,7 +442,18 @@ class PointNetSetAbstraction(nn.Module):
         self._fold = _FoldCache()
 
     def folded(self):
-        return self._fold.get(self.mlp_convs, self.mlp_bns, [True] * len(self.mlp_convs))
+        return self._fold.get(self, self.mlp_convs, self.mlp_bns, [True] * len(self.mlp_convs))
+
+    def train(self, mode=True):
+        self._fold.clear()
+        return super().train(mode)
+
+    def _fused_ok(self, xyz, points):
+        """Eval / no-autograd / fp32 (see _fusable) and a shape the fused kernel supports: up to PN2_MAX_LAYERS layers,
+        nsample a power of two <= 128, widths within shared memory -- otherwise the reference's composition runs."""
+        if self.group_all or len(self.mlp_convs) > _lib.PN2_MAX_LAYERS or not _fusable(self, xyz, points):
+            return False
+        return _fp32_supported(self.folded(), 3 + (0 if points is None else points.shape[1]), self.nsample)
 
     def forward_cl(self, xyz_cl, feat_cl, geometry=None, out_dtype=torch.float32):
         """Channel-last fused path: xyz (B, N, 3), feat (B, N, D) or None -> new_xyz (B, S, 3), (B, S, D').
@@ -399,7 +468,7 @@ class PointNetSetAbstraction(nn.Module):
 
     def forward(self, xyz, points):
         """xyz (B, 3, N), points (B, D, N) or None -> new_xyz (B, 3, S), new_points (B, D', S)"""
-        if not self.group_all and _fusable(self, xyz, points):
+        if self._fused_ok(xyz, points):
             new_xyz, out = self.forward_cl(to_channel_last(xyz), to_channel_last(points))
             return new_xyz.permute(0, 2, 1), to_channel_first(out)
         xyz_t = xyz.permute(0, 2, 1)
@@ -433,7 +502,18 @@ class PointNetSetAbstractionMsg(nn.Module):
         self._folds = [_FoldCache() for _ in mlp_list]
 
     def folded(self, i):
-        return self._folds[i].get(self.conv_blocks[i], self.bn_blocks[i], [True] * len(self.conv_blocks[i]))
+        return self._folds[i].get(self, self.conv_blocks[i], self.bn_blocks[i], [True] * len(self.conv_blocks[i]))
+
+    def train(self, mode=True):
+        for f in self._folds:
+            f.clear()
+        return super().train(mode)
+
+    def _fused_ok(self, xyz, points):
+        if any(len(c) > _lib.PN2_MAX_LAYERS for c in self.conv_blocks) or not _fusable(self, xyz, points):
+            return False
+        c0 = 3 + (0 if points is None else points.shape[1])
+        return all(_fp32_supported(self.folded(i), c0, k) for i, k in enumerate(self.nsample_list))
 
     def forward_cl(self, xyz_cl, feat_cl, geometry=None, out_dtype=torch.float32):
         """geometry = (new_xyz, [ball_idx per scale]) to share sampling / queries between modules."""
@@ -453,7 +533,7 @@ class PointNetSetAbstractionMsg(nn.Module):
         return new_xyz, out
 
     def forward(self, xyz, points):
-        if _fusable(self, xyz, points):
+        if self._fused_ok(xyz, points):
             new_xyz, out = self.forward_cl(to_channel_last(xyz), to_channel_last(points))
             return new_xyz.permute(0, 2, 1), to_channel_first(out)
         xyz_t = xyz.permute(0, 2, 1)
@@ -494,7 +574,16 @@ class PointNetFeaturePropagation(nn.Module):
         self._fold = _FoldCache()
 
     def folded(self):
-        return self._fold.get(self.mlp_convs, self.mlp_bns, [True] * len(self.mlp_convs))
+        return self._fold.get(self, self.mlp_convs, self.mlp_bns, [True] * len(self.mlp_convs))
+
+    def train(self, mode=True):
+        self._fold.clear()
+        return super().train(mode)
+
+    def _fused_ok(self, xyz1, xyz2, points1, points2):
+        if len(self.mlp_convs) > _lib.PN2_MAX_LAYERS or not _fusable(self, xyz1, xyz2, points1, points2):
+            return False
+        return _fp32_supported(self.folded(), points2.shape[1] + (0 if points1 is None else points1.shape[1]), 0)
 
     def forward_cl(self, xyz1_cl, xyz2_cl, feat1_cl, feat2_cl, mlp=None, nn_weights=None, row_order=None,
                    out_dtype=torch.float32):
@@ -514,7 +603,7 @@ class PointNetFeaturePropagation(nn.Module):
 
     def forward(self, xyz1, xyz2, points1, points2):
         """xyz1 (B, 3, N), xyz2 (B, 3, S), points1 (B, D1, N) or None, points2 (B, D2, S) -> (B, D', N)"""
-        if _fusable(self, xyz1, xyz2, points1, points2):
+        if self._fused_ok(xyz1, xyz2, points1, points2):
             out = self.forward_cl(to_channel_last(xyz1), to_channel_last(xyz2), to_channel_last(points1),
                                   to_channel_last(points2))
             return to_channel_first(out)

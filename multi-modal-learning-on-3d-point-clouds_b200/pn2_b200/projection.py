@@ -81,21 +81,28 @@ def view_params(camera_to_world, intrinsic, depth_min, depth_max, image_dims):
 
 
 def lift_views(points, feats, depth, camera_to_world, intrinsic, depth_min, depth_max, image_dims, accuracy,
-               reduce="max", return_pixels=False):
+               reduce="max", return_pixels=False, view_parameters=None):
     """Fused lifting for a batch.
 
     points (B, N, 3); feats (B, V, C, H, W) feature maps (e.g. ENet, C=128, H=32, W=41); depth (B, V, H, W);
     camera_to_world (B, V, 4, 4); intrinsic 4x4 (or 3x3) with fx, fy, cx, cy; image_dims = [W, H].
     reduce = "max" | "first".  Returns image_features (B, C, N) [, pix (B, V, N) int32 (-1 = not lifted),
-    count (B, V) int32].
+    count (B, V) int32].  view_parameters = (w2c (B,V,4,4), corner2 (B,V,3), corner4 (B,V,3), normals (B,V,6,3)) replaces
+    the internal `view_params(camera_to_world, ...)` call, for callers that already hold them (camera_to_world is then
+    unused and may be None).
     """
-    _lib.require_cuda(points, feats, depth, camera_to_world)
+    _lib.require_cuda(points, feats, depth)
     B, N, _ = points.shape
     _, V, C, H, W = feats.shape
     if [W, H] != [int(image_dims[0]), int(image_dims[1])]:
         raise _lib.Pn2Error("image_dims [W, H] = %s does not match the feature maps (H=%d, W=%d)" % (list(image_dims), H, W))
     dev = points.device
-    w2c, corner2, corner4, normals = view_params(camera_to_world, intrinsic, depth_min, depth_max, image_dims)
+    if view_parameters is None:
+        w2c, corner2, corner4, normals = view_params(camera_to_world, intrinsic, depth_min, depth_max, image_dims)
+    else:
+        w2c, corner2, corner4, normals = [_lib.check_f32(t, "view_parameters") for t in view_parameters]
+        if w2c.numel() != B * V * 16 or corner2.numel() != B * V * 3 or corner4.numel() != B * V * 3 or normals.numel() != B * V * 18:
+            raise _lib.Pn2Error("view_parameters do not match (B, V) = (%d, %d)" % (B, V))
     intr = (ctypes.c_float * 4)(float(intrinsic[0][0]), float(intrinsic[1][1]), float(intrinsic[0][2]), float(intrinsic[1][2]))
     out = torch.empty((B, C, N), dtype=torch.float32, device=dev)
     pix = torch.empty((B, V, N), dtype=torch.int32, device=dev) if return_pixels else None
@@ -111,13 +118,17 @@ def lift_views(points, feats, depth, camera_to_world, intrinsic, depth_min, dept
     return out
 
 
-def frustum_counts(points, camera_to_world, intrinsic, depth_min, depth_max, image_dims):
+def frustum_counts(points, camera_to_world, intrinsic, depth_min, depth_max, image_dims, view_parameters=None):
     """points (N, 3) cuda fp32, camera_to_world (P, 4, 4) -> (P,) int32: points inside each pose's viewing frustum.
     One launch for all poses of a scene; replaces the loader's per-pose-file loop over points_in_frustum_cpu
-    (data_utils/ScanNetDataLoader.py:91-97)."""
-    _lib.require_cuda(points, camera_to_world)
-    _, c2, c4, normals = view_params(camera_to_world, intrinsic, depth_min, depth_max, image_dims)
-    P, N = camera_to_world.shape[0], points.shape[0]
+    (data_utils/ScanNetDataLoader.py:91-97).  view_parameters = (corner2 (P,3), corner4 (P,3), normals (P,6,3)) replaces
+    the internal view_params call."""
+    points = _lib.check_f32(points, "points")
+    if view_parameters is None:
+        _, c2, c4, normals = view_params(camera_to_world, intrinsic, depth_min, depth_max, image_dims)
+    else:
+        c2, c4, normals = [_lib.check_f32(t, "view_parameters") for t in view_parameters]
+    P, N = c2.numel() // 3, points.shape[0]
     counts = torch.zeros((P,), dtype=torch.int32, device=points.device)
     points = points.contiguous()
     with torch.cuda.device(points.device):

@@ -6,7 +6,9 @@ cpu_baseline / --impl reference legs do.
 
 Parity status: the reference has no golden vectors for this path; the oracle is
 pinned against the reference's own kernels (oracle/_ref/ref_cuda.so) run on a
-B200 -- tests/test_ref_cuda.py live, and tests/golden/*.npz offline.
+B200 -- tests/test_ops_gpu.py live, tests/golden/ref_cuda_r1.npz offline -- and, for
+the lifting and the frustum count, against the reference's own utils/projection.py
+run on the host (tests/golden/projection_r2.npz); see tests/test_golden.py.
 """
 import ctypes
 import os
@@ -23,13 +25,11 @@ _i = ctypes.POINTER(ctypes.c_int32)
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "_build", "liboracle.so")
-        if not os.path.exists(path):
-            import importlib.util
-            spec = importlib.util.spec_from_file_location("_oracle_build", os.path.join(_HERE, "build.py"))
-            mod = importlib.util.module_from_spec(spec)
-            spec.loader.exec_module(mod)
-            mod.build_oracle()
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_oracle_build", os.path.join(_HERE, "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        path = mod.build_oracle()  # rebuilds only when pn2_oracle.c is newer than the library
         _LIB = ctypes.CDLL(path)
         _LIB.orc_project_point.restype = ctypes.c_int32
         _LIB.orc_opt_n_threads.restype = ctypes.c_int
@@ -173,6 +173,18 @@ def lift_views(points, feats, depth, w2c, corner2, corner4, normals, intr, dmin,
                          _fp(normals), _fp(intr), ctypes.c_float(dmin), ctypes.c_float(dmax), ctypes.c_float(acc),
                          1 if reduce == "first" else 0, _fp(out), _ip(pix))
     return out, pix
+
+
+def frustum_count(points, corners, normals, return_mask=False):
+    """points (N,3), corners (P,8,3), normals (P,6,3) fp32 -> counts (P,) int64 [, mask (P,N) bool]: the loader's fp64
+    frustum membership test, data_utils/ScanNetDataLoader.py:91-97 -> utils/projection.py:132-164."""
+    points, corners, normals = _f32(points), _f32(corners), _f32(normals)
+    N, P = points.shape[0], corners.shape[0]
+    counts = np.zeros(P, dtype=np.int64)
+    mask = np.zeros((P, N), dtype=np.uint8) if return_mask else None
+    lib().orc_frustum_count(N, P, _fp(points), _fp(corners), _fp(normals), counts.ctypes.data_as(ctypes.c_void_p),
+                            mask.ctypes.data_as(ctypes.c_void_p) if return_mask else None)
+    return (counts, mask.astype(bool)) if return_mask else counts
 
 
 def mlp_layer(x, w, b, relu=True):

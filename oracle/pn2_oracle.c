@@ -8,8 +8,11 @@
  * Parity status: the reference ships no tests or golden vectors for this path
  * (SURVEY.md section 4), so this restatement is pinned against outputs of the
  * reference's own CUDA kernels compiled verbatim into oracle/_ref/ref_cuda.so
- * and run on a B200 (tests/test_ref_cuda.py, fixtures under tests/golden/ made
- * by tests/golden/make_golden.py).
+ * and run on a B200 (live in tests/test_ops_gpu.py; offline through the fixture
+ * tests/golden/ref_cuda_r1.npz made by tests/golden/make_golden.py, checked by
+ * tests/test_golden.py), and -- for the lifting and the frustum count -- against
+ * vectors produced by the reference's own utils/projection.py run on the host
+ * (tests/golden/projection_r2.npz, tests/golden/make_golden_projection.py).
  *
  * Every function cites the reference file:line it follows (paths relative to
  * the reference tree).  All arithmetic is IEEE fp32 with the contraction the
@@ -310,6 +313,37 @@ void orc_lift_views(int B, int N, int V, int C, int H, int W, const float *point
                 }
             }
         }
+    }
+}
+
+/* Frustum membership count of the ScanNet loader's best-view selection:
+ * data_utils/ScanNetDataLoader.py:91-97 calls points_in_frustum_cpu
+ * (utils/projection.py:132-164) with corners / normals / points cast to fp64.
+ * corners (P,8,3) and normals (P,6,3) are the fp32 values of
+ * compute_frustum_corners / compute_frustum_normals; planes 0-2 are tested
+ * against corner 2, planes 3-5 against corner 4; predicate
+ * round(100 * s) / 100 < 0 in fp64.  counts (P); mask (P,N) bytes or NULL. */
+void orc_frustum_count(int N, int P, const float *points, const float *corners, const float *normals,
+                       int64_t *counts, uint8_t *mask) {
+#pragma omp parallel for schedule(static)
+    for (int q = 0; q < P; ++q) {
+        const float *c2 = corners + ((size_t)q * 8 + 2) * 3, *c4 = corners + ((size_t)q * 8 + 4) * 3;
+        int64_t cnt = 0;
+        for (int i = 0; i < N; ++i) {
+            const float *p = points + (size_t)i * 3;
+            int inside = 1;
+            for (int k = 0; k < 6; ++k) {
+                const float *c = k < 3 ? c2 : c4;
+                const float *nr = normals + ((size_t)q * 6 + k) * 3;
+                double s = ((double)p[0] - (double)c[0]) * (double)nr[0];
+                s += ((double)p[1] - (double)c[1]) * (double)nr[1];
+                s += ((double)p[2] - (double)c[2]) * (double)nr[2];
+                if (!(rint(s * 100.0) / 100.0 < 0.0)) inside = 0;
+            }
+            cnt += inside;
+            if (mask) mask[(size_t)q * N + i] = (uint8_t)inside;
+        }
+        counts[q] = cnt;
     }
 }
 

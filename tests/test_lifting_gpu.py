@@ -1,9 +1,17 @@
-"""GPU parity of the multi-view lifting kernel: bit-exact against the C oracle (same fixed fp32 evaluation
-order) and index agreement against the torch restatement of the reference's op sequence."""
+"""GPU parity of the multi-view lifting (rows A12-A14) and the loader's frustum count (row N2).
+
+Anchors, strongest first:
+  * tests/golden/projection_r2.npz -- vectors produced by the REFERENCE's own utils/projection.py and the view reductions of
+    model/pointnet2multiview.py run on the host (tests/golden/make_golden_projection.py).  The kernels are fed with the
+    reference's per-view parameters and must reproduce its decisions (identical except listed rounding-boundary cases)
+    and its lifted features bit for bit; the product's own parameter kernel is pinned to the reference's values separately.
+  * the C oracle (pinned to the same vectors by tests/test_golden.py) on further shapes, bit-exact.
+  * the torch restatement oracle/projection_ref.py (also pinned there) for the end-to-end agreement rate."""
 import numpy as np
 import pytest
 import torch
 
+from lifting_cases import PROJ, boundary_cases, mgj, ref_view_params
 from oracle import oracle as orc
 from oracle import projection_ref
 from pn2_b200 import projection, scenes
@@ -126,26 +134,139 @@ def test_projection_helper_surface(cuda):
     assert int(cnt) > 0
 
 
+def _lift_with_reference_params(cuda, name, reduce, gold):
+    _, B, N, V, C = mgj.CASES[name]
+    xyz, feats, depth, poses = mgj.lifting_inputs(name)
+    w2c, c2, c4, nrm = ref_view_params(gold, name)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    out, pix, count = projection.lift_views(t(xyz), t(feats), t(depth), None, mgj.INTRINSIC, mgj.DEPTH_MIN, mgj.DEPTH_MAX,
+                                            mgj.IMAGE_DIMS, mgj.ACCURACY, reduce=reduce, return_pixels=True,
+                                            view_parameters=(t(w2c), t(c2), t(c4), t(nrm)))
+    return (xyz, feats, depth, poses), (w2c, c2, c4, nrm), out.cpu().numpy(), pix.cpu().numpy(), count.cpu().numpy()
+
+
+@pytest.mark.parametrize("reduce", ["max", "first"])
+@pytest.mark.parametrize("name", list(mgj.CASES))
+def test_lift_views_reproduces_the_reference(cuda, name, reduce):
+    """pn2_lift_views fed with the reference's own per-view parameters (torch.inverse, compute_frustum_corners / _normals
+    as stored in the fixture) against the reference's compute_projection decisions, Projection.forward maps and view
+    reductions (utils/projection.py:166-256, model/pointnet2multiview.py:36-41 / 89-99)."""
+    gold = np.load(PROJ)
+    (xyz, feats, depth, _), (w2c, c2, c4, nrm), out, pix, count = _lift_with_reference_params(cuda, name, reduce, gold)
+    want = gold[name + "/pix"]
+    diff = np.argwhere(pix != want)
+    assert len(diff) <= 1e-3 * pix.size, "decision agreement %.5f" % (1 - len(diff) / pix.size)
+    assert boundary_cases(xyz, depth, w2c, c2, c4, nrm, diff).all(), "a decision differs away from any rounding boundary"
+    np.testing.assert_array_equal(count, (pix >= 0).sum(-1))
+    B = xyz.shape[0]
+    for b in range(B):
+        same = (pix[b] == want[b]).all(0)
+        np.testing.assert_array_equal(out[b][:, :mgj.KEEP_POINTS][:, same[:mgj.KEEP_POINTS]],
+                                      gold["%s/%s/head/%d" % (name, reduce, b)][:, same[:mgj.KEEP_POINTS]])
+        if same.all():
+            assert mgj.sha(out[b]) == str(gold["%s/%s/sha/%d" % (name, reduce, b)]), "lifted features differ from the reference's"
+        else:
+            np.testing.assert_allclose(out[b].astype(np.float64).sum(1), gold["%s/%s/chansum/%d" % (name, reduce, b)], atol=50.0)
+
+
+@pytest.mark.parametrize("name", list(mgj.CASES))
+def test_view_params_reproduce_the_reference(cuda, name):
+    """pn2_lift_setup (one launch) against the reference's torch.inverse / compute_frustum_corners / compute_frustum_normals
+    values: corners to 1 ulp-class error, normals to the cancellation the cross products allow, the inverse within the error
+    of the reference's own fp32 LU."""
+    gold = np.load(PROJ)
+    _, _, _, poses = mgj.lifting_inputs(name)
+    w2c, c2, c4, nrm = projection.view_params(torch.from_numpy(poses).to(cuda), mgj.INTRINSIC, mgj.DEPTH_MIN, mgj.DEPTH_MAX, mgj.IMAGE_DIMS)
+    rw, rc2, rc4, rn = ref_view_params(gold, name)
+
+    def close(a, b, rel):
+        a, b = a.double().cpu().numpy().reshape(b.shape), b.astype(np.float64)
+        assert np.abs(a - b).max() <= rel * np.abs(b).max(), np.abs(a - b).max() / np.abs(b).max()
+
+    close(c2, rc2, 2.5e-7)
+    close(c4, rc4, 2.5e-7)
+    close(nrm, rn, 2e-6)
+    close(w2c, rw, 2e-5)
+
+
+@pytest.mark.parametrize("name", list(mgj.CASES))
+def test_lift_views_end_to_end_agreement_with_the_reference(cuda, name):
+    """The whole product path (own parameter kernel + lifting) against the reference's decisions: the parameters differ
+    from the reference's in the last place, so a point may flip only on a rounding boundary."""
+    gold = np.load(PROJ)
+    _, B, N, V, C = mgj.CASES[name]
+    xyz, feats, depth, poses = mgj.lifting_inputs(name)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    w2c, c2, c4, nrm = ref_view_params(gold, name)
+    for reduce in ("max", "first"):
+        out, pix, _ = projection.lift_views(t(xyz), t(feats), t(depth), t(poses), mgj.INTRINSIC, mgj.DEPTH_MIN, mgj.DEPTH_MAX,
+                                            mgj.IMAGE_DIMS, mgj.ACCURACY, reduce=reduce, return_pixels=True)
+        pix, out = pix.cpu().numpy(), out.cpu().numpy()
+        want = gold[name + "/pix"]
+        diff = np.argwhere(pix != want)
+        assert len(diff) <= 1e-3 * pix.size
+        assert boundary_cases(xyz, depth, w2c, c2, c4, nrm, diff).all()
+        for b in range(B):
+            same = (pix[b] == want[b]).all(0)[:mgj.KEEP_POINTS]
+            np.testing.assert_array_equal(out[b][:, :mgj.KEEP_POINTS][:, same], gold["%s/%s/head/%d" % (name, reduce, b)][:, same])
+
+
+def test_compute_projection_and_projection_apply_reproduce_the_reference(cuda):
+    """The reference's call surface: ProjectionHelper.compute_projection -> ([count, idx...], [count, pix...]) int64 vectors
+    and Projection.apply on them (utils/projection.py:166-256), against the fixture."""
+    gold = np.load(PROJ)
+    name = "v3_n8192"
+    _, B, N, V, C = mgj.CASES[name]
+    xyz, feats, depth, poses = mgj.lifting_inputs(name)
+    helper = projection.ProjectionHelper(mgj.INTRINSIC, mgj.DEPTH_MIN, mgj.DEPTH_MAX, mgj.IMAGE_DIMS, mgj.ACCURACY)
+    w2c, c2, c4, nrm = ref_view_params(gold, name)
+    b, v = 0, V - 1
+    pts = torch.from_numpy(xyz[b]).to(cuda)
+    ind3d, ind2d = helper.compute_projection(pts, torch.from_numpy(depth[b, v]).to(cuda), torch.from_numpy(poses[b, v]).to(cuda), N)
+    n = int(ind3d[0])
+    got = np.full(N, -1, np.int64)
+    got[ind3d[1:1 + n].cpu().numpy()] = ind2d[1:1 + n].cpu().numpy()
+    want = gold[name + "/pix"][b, v]
+    diff = np.argwhere(got != want)
+    diff = np.concatenate([np.full((len(diff), 1), b), np.full((len(diff), 1), v), diff], 1)
+    assert len(diff) <= 1e-3 * N and boundary_cases(xyz, depth, w2c, c2, c4, nrm, diff).all()
+    # Projection.apply on the REFERENCE's index vectors -> the reference's single-view map, bit for bit
+    keep = np.nonzero(want >= 0)[0]
+    r3d = torch.zeros(N + 1, dtype=torch.int64)
+    r2d = torch.zeros(N + 1, dtype=torch.int64)
+    r3d[0] = r2d[0] = len(keep)
+    r3d[1:1 + len(keep)] = torch.from_numpy(keep)
+    r2d[1:1 + len(keep)] = torch.from_numpy(want[keep].astype(np.int64))
+    single = projection.Projection.apply(torch.from_numpy(feats[b, v]).to(cuda), r3d.to(cuda), r2d.to(cuda), N)
+    assert mgj.sha(single.cpu().numpy()) == str(gold["%s/single/sha/%d" % (name, b)])
+
+
 def test_frustum_counts_and_best_views(cuda):
-    """Row N2: the loader's best-view selection, all poses of a scene in one launch, fp64 as the reference."""
-    N, P = 8192, 150
-    x, _ = scenes.scannet_scene(90, N)
-    rng = np.random.default_rng(5)
-    centre = x.mean(0)
-    poses = np.stack([scenes.look_at_pose(centre + np.array([np.cos(a) * d, np.sin(a) * d, h]), centre + rng.normal(0, 0.5, 3))
-                      for a, d, h in zip(rng.uniform(0, 6.28, P), rng.uniform(0.5, 4.0, P), rng.uniform(0.0, 2.0, P))])
-    got = projection.frustum_counts(torch.from_numpy(x).to(cuda), torch.from_numpy(poses).to(cuda), INTR, DMIN, DMAX, DIMS).cpu().numpy()
-    helper = projection.ProjectionHelper(INTR, DMIN, DMAX, DIMS, ACC)
-    want = []
-    for q in range(P):
-        cc = helper.compute_frustum_corners(torch.from_numpy(poses[q]))[:, :3, 0]
-        nr = projection.frustum_normals(torch.cat([cc, torch.ones(8, 1)], 1))
-        # the reference's call: fp64 tensors on the CPU (data_utils/ScanNetDataLoader.py:96)
-        full = torch.cat([cc, torch.ones(8, 1)], 1).double()
-        want.append(int(helper.points_in_frustum_cpu(full, nr.double(), torch.from_numpy(x).double())))
-    want = np.array(want)
-    assert np.abs(got - want).max() <= 1 and (got != want).mean() <= 0.02  # rounding-boundary ties only
-    assert got.max() > 500 and (got == 0).any() is not None
-    views = projection.best_views(torch.from_numpy(x).to(cuda), torch.from_numpy(poses).to(cuda), 5, INTR, DMIN, DMAX, DIMS)
-    assert len(views) == 5 and views[0] == int(np.argmax(got))
-    assert all(got[v] > 100 or v == views[0] for v in views)
+    """Row N2: the loader's best-view selection (data_utils/ScanNetDataLoader.py:87-105), all poses of a scene
+    in one launch, fp64 as the reference.  Expected values: the reference's own points_in_frustum_cpu on the host
+    (fixture).  With the reference's corners / normals the counts must be identical; with the product's own parameter
+    kernel a count may differ only by points that sit on a rounding boundary of a plane test."""
+    gold = np.load(PROJ)
+    x, poses = mgj.frustum_inputs()
+    want = gold["frustum/counts"]
+    cor, nrm = gold["frustum/corners"], gold["frustum/normals"]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    exact = projection.frustum_counts(t(x), None, mgj.INTRINSIC, mgj.DEPTH_MIN, mgj.DEPTH_MAX, mgj.IMAGE_DIMS,
+                                      view_parameters=(t(cor[:, 2]), t(cor[:, 4]), t(nrm))).cpu().numpy()
+    np.testing.assert_array_equal(exact, want)
+    got = projection.frustum_counts(t(x), t(poses), mgj.INTRINSIC, mgj.DEPTH_MIN, mgj.DEPTH_MAX, mgj.IMAGE_DIMS).cpu().numpy()
+    # points within fp32 noise of a plane's -0.005 threshold, per pose (fp64 evaluation of the reference's parameters)
+    p = x.astype(np.float64)
+    near = np.zeros(len(want), np.int64)
+    for q in range(len(want)):
+        close = np.zeros(len(p), bool)
+        for k in range(6):
+            s = 100.0 * ((p - cor[q, 2 if k < 3 else 4].astype(np.float64)) @ nrm[q, k].astype(np.float64))
+            close |= np.abs(s + 0.5) < 1e-3
+        near[q] = close.sum()
+    assert (np.abs(got - want) <= near).all(), (got - want)[np.abs(got - want) > near]
+    assert (got != want).mean() <= 0.05
+    views = projection.best_views(t(x), t(poses), 5, mgj.INTRINSIC, mgj.DEPTH_MIN, mgj.DEPTH_MAX, mgj.IMAGE_DIMS)
+    if (got == want).all():
+        assert views == gold["frustum/best5"].tolist()
+    assert views[0] == int(np.argmax(got))
