@@ -272,3 +272,20 @@ def test_backbone_nuscenes_16384_points(cuda, precision):
     with torch.no_grad():
         got = copy.deepcopy(model).to(cuda)(xyz.to(cuda), feat.to(cuda))
     assert_close(got, want, tol(precision, 2e-5))
+
+
+def test_backbone_nuscenes_raw_sweep_size_batch2(cuda, precision):
+    """BASELINE config 4 at its stress size: two synthetic 32-beam sweeps resampled to 34 720 points (with replacement, so
+    duplicate returns and FPS ties occur), cluster / DSMEM FPS with 4096 centroids, cell-list ball query and 3-NN."""
+    torch.manual_seed(8)
+    model = PointNet2Backbone().eval()
+    randomize_bn(model, 11)
+    n = 34720
+    sweeps = [scenes.lidar_sweep(20 + i, n) for i in range(2)]
+    xyz = torch.from_numpy(np.stack([s[0][:n].T for s in sweeps]).copy())
+    feat = torch.from_numpy(np.stack([s[1][:n].T for s in sweeps]).copy())
+    want = modules_ref.backbone_forward_ref(model, xyz, feat)
+    with torch.no_grad():
+        got = copy.deepcopy(model).to(cuda)(xyz.to(cuda), feat.to(cuda))
+    assert got.shape == (2, 128, n)
+    assert_close(got, want, tol(precision, 2e-5))

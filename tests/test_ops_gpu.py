@@ -84,6 +84,18 @@ def test_fps_few_warp_kernels_agree_with_reference(cuda, mode, kind, B, N, M):
     np.testing.assert_array_equal(got, orc.furthest_point_sample(xyz, M))
 
 
+@pytest.mark.parametrize("kind,B,N,M", [("dup", 1, 49153, 60), ("lattice", 1, 60000, 48), ("dup", 2, 65536, 40), ("uniform", 1, 57000, 64),
+                                        ("dup", 1, 70000, 40), ("dup", 2, 131072, 24), ("lattice", 1, 100000, 32), ("uniform", 1, 65537, 48)])
+def test_fps_large_clouds_bit_exact(cuda, kind, B, N, M):
+    """The 8-CTA cluster kernel (49152 < N <= 65536, tie key extended by the thread's half) and fps_global_kernel
+    (N > 65536, running minima in caller scratch), with duplicated / lattice points so that exact ties are frequent."""
+    xyz = clouds(kind, B, N, 7 * N + M)
+    got = pu.furthest_point_sample(dev(xyz, cuda), M).cpu().numpy()
+    np.testing.assert_array_equal(got, orc.furthest_point_sample(xyz, M))
+    if ref_cuda.available():
+        np.testing.assert_array_equal(got, ref_cuda.furthest_point_sample(dev(xyz, cuda), M).cpu().numpy())
+
+
 def test_fps_properties_full_size(cuda):
     # BASELINE config size, properties that need no oracle: first index 0, unique picks while distinct
     # points remain, and the running minimum distance of the picks is non-increasing.
