@@ -135,21 +135,33 @@ def cpu_reference_scenes_per_sec(steps, warmup, sample_scenes):
     return sample_scenes * steps / dt, dt / steps * 1e3, max(cores, orc.num_threads())
 
 
+def workload_config(batch, world):
+    """The `config` object shared by both arms (the driver compares them)."""
+    return {"workload": "PointNet2SemSeg SSG forward (4 SA + 4 FP + head), ScanNet-shaped synthetic scenes drawn with "
+                        "replacement, 8192 pts, batch %d per GPU, scene-sharded (no collective)" % batch,
+            "npoints": NPOINTS, "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": "scene-sharded x%d" % world}
+
+
 def run_reference(args):
+    """The reference arm: the reference ships no CPU implementation of this path (model/pointnet2_utils.py:7 hard-imports
+    the CUDA extension), so this times the restated CPU path -- the C oracle's geometry (OpenMP over the clouds of the
+    batch) + torch CPU conv/BN on all host threads -- on the SAME config as our arm: one step = one batch of `--batch`
+    scenes.  Under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    sample = 4
+    sample = args.batch
     value, ms, cores = cpu_reference_scenes_per_sec(args.steps, args.warmup, sample)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PointNet2SemSeg SSG forward, ScanNet-shaped synthetic scenes, 8192 pts; CPU step = %d scenes" % sample,
-                   "npoints": NPOINTS, "batch_per_step": sample},
+        "config": workload_config(args.batch, max(world, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "scenes/s", "cores": cores, "kind": "port",
-                         "sample": "%d scenes per step x %d steps; restated CPU path (the reference ships no CPU implementation): "
-                                   "C oracle geometry with OpenMP + torch CPU conv/BN" % (sample, args.steps)},
+                         "sample": "%d scenes per step (one full batch of the workload) x %d steps; restated CPU path (the reference "
+                                   "ships no CPU implementation): C oracle geometry, OpenMP over the clouds of the batch, + torch CPU "
+                                   "conv/BN on all host threads" % (sample, args.steps)},
         "e2e": {"value": value, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -178,36 +190,132 @@ def time_ref_gpu(model, device, batch):
                     "TF32 allowed as torch defaults), batch %d, inputs resident, 5 steps" % batch}
 
 
-def time_train_step_msg(device, batch=8, steps=4):
-    """BASELINE config[1] as a data point: MSG semseg TRAIN step (forward + backward + Adam) on this GPU.  Geometry and its
-    backward scatter-adds are our kernels; conv / BatchNorm(train) / autograd are torch, as in the reference (the fused
-    training kernels are SURVEY 8f row N1, not built yet)."""
+def time_train_step_msg(device, batch=4, steps=4, world=1, rank=0):
+    """BASELINE config[1]: MSG semseg TRAIN step (forward + backward + Adam), `batch` scenes per GPU, scenes sharded over
+    the ranks; under torchrun the gradients are all-reduced by DDP (NCCL) -- the only collective of the whole path.
+    Timed on the device (CUDA events), max over ranks by the caller."""
     import torch.nn.functional as F
     from pn2_b200 import scenes
     from pn2_b200.models import PointNet2Multiview2Msg
     torch.manual_seed(0)
     net = PointNet2Multiview2Msg(NUM_CLASSES).to(device).train()
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
-    pts = torch.from_numpy(scenes.scannet_batch(77, batch, NPOINTS)).to(device)
+    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[device.index]) if world > 1 else net
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    pts = torch.from_numpy(scenes.scannet_batch(77 + 1000 * rank, batch, NPOINTS)).to(device)
     xyz = pts[:, :, :3].permute(0, 2, 1).contiguous()
     img = torch.randn(batch, 128, NPOINTS, device=device)
     target = (pts[:, :, 2].clamp(0, 2.69) / 2.7 * 20).long() + 1
-    ts = []
+    evs = []
     for i in range(steps + 2):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         opt.zero_grad(set_to_none=True)
-        loss = F.cross_entropy(net(xyz, img).reshape(-1, NUM_CLASSES), target.reshape(-1), ignore_index=0)
+        loss = F.cross_entropy(model(xyz, img).reshape(-1, NUM_CLASSES), target.reshape(-1), ignore_index=0)
         loss.backward()
         opt.step()
-        torch.cuda.synchronize()
-        ts.append(time.perf_counter() - t0)
-    ms = float(np.median(ts[2:])) * 1e3
-    del net, opt
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = float(np.median([x.elapsed_time(y) for x, y in evs[2:]]))
+    del net, opt, model
     torch.cuda.empty_cache()
-    return {"value": batch / ms * 1e3, "unit": "scenes/s", "ms_per_step": ms, "batch": batch,
-            "what": "PointNet2Multiview2Msg point branch (model/pointnet2multiview.py:179-233), fwd + bwd + Adam, synthetic lifted "
-                    "features, one GPU; geometry on our kernels, conv/BN/autograd torch (unfused training path)"}
+    return ms
+
+
+def time_other_configs(device, B):
+    """BASELINE configs 2-4 on one GPU as data points (inference, fused path, CUDA events): the MSG stack forward (config 2's
+    network), multi-view lifting + point branch (config 3), the nuScenes backbone at 16 384 and 34 720 points (config 4)."""
+    from pn2_b200 import scenes
+    from pn2_b200.models import PipelinedForward, PointNet2Backbone, PointNet2Multiview2, PointNet2Multiview2Msg
+    out = {}
+
+    def eager_ms(fn, iters=5):
+        with torch.no_grad():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(iters):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record(); torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    def pipelined_ms(model, a, b_, n=40):
+        pipe = PipelinedForward(model, a, b_, depth=6)
+        for _ in range(12):
+            pipe.submit(a, b_)
+        pipe.join()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            pipe.submit(a, b_)
+        pipe.join()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    torch.manual_seed(0)
+    pts = scenes.scannet_batch(0, B, NPOINTS).astype(np.float32)
+    xyz = torch.from_numpy(pts[:, :, :3]).to(device).permute(0, 2, 1).contiguous()
+    img = torch.randn(B, 128, NPOINTS, device=device)
+    msg = PointNet2Multiview2Msg(NUM_CLASSES).eval().to(device)
+    ms = pipelined_ms(msg, xyz, img)
+    out["config2_msg_forward"] = {"ms_per_step": ms, "value": B / ms * 1e3, "unit": "scenes/s", "batch": B,
+                                  "what": "PointNet2Multiview2Msg point branch forward (MSG SA x6, FP x4, head; synthetic lifted features), "
+                                          "6 graphs in flight"}
+    del msg
+    V = 3
+    mv = [scenes.multiview_inputs(7000 + i, pts[i, :, :3], V, 128) for i in range(B)]
+    feats = torch.from_numpy(np.stack([m[0] for m in mv])).to(device)
+    depth = torch.from_numpy(np.stack([m[1] for m in mv])).to(device)
+    poses = torch.from_numpy(np.stack([m[2] for m in mv]).astype(np.float32)).to(device)
+    ssg = PointNet2Multiview2(NUM_CLASSES).eval().to(device)
+    ms = eager_ms(lambda: ssg.forward_views(xyz, feats, depth, poses, scenes.SCANNET_INTRINSIC, 0.1, 4.0, scenes.SCANNET_IMAGE_DIMS, 0.05))
+    out["config3_forward_views"] = {"ms_per_step": ms, "value": B / ms * 1e3, "unit": "scenes/s", "batch": B,
+                                    "what": "PointNet2Multiview2.forward_views: lifting of 3 views (128 x 32 x 41 maps, ENet output as "
+                                            "input, first-non-zero reduction) + point branch, eager"}
+    ms = pipelined_ms(ssg, xyz, img)
+    out["config3_point_branch"] = {"ms_per_step": ms, "value": B / ms * 1e3, "unit": "scenes/s", "batch": B,
+                                   "what": "PointNet2Multiview2 point branch (lifted features resident), 6 graphs in flight"}
+    del ssg, feats, depth, poses
+    bb = PointNet2Backbone().eval().to(device)
+    for n in (16384, 34720):
+        sw = [scenes.lidar_sweep(50 + i, n) for i in range(16)]
+        x3 = torch.from_numpy(np.stack([s_[0] for s_ in sw]).astype(np.float32)).to(device).permute(0, 2, 1).contiguous()
+        f2 = torch.from_numpy(np.stack([s_[1] for s_ in sw]).astype(np.float32)).to(device).permute(0, 2, 1).contiguous()
+        ms = eager_ms(lambda: bb(x3, f2))
+        out["config4_backbone_n%d" % n] = {"ms_per_step": ms, "value": 16 / ms * 1e3, "unit": "sweeps/s", "batch": 16,
+                                           "what": "nuScenes backbone (model/pointmaskrcnn.py:8-32), batch 16 x %d points, eager" % n}
+        del x3, f2
+    del bb
+    torch.cuda.empty_cache()
+    return out
+
+
+def ncu_traffic(kernel_substr="row_mlp_tc_kernel_bf16(", grid=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` summary of this
+    round (profiles/r2_tc_mlp_ncu_full_summary.csv, written by scripts/summarize_ncu_full.py from the .ncu-rep): the LAST
+    matching launch of one forward (fp1 + head).  Returns (bytes or None, file name)."""
+    import csv
+    for name in ("r2_tc_mlp_ncu_full_summary.csv", "r1_tc_mlp_v5_ncu_full_summary.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        try:
+            rows = list(csv.reader(open(path)))
+            head = rows[0]
+            ir, iw = head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
+            units = rows[1]
+            scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+            hit = [r for r in rows[2:] if r and kernel_substr in r[0]]
+            if hit:
+                r = hit[-1]
+                return float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0), "profiles/" + name
+        except (ValueError, IndexError, OSError):
+            continue
+    return None, None
 
 
 def op_rooflines(device, batch, pk):
@@ -283,6 +391,9 @@ def op_rooflines(device, batch, pk):
 def run_ours(args):
     import torch.distributed as dist
     from pn2_b200 import _lib
+    from pn2_b200 import pointnet_util as _pu
+    from pn2_b200 import scenes as _scenes
+    from pn2_b200.models import GraphedForward, PipelinedForward
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -296,20 +407,14 @@ def run_ours(args):
     pk = peaks()
     B = args.batch
     if args.fps_mode:
-        import ctypes
-        from pn2_b200 import _lib
-        _lib.load().pn2_debug_set_fps_mode(ctypes.c_int(args.fps_mode))
+        _lib.load().pn2_debug_set_fps_mode(args.fps_mode)
     if args.tc_max_ctas > 0:
-        import ctypes
-        from pn2_b200 import _lib
-        _lib.load().pn2_debug_set_tc_max_ctas(ctypes.c_int(args.tc_max_ctas))
-    from pn2_b200 import pointnet_util as _pu
+        _lib.load().pn2_debug_set_tc_max_ctas(args.tc_max_ctas)
     _pu.set_mlp_precision(args.precision)  # the drop-in modules default to fp32 (1e-5 parity); the benchmark path is bf16
     model = build_model(device)
     # rotating inputs: 24 distinct batches = 151 MB of input (+ the activations they produce) > the 126 MB L2
     n_rot = 24
     hosts = host_batches(rank, B, 8)
-    from pn2_b200 import scenes as _scenes
     devs = [torch.from_numpy(_scenes.scannet_batch(100000 * rank + 1000 + i * B, B, NPOINTS)).to(device).permute(0, 2, 1).contiguous()
             for i in range(n_rot)]  # (B, 6, N) resident, as the train script feeds it
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
@@ -319,12 +424,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    from pn2_b200.models import GraphedForward, PipelinedForward
     ex_xyz, ex_pts = devs[0][:, :3].contiguous(), devs[0][:, 3:].contiguous()
     graphed = None if args.no_graph else GraphedForward(model, ex_xyz, ex_pts)
     depth = 1 if args.no_graph else max(1, args.pipeline)
     pipe = PipelinedForward(model, ex_xyz, ex_pts, depth) if depth > 1 else None
-
     clocks = ClockSampler(local)
 
     def step(i):
@@ -332,6 +435,67 @@ def run_ours(args):
         if graphed is not None:
             return graphed.run(x[:, :3], x[:, 3:])
         return model(x[:, :3], x[:, 3:])
+
+    def run_e2e(pipe_, graphed_, out_shape, out_dtype, fwd, warm):
+        """Pinned host (B, N, 6) -> H2D -> forward -> D2H of the result, every step.  `warm` untimed steps of the same
+        protocol run first (pipeline fill, first touch of the pinned buffers), then exactly args.steps timed ones.  The
+        read-back is split in two halves on two copy streams so that it overlaps the next batch's H2D and forward."""
+        n_slots = max(depth, 1)
+        stages = [torch.empty((B, NPOINTS, 6), dtype=torch.float32, device=device) for _ in range(n_slots)]
+        outs_host = [torch.empty(out_shape, dtype=out_dtype).pin_memory() for _ in range(n_slots)]
+        copy_in = torch.cuda.Stream(device)
+        copy_out = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
+        slot_free = [None] * n_slots
+        half = max(B // 2, 1)
+
+        def one(i):
+            k = i % n_slots
+            with torch.cuda.stream(copy_in):
+                if slot_free[k] is not None:
+                    copy_in.wait_event(slot_free[k])   # the previous forward of this slot has consumed its staging buffer
+                stages[k].copy_(hosts[i % len(hosts)], non_blocking=True)
+                h2d = torch.cuda.Event()
+                h2d.record(copy_in)
+            x = stages[k].permute(0, 2, 1)
+            if pipe_ is not None:
+                y, done, st = pipe_.submit(x[:, :3], x[:, 3:], after=h2d)
+            else:
+                torch.cuda.current_stream().wait_event(h2d)
+                y = graphed_.run(x[:, :3], x[:, 3:]) if graphed_ is not None else fwd(x[:, :3], x[:, 3:])
+                done = torch.cuda.Event()
+                done.record()
+                st = torch.cuda.current_stream()
+            slot_free[k] = done
+            for c, (lo, hi) in enumerate(((0, half), (half, B))):
+                if lo >= hi:
+                    continue
+                with torch.cuda.stream(copy_out[c]):
+                    copy_out[c].wait_event(done)
+                    outs_host[k][lo:hi].copy_(y[lo:hi], non_blocking=True)
+                    d2h = torch.cuda.Event()
+                    d2h.record(copy_out[c])
+                st.wait_event(d2h)  # the slot's static output may only be overwritten after it has been read back
+
+        def drain():
+            if pipe_ is not None:
+                pipe_.join()
+            for c in copy_out:
+                torch.cuda.current_stream().wait_stream(c)
+
+        copy_in.wait_stream(torch.cuda.current_stream())
+        for i in range(warm):
+            one(i)
+        drain()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        copy_in.wait_stream(torch.cuda.current_stream())
+        for i in range(args.steps):
+            one(warm + i)
+        drain()
+        b.record()
+        barrier()
+        return a.elapsed_time(b)
 
     with torch.no_grad():
         for i in range(args.warmup):
@@ -388,88 +552,100 @@ def run_ours(args):
         model.single_stream = False
         dom_ms = [a.elapsed_time(b) for a, b in timers.get("fp1_head", [])][1:]
         # ---- end to end: pinned host (B,N,6) -> H2D -> forward -> D2H of the result, every step ----------------------
-        def run_e2e(pipe_, graphed_, out_shape, out_dtype, fwd):
-            n_slots = max(depth, 1)
-            stages = [torch.empty((B, NPOINTS, 6), dtype=torch.float32, device=device) for _ in range(n_slots)]
-            outs_host = [torch.empty(out_shape, dtype=out_dtype).pin_memory() for _ in range(n_slots)]
-            copy_in, copy_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
-            slot_free = [None] * n_slots
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            copy_in.wait_stream(torch.cuda.current_stream())
-            for i in range(args.steps):
-                k = i % n_slots
-                with torch.cuda.stream(copy_in):
-                    if slot_free[k] is not None:
-                        copy_in.wait_event(slot_free[k])   # the previous forward of this slot has consumed its staging buffer
-                    stages[k].copy_(hosts[i % len(hosts)], non_blocking=True)
-                    h2d = torch.cuda.Event()
-                    h2d.record(copy_in)
-                x = stages[k].permute(0, 2, 1)
-                if pipe_ is not None:
-                    y, done, st = pipe_.submit(x[:, :3], x[:, 3:], after=h2d)
-                else:
-                    torch.cuda.current_stream().wait_event(h2d)
-                    y = graphed_.run(x[:, :3], x[:, 3:]) if graphed_ is not None else fwd(x[:, :3], x[:, 3:])
-                    done = torch.cuda.Event()
-                    done.record()
-                    st = torch.cuda.current_stream()
-                slot_free[k] = done
-                with torch.cuda.stream(copy_out):
-                    copy_out.wait_event(done)
-                    outs_host[k].copy_(y, non_blocking=True)
-                    d2h = torch.cuda.Event()
-                    d2h.record(copy_out)
-                st.wait_event(d2h)  # the slot's static output may only be overwritten after it has been read back
-            if pipe_ is not None:
-                pipe_.join()
-            torch.cuda.current_stream().wait_stream(copy_out)
-            b.record()
-            barrier()
-            return a.elapsed_time(b)
-
+        e2e_warm = max(args.warmup, 2 * depth)
         # (1) the reference protocol: the full fp32 logits come back (train_scannet_semseg.py:204 `pred.cpu().numpy()`)
         clocks.begin()
-        e2e_ms = run_e2e(pipe, graphed, (B, NPOINTS, NUM_CLASSES), torch.float32, model)
+        e2e_ms = run_e2e(pipe, graphed, (B, NPOINTS, NUM_CLASSES), torch.float32, model, e2e_warm)
         clocks.end()
         # (2) predict(): the arg-max the evaluation loop takes from those logits, fused into the head kernel; 1 byte per point
         e2e_lab_ms = 0.0
         if model.can_fuse_labels() and not args.no_graph:
             pipe_l = PipelinedForward(model, ex_xyz, ex_pts, depth, labels=True) if depth > 1 else None
             graphed_l = GraphedForward(model, ex_xyz, ex_pts, labels=True) if depth <= 1 else None
-            for i in range(args.warmup):
-                if pipe_l is not None:
-                    pipe_l.submit(devs[i % n_rot][:, :3], devs[i % n_rot][:, 3:])
-                else:
-                    graphed_l.run(devs[i % n_rot][:, :3], devs[i % n_rot][:, 3:])
-            if pipe_l is not None:
-                pipe_l.join()
             clocks.begin()
-            e2e_lab_ms = run_e2e(pipe_l, graphed_l, (B, NPOINTS), torch.uint8, model.predict)
+            e2e_lab_ms = run_e2e(pipe_l, graphed_l, (B, NPOINTS), torch.uint8, model.predict, e2e_warm)
             clocks.end()
+            del pipe_l, graphed_l
         clocks.close()
 
-    t = torch.tensor([total_ms, e2e_ms, e2e_lab_ms], dtype=torch.float64, device=device)
+        # ---- further legs of the same line (not the headline): fp32 MLP path, BASELINE config 1's batch of 2 ----------
+        legs = {}
+        if not args.no_graph and not args.no_extras:
+            def pipelined_value(model_, xs, steps_, depth_):
+                pp = PipelinedForward(model_, xs[0][:, :3].contiguous(), xs[0][:, 3:].contiguous(), depth_)
+                for i in range(max(3, depth_)):
+                    pp.submit(xs[i % len(xs)][:, :3], xs[i % len(xs)][:, 3:])
+                pp.join()
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(steps_):
+                    pp.submit(xs[i % len(xs)][:, :3], xs[i % len(xs)][:, 3:])
+                pp.join()
+                e1.record()
+                barrier()
+                return e0.elapsed_time(e1) / steps_
+
+            def one_at_a_time_ms(model_, xs, steps_):
+                g = GraphedForward(model_, xs[0][:, :3].contiguous(), xs[0][:, 3:].contiguous())
+                ts = []
+                for i in range(steps_ + 3):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    g.run(xs[i % len(xs)][:, :3], xs[i % len(xs)][:, 3:])
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                return float(np.median(ts[3:]))
+
+            if args.precision == "bf16":
+                prev = _pu.set_mlp_precision("fp32")
+                try:
+                    k32 = max(3, min(args.steps, 20))
+                    ms32 = pipelined_value(model, devs, k32, depth)
+                    legs["fp32"] = {"value": world * B / ms32 * 1e3, "unit": "scenes/s", "ms_per_step": ms32, "steps": k32, "dtype": "f32",
+                                    "what": "the same workload on the fp32 FFMA shared-MLP kernels (row_mlp.cu; 1e-5 relative to the "
+                                            "reference instead of the bf16 path's 2e-2), %d batches in flight" % depth}
+                finally:
+                    _pu.set_mlp_precision(prev)
+            b2 = [d[:2].contiguous() for d in devs]   # BASELINE configs[0]: batch 2
+            lat = one_at_a_time_ms(model, b2, 20)
+            thr = pipelined_value(model, b2, max(20, min(args.steps, 100)), depth)
+            legs["batch2"] = {"latency_ms": lat, "value_one_at_a_time": world * 2 / lat * 1e3, "value": world * 2 / thr * 1e3, "unit": "scenes/s",
+                              "ms_per_step": thr,
+                              "what": "BASELINE configs[0] shape: batch 2 x 8192 points per GPU.  latency_ms = one CUDA-graph forward at a "
+                                      "time, L2 flushed in between; value = %d graphs of batch 2 in flight" % depth}
+
+    # ---- BASELINE config[1]: the MSG train step, scenes sharded over the ranks, DDP gradient all-reduce -----------------
+    train_ms = 0.0
+    if not args.no_extras:
+        train_ms = time_train_step_msg(device, batch=4, steps=4, world=world, rank=rank)
+
+    t = torch.tensor([total_ms, e2e_ms, e2e_lab_ms, train_ms] + [legs.get("fp32", {}).get("ms_per_step", 0.0),
+                                                                 legs.get("batch2", {}).get("ms_per_step", 0.0)],
+                     dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, e2e_lab_ms = t.tolist()
+    total_ms, e2e_ms, e2e_lab_ms, train_ms, ms32_max, msb2_max = t.tolist()
     if rank == 0:
         value = world * B * args.steps / (total_ms / 1e3)
         e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+        cfg = workload_config(B, world)
         line = {
             "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "ms_per_step_one_at_a_time": serial_ms / args.steps,
             "value_one_at_a_time": world * B * args.steps / (serial_ms / 1e3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": model.compute_dtype, "data": "synthetic",
-            "config": {"workload": "PointNet2SemSeg SSG forward (4 SA + 4 FP + head), ScanNet-shaped synthetic scenes drawn with "
-                                   "replacement, 8192 pts, batch %d per GPU, scene-sharded (no collective)" % B,
-                       "npoints": NPOINTS, "batch_per_gpu": B, "global_batch": B * world, "parallelism": "scene-sharded x%d" % world,
-                       "l2": "inputs rotate over %d distinct batches (%.0f MB > L2); the one-at-a-time figure flushes L2 (256 MiB) "
+            "config": cfg,
+            "timing": {"l2": "inputs rotate over %d distinct batches (%.0f MB > L2); the one-at-a-time figure flushes L2 (256 MiB) "
                              "between steps" % (n_rot, n_rot * B * NPOINTS * 6 * 4 / 1e6),
-                       "launch": "eager, 3 streams" if graphed is None else "CUDA graph replay (3 streams captured), %d batches in flight" % depth},
+                       "launch": "eager, 3 streams" if graphed is None else "CUDA graph replay (3 streams captured), %d batches in flight" % depth,
+                       "e2e_warmup_steps": e2e_warm},
             "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": B * NPOINTS * 6 * 4,
-                    "d2h_bytes_per_step": B * NPOINTS * NUM_CLASSES * 4, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": B * NPOINTS * NUM_CLASSES * 4, "ms_per_step": e2e_ms / args.steps,
+                    "what": "pinned host (B, N, 6) -> H2D -> forward -> D2H of the (B, N, 21) fp32 logits every step (the reference's "
+                            "evaluation protocol, train_scannet_semseg.py:204); %d untimed warm-up steps" % e2e_warm},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "tflops": value * FLOPS_PER_SCENE / 1e12,
@@ -480,30 +656,47 @@ def run_ours(args):
                                   "ms_per_step": e2e_lab_ms / args.steps,
                                   "what": "same protocol through PointNet2SemSeg.predict(): per-point class predictions (uint8) "
                                           "read back instead of fp32 logits; the arg-max is fused into the head kernel"}
+        if "fp32" in legs:
+            legs["fp32"]["ms_per_step"] = ms32_max
+            legs["fp32"]["value"] = world * B / ms32_max * 1e3
+            line["value_fp32"] = legs["fp32"]
+        if "batch2" in legs:
+            legs["batch2"]["ms_per_step"] = msb2_max
+            legs["batch2"]["value"] = world * 2 / msb2_max * 1e3
+            line["batch2"] = legs["batch2"]
+            line["value_b2_latency_ms"] = legs["batch2"]["latency_ms"]
+        extra = {}
+        if train_ms > 0:
+            extra["config2_msg_train_step"] = {
+                "value": world * 4 / train_ms * 1e3, "unit": "scenes/s", "ms_per_step": train_ms, "batch_per_gpu": 4, "n_gpus": world,
+                "what": "BASELINE configs[1]: PointNet2Multiview2Msg point branch (model/pointnet2multiview.py:179-233), forward + "
+                        "backward + Adam, 4 scenes per GPU, scene-sharded" + (", DDP gradient all-reduce over NCCL" if world > 1 else "")
+                        + "; geometry and its backwards on our kernels, conv / BatchNorm(train) / autograd torch"}
         if dom_ms:
             ms = float(np.mean(dom_ms))
             achieved = B * FP1_HEAD_FLOPS_PER_SCENE / (ms / 1e3) / 1e12
             peak = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
+            traffic, traffic_src = ncu_traffic() if B == 32 else (None, None)
             line["roofline"] = {"kernel": "row_mlp_tc_kernel (fused fp1 + head: 3-NN interpolation gather + 131-128-128-128-128-21 "
                                           "tcgen05 MLP over %d rows)" % (B * NPOINTS),
                                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                                # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full at batch 32
-                                # (profiles/r1_tc_mlp_v5_ncu_full_summary.csv, last row); the 22 MB of logits stay in L2
-                                "traffic": 19.14e6 if B == 32 else None,
+                                "traffic": traffic, "traffic_source": traffic_src,
                                 "algorithmic_bytes": B * NPOINTS * (12 + 12 + 24 + 4 * NUM_CLASSES) + B * 1024 * 128 * 2,
                                 "ms": ms, "share_of_step_one_at_a_time": ms / (serial_ms / args.steps),
-                                "peak_source": pk["source"] + " bf16 sustained (kernel timed inside eager steps, alone on the GPU)",
-                                "note": "largest full-GPU kernel of the step; its 128-row tiles are a latency chain (gather -> 5 x [MMA, "
-                                        "TMEM epilogue]) overlapped only across the 3 CTAs of an SM, not tensor bound "
-                                        "(ncu: tensor pipe 16 % active, issue slots 40 %, l1tex 43 %)"}
+                                "peak_source": pk["source"] + " bf16 sustained (kernel timed inside eager steps, alone on the GPU)"}
         if world == 1 and not args.no_extras:
             line["kernels"] = op_rooflines(device, B, pk)
             line["ref_gpu"] = time_ref_gpu(model, device, B)
-            line["train_step_msg"] = time_train_step_msg(device)
-            cpu_v, cpu_ms, cores = cpu_reference_scenes_per_sec(3, 1, 4)
+            with torch.no_grad():
+                extra.update(time_other_configs(device, B))
+            cpu_steps = 3
+            cpu_v, cpu_ms, cores = cpu_reference_scenes_per_sec(cpu_steps, 1, B)
             line["cpu_baseline"] = {"value": cpu_v, "unit": "scenes/s", "cores": cores, "kind": "port",
-                                    "sample": "4 scenes per step x 3 steps (+1 warm-up); restated CPU path (the reference ships "
-                                              "no CPU implementation): C oracle geometry with OpenMP + torch CPU conv/BN"}
+                                    "sample": "%d scenes per step (one full batch) x %d steps (+1 warm-up); restated CPU path (the reference "
+                                              "ships no CPU implementation): C oracle geometry with OpenMP over the clouds + torch CPU "
+                                              "conv/BN on all host threads" % (B, cpu_steps)}
+        if extra:
+            line["extra"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
