@@ -33,6 +33,8 @@ def main():
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
+    from pn2_b200 import pointnet_util
+    pointnet_util.set_mlp_precision("bf16")  # tensor-core shared MLP (2e-2); the modules' default is fp32
     model = PointNet2SemSeg(NUM_CLASSES).eval().to(dev)
     B = args.batch
     rng = np.random.default_rng(0)

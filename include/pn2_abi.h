@@ -266,6 +266,9 @@ void pn2_debug_set_fps_mode(int mode);
 void pn2_debug_set_tc_timestamps(long long *buf);
 /* Caps the resident CTAs per SM of the tensor-core MLP kernel (bench.py --tc-max-ctas; default 8 = no cap). */
 void pn2_debug_set_tc_max_ctas(int n);
+/* Worker warps per 128-row tile of the tensor-core MLP kernel: 4 (up to 4 CTAs per SM), 8 (two warps per TMEM lane
+ * quarter splitting the columns, up to 2 CTAs per SM) or 0 = chosen by launch size (default).  Results are identical. */
+void pn2_debug_set_tc_workers(int n);
 /* Kernel choice of pn2_three_interpolate: 0 automatic, 1 tiled kernels only, 32 the lane-along-channel kernel wherever it
  * applies (+ 256 / 4096 / 512: 256 / 768 / 1024 threads per CTA instead of 512; + 1024: no stores, + 2048: no row reads --
  * bisect probes, results are then meaningless).  scripts/interp_sweep.py. */

@@ -32,7 +32,8 @@
 namespace pn2 {
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 192;      // 4 worker warps + producer + issuer
+constexpr int TC_THREADS_W8 = 320;   // 8 worker warps (two per TMEM lane quarter, splitting the columns) + producer + issuer
 constexpr int TC_ROWS = 128;
 constexpr int KBLK = 64;                       // bf16 elements per 128-byte swizzle row
 constexpr int A_BLOCK_BYTES = TC_ROWS * 128;   // one k-block of A: 128 rows x 128 B
@@ -185,6 +186,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // Instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n  (cute UMMA::InstrDescriptor)
 __device__ __forceinline__ uint32_t umma_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+}
+
+// two fp32 values -> packed bf16x2 (lo in the low half), optionally with ReLU in the same instruction
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi, int relu) {
+    uint32_t d;
+    if (relu)
+        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 
 // byte offset of the 16-byte chunk holding elements [8*c8, 8*c8+8) of row r in a [rows x K] operand
@@ -587,8 +598,12 @@ __device__ __forceinline__ void coop_gather_bf16(const TcParams &p, const RowPre
 
 // Two instantiations (kernels below): fp32 gathered features (lean: 80 registers, 4 CTAs/SM) and bf16 gathered features
 // (96 registers, 3 CTAs/SM).
-template <bool kInBf16>
+template <bool kInBf16, int NWW>
 __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
+    // NWW worker warps: warp w serves TMEM lane quarter (w & 3), i.e. tile rows 32 (w & 3) .. +31; with NWW == 8 the warps
+    // w and w + 4 share a quarter and split its work by columns (half = w >> 2): the gather of a tile has twice the loads
+    // in flight and every epilogue is half as long -- the per-tile latency chain, not issue slots, is what bounds the kernel.
+    constexpr int NHALF = NWW / 4;
     // 1024-byte alignment for the 128B-swizzled operand tiles.  The alignment is REQUESTED on the declaration (no manual
     // round-up through an integer: that hid the address space from the compiler, which then emitted generic LD.E / ST.E
     // for every shared-memory access of the gather and the epilogues) and verified once.
@@ -619,7 +634,7 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
         }
         // one arrival per worker warp (after __syncwarp): every arrival wakes the warps parked on ANY barrier of the CTA,
         // so 128 per-thread arrivals per layer kept the producer / issuer warps spinning (3 M wake-ups per sa1 launch)
-        mbar_init(bar_a, TC_ROWS / 32);
+        mbar_init(bar_a, NWW);
         mbar_init(bar_acc, 1);
         mbar_init(bar_afree, 1);
         for (int q = 0; q < 4; ++q) mbar_init(bar_blk + 8 * q, 1);
@@ -627,9 +642,9 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
     }
     for (int l = 0; l < p.num_layers; ++l) {
         const TcLayer &L = p.layer[l];
-        for (int c = threadIdx.x; c < L.npad; c += TC_THREADS) sbias[L.bias_off + c] = c < L.cout ? __ldg(L.bias + c) : 0.f;
+        for (int c = threadIdx.x; c < L.npad; c += (NWW + 2) * 32) sbias[L.bias_off + c] = c < L.cout ? __ldg(L.bias + c) : 0.f;
     }
-    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    if (warp == NWW + 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -637,7 +652,7 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
 
     // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; barriers, TMEM and biases are set
     // up once.  Several CTAs share an SM, so one CTA's gather / epilogue overlaps another's MMAs.
-    if (warp == 4) {
+    if (warp == NWW) {
         // ===== weight producer: every tile of every layer, in MMA order, through the ring =====
         if (lane == 0) {
             int stage = 0;
@@ -683,7 +698,7 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == NWW + 1) {
         // ===== MMA issuer: all 32 lanes walk the schedule (uniform control flow), one elected lane issues =====
         {
             const uint32_t leader = elect_one();
@@ -763,8 +778,10 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
         }
     } else {
         // ===== gather + epilogue warps: thread <-> row <-> TMEM lane =====
-        const int r = threadIdx.x;  // 0..127
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int r = threadIdx.x & (TC_ROWS - 1);  // tile row = TMEM lane
+        const int wq = warp & 3;                     // lane quarter
+        const int half = warp >> 2;                  // which share of the columns (NWW == 8)
+        const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
         uint32_t it = 0;
         long long out_row = 0;
         bool srow_ok = false;
@@ -808,12 +825,27 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                         const int blk0_end = min(ce, Dm >> 3);
                         const int nc = blk0_end - cb;
                         if ((Dm & 63) == 0 && nc >= 4 && (nc & (nc - 1)) == 0) {
-                            if (p.mode == MODE_SA) coop_gather_bf16<4>(p, pre, a_buf, warp, lane, cb, cb, blk0_end);
-                            else coop_gather_bf16<2>(p, pre, a_buf, warp, lane, cb, cb, blk0_end);
+                            // two warps per quarter: each takes half of the chunk columns of the same 32 rows
+                            const bool split = NHALF == 2 && nc >= 8;
+                            const int ncw = split ? nc >> 1 : nc;
+                            const int c_lo = cb + (split ? half * ncw : 0);
+                            if (split || half == 0) {
+                                if (p.mode == MODE_SA) coop_gather_bf16<4>(p, pre, a_buf, wq, lane, cb, c_lo, c_lo + ncw);
+                                else coop_gather_bf16<2>(p, pre, a_buf, wq, lane, cb, c_lo, c_lo + ncw);
+                            }
                             from = blk0_end;
                         }
                     }
-                    if (from < ce) gather_tail_tc<kInBf16>(p, ctx, dst, from, ce, sk, sk_valid);
+                    if (from < ce) {
+                        // thread-per-row part (fp32 features, tails): the two warps of a quarter take a chunk range each
+                        int t_lo = from, t_hi = ce;
+                        if (NHALF == 2) {
+                            const int mid = from + (((ce - from + 1) >> 1) + 3 & ~3);  // multiples of 4 chunks keep the 128-bit paths
+                            if (half == 0) t_hi = mid < ce ? mid : ce;
+                            else t_lo = mid < ce ? mid : ce;
+                        }
+                        if (t_lo < t_hi) gather_tail_tc<kInBf16>(p, ctx, dst, t_lo, t_hi, sk, sk_valid);
+                    }
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_a);
@@ -852,12 +884,16 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                             mbar_wait(bar_blk + 8 * cb, tile_it & 1);
                             tc_fence_after();
                         }
-                        const int ch0 = cb * 128 + warp * 32;
+                        const int ch0 = cb * 128 + wq * 32;
                         if (ch0 >= cout) continue;  // warp-uniform: e.g. 64 channels keep two warps busy
+                        // two warps per quarter: samples [0, 64) and [64, 128) (whole groups while nsample <= 64)
+                        const bool tsplit = NHALF == 2 && K <= 64;
+                        if (!tsplit && half != 0) continue;
+                        const int s_lo = tsplit ? half * 64 : 0, s_hi = tsplit ? s_lo + 64 : TC_ROWS;
                         const int ch = ch0 + lane;
                         const float bias = bl[ch];
                         float run = 0.f;
-                        for (int s0 = 0; s0 < TC_ROWS; s0 += 32) {
+                        for (int s0 = s_lo; s0 < s_hi; s0 += 32) {
                             uint32_t acc[32];
                             tmem_ld32(lane_base + (uint32_t)(cb * 128 + s0), acc);
                             float v[32];
@@ -900,13 +936,16 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                 } else {
                 float am_best = 0.f;  // running arg-max over the channels of this thread's row (PN2_FLAG_OUT_ARGMAX)
                 int am_idx = -1;
-                for (int c0 = 0; c0 < npad; c0 += 32) {
+                // two warps per quarter alternate 32-column chunks; outputs that need the whole row in one thread (arg-max)
+                // or the warp-private staging (odd row pitch) stay with the first warp
+                const bool csplit = NHALF == 2 && (!last || (!p.out_argmax && ((cout * (p.out_bf16 ? 2 : 4)) & 15) == 0));
+                if (csplit || half == 0)
+                for (int c0 = csplit ? 32 * half : 0; c0 < npad; c0 += csplit ? 64 : 32) {
                     uint32_t acc[32];
                     tmem_ld32(lane_base + (uint32_t)c0, acc);
                     if (!last) {
                         // bias add as packed f32x2, conversion to bf16x2, ReLU on the packed pair (max(bf16(x), 0) ==
                         // bf16(max(x, 0))): ~70 instructions per 32 columns instead of ~130
-                        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 b0 = *reinterpret_cast<const float4 *>(bl + c0 + 8 * q);
@@ -915,15 +954,10 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                             const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 2]), __uint_as_float(acc[8 * q + 3])), make_float2(b0.z, b0.w));
                             const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 4]), __uint_as_float(acc[8 * q + 5])), make_float2(b1.x, b1.y));
                             const float2 s3 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 6]), __uint_as_float(acc[8 * q + 7])), make_float2(b1.z, b1.w));
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(s0.x, s0.y), h1 = __floats2bfloat162_rn(s1.x, s1.y);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(s2.x, s2.y), h3 = __floats2bfloat162_rn(s3.x, s3.y);
-                            if (relu) {
-                                h0 = __hmax2(h0, zero2); h1 = __hmax2(h1, zero2);
-                                h2 = __hmax2(h2, zero2); h3 = __hmax2(h3, zero2);
-                            }
+                            // conversion to bf16x2 with the ReLU folded into the instruction (cvt.rn.relu.bf16x2.f32)
                             uint4 pk;
-                            pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                            pk.x = cvt_bf16x2(s0.x, s0.y, relu); pk.y = cvt_bf16x2(s1.x, s1.y, relu);
+                            pk.z = cvt_bf16x2(s2.x, s2.y, relu); pk.w = cvt_bf16x2(s3.x, s3.y, relu);
                             *reinterpret_cast<uint4 *>(a_buf + swz_chunk(r, (c0 >> 3) + q, TC_ROWS)) = pk;
                         }
                         continue;
@@ -979,7 +1013,7 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                             }
                         } else {
                             // odd widths (the 21-class head): transpose through the (now idle) A buffer, one row per store
-                            float *stg = reinterpret_cast<float *>(a_buf) + warp * (32 * 33);
+                            float *stg = reinterpret_cast<float *>(a_buf) + wq * (32 * 33);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
                             __syncwarp();
@@ -987,7 +1021,7 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                             if (col < cout) {
 #pragma unroll 8
                                 for (int rr = 0; rr < 32; ++rr) {
-                                    const long long dst = srow[warp * 32 + rr];
+                                    const long long dst = srow[wq * 32 + rr];
                                     if (dst >= 0) {
                                         if (p.out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.out)[(size_t)dst * cout + col] = __float2bfloat16_rn(stg[rr * 33 + lane]);
                                         else p.out[(size_t)dst * cout + col] = stg[rr * 33 + lane];
@@ -1010,21 +1044,24 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
             ++tile_it;
             // the FP store staging aliases other warps' rows of A: all four warps leave the tile together
             tc_fence_before();
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(NWW * 32) : "memory");
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == NWW + 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // Entry points.  fp32 features: 80 registers, 4 CTAs/SM.  bf16 features: 96 registers (a few spilled words) is what
 // 3 CTAs x 6 warps allow -- the 18 warps spread 5/5/4/4 over the four 16 K-register partitions (__maxnreg__(112) removes
 // the spills and drops to 2 CTAs/SM: fp1+head 120 -> 164 us); blocks that shared memory or TMEM limit to <= 2 CTAs/SM
 // anyway use the un-spilled build.
-__global__ void __launch_bounds__(TC_THREADS, 4) row_mlp_tc_kernel_f32(const __grid_constant__ TcParams p) { row_mlp_tc_body<false>(p); }
-__global__ void __launch_bounds__(TC_THREADS, 3) row_mlp_tc_kernel_bf16(const __grid_constant__ TcParams p) { row_mlp_tc_body<true>(p); }
-__global__ void __launch_bounds__(TC_THREADS, 2) row_mlp_tc_kernel_bf16_wide(const __grid_constant__ TcParams p) { row_mlp_tc_body<true>(p); }
+__global__ void __launch_bounds__(TC_THREADS, 4) row_mlp_tc_kernel_f32(const __grid_constant__ TcParams p) { row_mlp_tc_body<false, 4>(p); }
+__global__ void __launch_bounds__(TC_THREADS, 3) row_mlp_tc_kernel_bf16(const __grid_constant__ TcParams p) { row_mlp_tc_body<true, 4>(p); }
+__global__ void __launch_bounds__(TC_THREADS, 2) row_mlp_tc_kernel_bf16_wide(const __grid_constant__ TcParams p) { row_mlp_tc_body<true, 4>(p); }
+// Eight worker warps per 128-row tile, at most two CTAs per SM (102 registers): half the per-tile latency chain.
+__global__ void __launch_bounds__(TC_THREADS_W8, 2) row_mlp_tc_kernel_f32_w8(const __grid_constant__ TcParams p) { row_mlp_tc_body<false, 8>(p); }
+__global__ void __launch_bounds__(TC_THREADS_W8, 2) row_mlp_tc_kernel_bf16_w8(const __grid_constant__ TcParams p) { row_mlp_tc_body<true, 8>(p); }
 
 // ---- weight packing -----------------------------------------------------------------------------------
 // Packed image of one layer: for nb in n-blocks, for kb in k-blocks: a [nblk rows x 64 bf16] tile, row n at n*128 B,
@@ -1136,6 +1173,7 @@ Plan make_plan_capped(const pn2_mlp *mlp, int nblk_cap) {
 }
 
 int g_tc_max_ctas = 8;  // developer knob (pn2_debug_set_tc_max_ctas)
+int g_tc_workers = 0;   // worker warps per tile: 0 = by launch size, 4, or 8 (pn2_debug_set_tc_workers)
 
 int ctas_per_sm(const Plan &P) {
     int per_sm = (int)((TC_SMEM_LIMIT + 1024) / P.smem_bytes);
@@ -1222,10 +1260,19 @@ int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, c
     int per_sm = ctas_per_sm(P);
     if (p.in_bf16 && per_sm > 3) per_sm = 3;  // register budget of the bf16-input build
     void (*kernel)(TcParams) = !p.in_bf16 ? row_mlp_tc_kernel_f32 : (per_sm <= 2 ? row_mlp_tc_kernel_bf16_wide : row_mlp_tc_kernel_bf16);
+    int threads = TC_THREADS;
+    // small launches (a few tiles per SM at most) cannot fill the SM with tiles in flight: split each tile over 8 worker
+    // warps instead (measured, batch 32: sa3 31 -> 29, sa4 27 -> 25, fp4 40 -> 37, fp3 31 -> 28, fp2 31 -> 29 us; launches
+    // with many tiles per SM are faster with 3-4 resident CTAs of 4 worker warps: sa1 93 vs 133 us)
+    if (g_tc_workers == 8 || (g_tc_workers == 0 && tiles <= 4ll * sm_count())) {
+        if (per_sm > 2) per_sm = 2;
+        kernel = p.in_bf16 ? row_mlp_tc_kernel_bf16_w8 : row_mlp_tc_kernel_f32_w8;
+        threads = TC_THREADS_W8;
+    }
     PN2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
     long long grid = (long long)per_sm * sm_count();
     if (grid > tiles) grid = tiles;
-    kernel<<<(unsigned)grid, TC_THREADS, P.smem_bytes, s>>>(p);
+    kernel<<<(unsigned)grid, threads, P.smem_bytes, s>>>(p);
     PN2_LAUNCH_OK("row_mlp_tc_kernel");
     return PN2_OK;
 }
@@ -1234,6 +1281,7 @@ int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, c
 }  // namespace pn2
 
 extern "C" void pn2_debug_set_tc_max_ctas(int n) { pn2::g_tc_max_ctas = n < 1 ? 1 : n; }
+extern "C" void pn2_debug_set_tc_workers(int n) { pn2::g_tc_workers = (n == 8 || n == 4) ? n : 0; }
 
 extern "C" int pn2_mlp_bf16_supported(const pn2_mlp *mlp) {
     if (!mlp || mlp->num_layers < 1 || mlp->num_layers > PN2_MAX_LAYERS) return 0;

@@ -17,6 +17,7 @@ Two execution paths per module:
     kernels for the geometry, torch.nn for conv/BN -- with identical semantics.
 """
 import ctypes
+import os
 import threading
 from time import time
 
@@ -99,7 +100,9 @@ class FoldedMlp:
         return buf
 
 
-_PRECISION = "fp32"
+_PRECISION = os.environ.get("PN2_MLP_PRECISION", "fp32")  # "fp32" | "bf16"; see set_mlp_precision
+if _PRECISION not in ("bf16", "fp32"):
+    raise ValueError("PN2_MLP_PRECISION must be 'bf16' or 'fp32'")
 
 
 def set_mlp_precision(precision):

@@ -8,6 +8,7 @@ from pn2_b200 import pointnet2_utils as pu
 from pn2_b200.models import PointNet2SemSeg
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+U.set_mlp_precision("bf16")
 torch.manual_seed(0)
 model = PointNet2SemSeg(21).eval().to(dev)
 pts = torch.from_numpy(scenes.scannet_batch(0, B, 8192)).to(dev)

@@ -24,6 +24,8 @@ pts = torch.from_numpy(scenes.scannet_batch(0, B, 8192)).to(dev)
 x6 = pts.permute(0, 2, 1).contiguous()
 lib = _lib.load()
 lib.pn2_debug_set_tc_timestamps.argtypes = [ctypes.c_void_p]
+if os.environ.get("TC_MAX_CTAS"):
+    lib.pn2_debug_set_tc_max_ctas(int(os.environ["TC_MAX_CTAS"]))
 TC = ("pn2_sa_mlp_max_bf16", "pn2_fp_mlp_bf16")
 NAMES = ["sa1", "sa2", "sa3", "sa4", "fp4", "fp3", "fp2", "fp1+head"]
 
