@@ -109,6 +109,13 @@ int pn2_lift_views(int b, int n, int v, int c, int h, int w, const float *points
                    float depth_min, float depth_max, float accuracy, int reduce, float *out, int32_t *pix,
                    int32_t *count, void *stream);
 
+/* The same operator taking the camera poses directly: c2w (B,V,4,4) camera-to-world and cam_corners (HOST pointer, 8x3
+ * floats, as for pn2_lift_setup) replace w2c / corner2 / corner4 / normals; the per-view parameters are derived inside the
+ * projection kernel with the arithmetic of pn2_lift_setup (bit-identical), saving a launch per call. */
+int pn2_lift_views_poses(int b, int n, int v, int c, int h, int w, const float *points, const float *feats, const float *depth,
+                         const float *c2w, const float *cam_corners, const float *intr, float depth_min, float depth_max,
+                         float accuracy, int reduce, float *out, int32_t *pix, int32_t *count, void *stream);
+
 /* Best-view selection of the ScanNet loader (data_utils/ScanNetDataLoader.py:87-105 -> utils/projection.py:132-164):
  * number of the n points inside the frustum of each of num_poses cameras, evaluated in fp64 as the reference does.
  * corner2/corner4 (P,3), normals (P,6,3) as for pn2_lift_views; counts (P) int32 must be pre-zeroed. */
@@ -266,6 +273,8 @@ void pn2_debug_set_fps_mode(int mode);
 void pn2_debug_set_tc_timestamps(long long *buf);
 /* Caps the resident CTAs per SM of the tensor-core MLP kernel (bench.py --tc-max-ctas; default 8 = no cap). */
 void pn2_debug_set_tc_max_ctas(int n);
+/* Lifting gather kernel: 0 automatic (pixel-major slab when n % 4 == 0), 1 = the channel-major slab kernel only. */
+void pn2_debug_set_lift_mode(int mode);
 /* Worker warps per 128-row tile of the tensor-core MLP kernel: 4 (up to 4 CTAs per SM), 8 (two warps per TMEM lane
  * quarter splitting the columns, up to 2 CTAs per SM) or 0 = chosen by launch size (default).  Results are identical. */
 void pn2_debug_set_tc_workers(int n);

@@ -56,6 +56,16 @@ def frustum_normals(corners):
                        dim=-2)
 
 
+def _camera_corners(intrinsic, depth_min, depth_max, image_dims):
+    """The eight camera-space frustum corners (24 Python floats), utils/projection.py:37-44."""
+    W, H = image_dims
+    cam = []
+    for d in (depth_min, depth_max):
+        for (u, v) in ((0, 0), (W - 1, 0), (W - 1, H - 1), (0, H - 1)):
+            cam += _skeleton(intrinsic, u, v, d)  # Python floats, rounded to fp32 by ctypes as torch.Tensor(...) does
+    return cam
+
+
 def view_params(camera_to_world, intrinsic, depth_min, depth_max, image_dims):
     """camera_to_world (..., 4, 4) cuda -> (w2c (..., 4, 4), corner2 (..., 3), corner4 (..., 3), normals (..., 6, 3)):
     everything the lifting / frustum tests need per view, in ONE launch (pn2_lift_setup) instead of the ~25 torch ops of
@@ -65,12 +75,7 @@ def view_params(camera_to_world, intrinsic, depth_min, depth_max, image_dims):
     c2w = camera_to_world.to(torch.float32).contiguous()
     lead = c2w.shape[:-2]
     nv = c2w.numel() // 16
-    W, H = image_dims
-    cam = []
-    for d in (depth_min, depth_max):
-        for (u, v) in ((0, 0), (W - 1, 0), (W - 1, H - 1), (0, H - 1)):
-            cam += _skeleton(intrinsic, u, v, d)  # Python floats, rounded to fp32 below as torch.Tensor(...) does
-    cam = (ctypes.c_float * 24)(*cam)
+    cam = (ctypes.c_float * 24)(*_camera_corners(intrinsic, depth_min, depth_max, image_dims))
     w2c_c = torch.empty((nv, 16), dtype=torch.float32, device=c2w.device)
     c2_c = torch.empty((nv, 3), dtype=torch.float32, device=c2w.device)
     c4_c = torch.empty((nv, 3), dtype=torch.float32, device=c2w.device)
@@ -97,22 +102,32 @@ def lift_views(points, feats, depth, camera_to_world, intrinsic, depth_min, dept
     if [W, H] != [int(image_dims[0]), int(image_dims[1])]:
         raise _lib.Pn2Error("image_dims [W, H] = %s does not match the feature maps (H=%d, W=%d)" % (list(image_dims), H, W))
     dev = points.device
-    if view_parameters is None:
-        w2c, corner2, corner4, normals = view_params(camera_to_world, intrinsic, depth_min, depth_max, image_dims)
-    else:
-        w2c, corner2, corner4, normals = [_lib.check_f32(t, "view_parameters") for t in view_parameters]
-        if w2c.numel() != B * V * 16 or corner2.numel() != B * V * 3 or corner4.numel() != B * V * 3 or normals.numel() != B * V * 18:
-            raise _lib.Pn2Error("view_parameters do not match (B, V) = (%d, %d)" % (B, V))
     intr = (ctypes.c_float * 4)(float(intrinsic[0][0]), float(intrinsic[1][1]), float(intrinsic[0][2]), float(intrinsic[1][2]))
     out = torch.empty((B, C, N), dtype=torch.float32, device=dev)
     pix = torch.empty((B, V, N), dtype=torch.int32, device=dev) if return_pixels else None
     count = torch.zeros((B, V), dtype=torch.int32, device=dev) if return_pixels else None
-    points, feats, depth = points.contiguous(), feats.contiguous(), depth.contiguous()
-    with torch.cuda.device(dev):
-        _lib.call("pn2_lift_views", B, N, V, C, H, W, ptr(points), ptr(feats), ptr(depth), ptr(w2c), ptr(corner2),
-                  ptr(corner4), ptr(normals), intr, float(depth_min), float(depth_max), float(accuracy),
-                  _lib.REDUCE_FIRST if reduce == "first" else _lib.REDUCE_MAX, ptr(out), ptr(pix), ptr(count),
-                  _lib.stream_ptr(dev))
+    points, feats, depth = _lib.check_f32(points, "points"), _lib.check_f32(feats, "feats"), _lib.check_f32(depth, "depth")
+    red = _lib.REDUCE_FIRST if reduce == "first" else _lib.REDUCE_MAX
+    if view_parameters is None and V * H * W * 16 <= 200 * 1024:
+        # the per-view parameters are derived inside the projection kernel (same arithmetic as view_params / pn2_lift_setup)
+        c2w = _lib.check_f32(camera_to_world, "camera_to_world")
+        if c2w.numel() != B * V * 16:
+            raise _lib.Pn2Error("camera_to_world must be (B, V, 4, 4) = (%d, %d, 4, 4)" % (B, V))
+        cam = (ctypes.c_float * 24)(*_camera_corners(intrinsic, depth_min, depth_max, image_dims))
+        with torch.cuda.device(dev):
+            _lib.call("pn2_lift_views_poses", B, N, V, C, H, W, ptr(points), ptr(feats), ptr(depth), ptr(c2w), cam, intr,
+                      float(depth_min), float(depth_max), float(accuracy), red, ptr(out), ptr(pix), ptr(count), _lib.stream_ptr(dev))
+    else:
+        if view_parameters is None:
+            w2c, corner2, corner4, normals = view_params(camera_to_world, intrinsic, depth_min, depth_max, image_dims)
+        else:
+            w2c, corner2, corner4, normals = [_lib.check_f32(t, "view_parameters") for t in view_parameters]
+            if w2c.numel() != B * V * 16 or corner2.numel() != B * V * 3 or corner4.numel() != B * V * 3 or normals.numel() != B * V * 18:
+                raise _lib.Pn2Error("view_parameters do not match (B, V) = (%d, %d)" % (B, V))
+        with torch.cuda.device(dev):
+            _lib.call("pn2_lift_views", B, N, V, C, H, W, ptr(points), ptr(feats), ptr(depth), ptr(w2c), ptr(corner2),
+                      ptr(corner4), ptr(normals), intr, float(depth_min), float(depth_max), float(accuracy), red, ptr(out), ptr(pix),
+                      ptr(count), _lib.stream_ptr(dev))
     if return_pixels:
         return out, pix, count
     return out
