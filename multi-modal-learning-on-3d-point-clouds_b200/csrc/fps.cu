@@ -55,6 +55,26 @@ __device__ __forceinline__ void update_min(const float (&x)[P], const float (&y)
     }
 }
 
+// The same update that also returns max_i tm[i] (values only): pairs of running minima go through FMNMX3.
+template <int P>
+__device__ __forceinline__ float update_min_max(const float (&x)[P], const float (&y)[P], const float (&z)[P], float (&tm)[P],
+                                                float cx, float cy, float cz) {
+    static_assert(P % 2 == 0, "pairs");
+    const float2 nx = make_float2(-cx, -cx), ny = make_float2(-cy, -cy), nz = make_float2(-cz, -cz);
+    float best = 0.f;  // running minima are >= 0
+#pragma unroll
+    for (int i = 0; i < P; i += 2) {
+        const float2 dx = __fadd2_rn(make_float2(x[i], x[i + 1]), nx);
+        const float2 dy = __fadd2_rn(make_float2(y[i], y[i + 1]), ny);
+        const float2 dz = __fadd2_rn(make_float2(z[i], z[i + 1]), nz);
+        const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+        tm[i] = fminf(d.x, tm[i]);
+        tm[i + 1] = fminf(d.y, tm[i + 1]);
+        best = fmaxf(fmaxf(best, tm[i]), tm[i + 1]);
+    }
+    return best;
+}
+
 template <int T>
 struct Log2 {
     static constexpr int value = 1 + Log2<T / 2>::value;
@@ -149,7 +169,17 @@ fps_reg_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__restr
 // bitrev10(t + T*s) = bitrev10(t) + bitrev_{log2 SUB}(s), so the in-thread tie order is "s in bit-reversed order, then
 // q ascending": the points are held in that order (slot j = bitrev(s)*Q + q) and the first strict maximum in ascending
 // j is the reference's winner.
-template <int T, int Q>
+//
+// kValueFirst (developer mode 6, NOT the default): the round reduces the VALUE of the maximum only (one FMNMX3 per pair of
+// points in the update, one CREDUX per warp, one shared-memory hop); which point holds it is worked out afterwards by the
+// few threads whose own maximum equals it -- first slot in tie order, then an atomic minimum of the tie keys in shared
+// memory -- instead of carrying (value, slot) pairs through a 31-step select tree in every thread.  Fewer instructions
+// for seven of the eight warps (the round issues 2.7 instructions per cycle and SM: 2256 warp instructions in 1038 cycles
+// at 32 points per thread), but one more block barrier in the serial tail of the round; measured (32 clouds, bit-identical
+// results): 0.571 vs 0.529 us per round at 8192 points, 0.414 vs 0.324 at 4096, 0.345 vs 0.240 at 2048, 0.321 vs 0.209 at
+// 1024 -- the dependent chain (tree, CREDUX pair, barrier, CREDUX pair, decode, coordinate fetch), not issue, is what a
+// round costs.
+template <int T, int Q, bool kValueFirst>
 __global__ void __launch_bounds__(T, 1)
 fps_few_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__restrict__ idx_all,
                float *__restrict__ new_xyz_all) {
@@ -157,6 +187,8 @@ fps_few_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__restr
     extern __shared__ float smem[];
     float *sx = smem, *sy = smem + 1024 * Q, *sz = smem + 2 * 1024 * Q;
     __shared__ unsigned long long slot[2][32];
+    __shared__ uint32_t slotv[2][32];
+    __shared__ uint32_t win[2];
 
     const float *xyz = xyz_all + (size_t)blockIdx.x * n * 3;
     int32_t *idx = idx_all + (size_t)blockIdx.x * m;
@@ -180,11 +212,47 @@ fps_few_kernel(int n, int m, const float *__restrict__ xyz_all, int32_t *__restr
     const uint32_t rank0 = __brev((uint32_t)t) >> 22;  // bitrev10(t); t < T so its low log2(SUB) bits are free
     const uint32_t inv_base = 0xFFFFFFFFu - (rank0 << QB);
     float *new_xyz = new_xyz_all ? new_xyz_all + (size_t)blockIdx.x * m * 3 : nullptr;
-    if (t == 0) idx[0] = 0;
+    if (t == 0) {
+        idx[0] = 0;
+        win[0] = win[1] = 0xFFFFFFFFu;
+    }
     __syncthreads();
     float x1 = sx[0], y1 = sy[0], z1 = sz[0];
     if (t == 0 && new_xyz) {
         new_xyz[0] = x1; new_xyz[1] = y1; new_xyz[2] = z1;
+    }
+
+    if constexpr (kValueFirst && P % 2 == 0) {
+        for (int r = 1; r < m; ++r) {
+            const float lm = update_min_max<P>(x, y, z, tm, x1, y1, z1);
+            const uint32_t hi = __float_as_uint(lm);  // non-negative floats order like their bit patterns
+            const uint32_t wh = __reduce_max_sync(0xffffffffu, hi);
+            if (lane == 0) slotv[r & 1][warp] = wh;
+            __syncthreads();
+            if (t == 0) win[(r + 1) & 1] = 0xFFFFFFFFu;  // next round's cell; its last readers are past this barrier
+            const uint32_t M = __reduce_max_sync(0xffffffffu, lane < NW ? slotv[r & 1][lane] : 0u);
+            if (hi == M) {
+                // this thread holds a point at the maximum: its first such slot in tie order, then the smallest tie key wins
+                int bj = P - 1;
+#pragma unroll
+                for (int j = P - 2; j >= 0; --j) bj = (__float_as_uint(tm[j]) == M) ? j : bj;
+                const uint32_t key = (rank0 << QB) + ((((uint32_t)bj / Q) << QB) | ((uint32_t)bj % Q));
+                atomicMin(&win[r & 1], key);
+            }
+            __syncthreads();
+            const uint32_t tie = win[r & 1];
+            const int k = (int)(tie & QMASK) * 1024 + (int)(__brev(tie >> QB) >> 22);
+            x1 = sx[k];
+            y1 = sy[k];
+            z1 = sz[k];
+            if (t == 0) {
+                idx[r] = k;
+                if (new_xyz) {
+                    new_xyz[3 * r] = x1; new_xyz[3 * r + 1] = y1; new_xyz[3 * r + 2] = z1;
+                }
+            }
+        }
+        return;
     }
 
     for (int r = 1; r < m; ++r) {
@@ -515,11 +583,18 @@ int launch_reg(int b, int n, int m, const float *xyz, int32_t *idx, float *new_x
     return PN2_OK;
 }
 
+int fps_force_mode();
+
 template <int T, int Q>
 int launch_few(int b, int n, int m, const float *xyz, int32_t *idx, float *new_xyz, cudaStream_t s) {
     const size_t smem = (size_t)3 * 1024 * Q * sizeof(float);
-    PN2_CUDA(cudaFuncSetAttribute(fps_few_kernel<T, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fps_few_kernel<T, Q><<<b, T, smem, s>>>(n, m, xyz, idx, new_xyz);
+    if (fps_force_mode() == 6) {  // developer mode 6: the value-first round (measured slower, see the kernel's comment)
+        PN2_CUDA(cudaFuncSetAttribute(fps_few_kernel<T, Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fps_few_kernel<T, Q, true><<<b, T, smem, s>>>(n, m, xyz, idx, new_xyz);
+    } else {
+        PN2_CUDA(cudaFuncSetAttribute(fps_few_kernel<T, Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fps_few_kernel<T, Q, false><<<b, T, smem, s>>>(n, m, xyz, idx, new_xyz);
+    }
     PN2_LAUNCH_OK("fps_few_kernel");
     return PN2_OK;
 }
