@@ -566,6 +566,15 @@ def run_ours(args):
             e2e_lab_ms = run_e2e(pipe_l, graphed_l, (B, NPOINTS), torch.uint8, model.predict, e2e_warm)
             clocks.end()
             del pipe_l, graphed_l
+        # (3) bf16 logits: the tensor-core head's outputs carry bf16-MMA precision; storing them as bf16 halves the read-back
+        e2e_bf16_ms = 0.0
+        if args.precision == "bf16" and model.can_fuse_labels() and not args.no_graph:
+            pipe_h = PipelinedForward(model, ex_xyz, ex_pts, depth, logits_dtype=torch.bfloat16) if depth > 1 else None
+            graphed_h = GraphedForward(model, ex_xyz, ex_pts, logits_dtype=torch.bfloat16) if depth <= 1 else None
+            clocks.begin()
+            e2e_bf16_ms = run_e2e(pipe_h, graphed_h, (B, NPOINTS, NUM_CLASSES), torch.bfloat16, None, e2e_warm)
+            clocks.end()
+            del pipe_h, graphed_h
         clocks.close()
 
         # ---- further legs of the same line (not the headline): fp32 MLP path, BASELINE config 1's batch of 2 ----------
@@ -622,12 +631,12 @@ def run_ours(args):
     if not args.no_extras:
         train_ms = time_train_step_msg(device, batch=4, steps=4, world=world, rank=rank)
 
-    t = torch.tensor([total_ms, e2e_ms, e2e_lab_ms, train_ms] + [legs.get("fp32", {}).get("ms_per_step", 0.0),
+    t = torch.tensor([total_ms, e2e_ms, e2e_lab_ms, train_ms, e2e_bf16_ms] + [legs.get("fp32", {}).get("ms_per_step", 0.0),
                                                                  legs.get("batch2", {}).get("ms_per_step", 0.0)],
                      dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, e2e_lab_ms, train_ms, ms32_max, msb2_max = t.tolist()
+    total_ms, e2e_ms, e2e_lab_ms, train_ms, e2e_bf16_ms, ms32_max, msb2_max = t.tolist()
     if rank == 0:
         value = world * B * args.steps / (total_ms / 1e3)
         e2e_value = world * B * args.steps / (e2e_ms / 1e3)
@@ -656,6 +665,19 @@ def run_ours(args):
                                   "ms_per_step": e2e_lab_ms / args.steps,
                                   "what": "same protocol through PointNet2SemSeg.predict(): per-point class predictions (uint8) "
                                           "read back instead of fp32 logits; the arg-max is fused into the head kernel"}
+        if e2e_bf16_ms > 0:
+            line["e2e_bf16_logits"] = {"value": world * B * args.steps / (e2e_bf16_ms / 1e3), "unit": "scenes/s",
+                                       "h2d_bytes_per_step": B * NPOINTS * 6 * 4, "d2h_bytes_per_step": B * NPOINTS * NUM_CLASSES * 2,
+                                       "ms_per_step": e2e_bf16_ms / args.steps,
+                                       "what": "same protocol with the (B, N, 21) logits stored and read back as bf16 (the tensor-core head "
+                                               "computes them with bf16 operands; forward_fused(logits_dtype=torch.bfloat16))"}
+        host_probe = os.path.join(ROOT, "profiles", "r2_host_link_probe.json")
+        if os.path.exists(host_probe):
+            line["e2e"]["host_link_ceiling"] = {"source": "profiles/r2_host_link_probe.json",
+                                                "note": "measured pinned D2H bandwidth of this pool's boxes with all ranks copying at once "
+                                                        "(GB/s aggregate): 56 / 75 / 80 / 109 at 1 / 2 / 4 / 8 GPUs, 76 with H2D running too; "
+                                                        "fp32 logits need 41 GB/s per GPU at the device rate, so beyond 2 GPUs this leg is "
+                                                        "bounded by the host links (8 GPUs: 126 k scenes/s = 87 GB/s D2H + 25 GB/s H2D)"}
         if "fp32" in legs:
             legs["fp32"]["ms_per_step"] = ms32_max
             legs["fp32"]["value"] = world * B / ms32_max * 1e3

@@ -80,9 +80,10 @@ class PointNet2SemSeg(nn.Module):
         relus = [True] * len(self.fp1.mlp_convs) + [True, False]
         return self._head_fold.get(self, convs, bns, relus)
 
-    def forward_fused(self, xyz, points, labels=False):
+    def forward_fused(self, xyz, points, labels=False, logits_dtype=torch.float32):
         """xyz (B, 3, N), points (B, D, N) -> (B, N, num_classes), contiguous; labels=True -> (B, N) uint8 class
-        predictions (arg-max fused into the head, see predict()).
+        predictions (arg-max fused into the head, see predict()); logits_dtype=torch.bfloat16 (tensor-core path only) stores
+        the logits as bf16 -- they carry bf16-MMA precision anyway -- which halves what an evaluation loop reads back.
 
         The geometry of every level depends on coordinates only, so it runs ahead of the feature path on two side
         streams: FPS chain + 3-NN on one, ball queries on another; the fused SA/FP kernels follow on the caller's
@@ -181,7 +182,7 @@ class PointNet2SemSeg(nn.Module):
         l1 = self.fp2.forward_cl(levels[1], levels[2], l1, l2, nn_weights=nnw[2], out_dtype=act)
         main.wait_event(nn_done[3])
         order0 = grids[0].order if 0 in grids else None
-        head_dtype = torch.uint8 if labels else torch.float32
+        head_dtype = torch.uint8 if labels else logits_dtype
         if self.timers is None:
             return self.fp1.forward_cl(xyz_cl, levels[1], feat_cl, l1, mlp=self._fp1_with_head(), nn_weights=nnw[3],
                                        row_order=order0, out_dtype=head_dtype)
@@ -449,11 +450,13 @@ class GraphedForward:
     one graph launch (no per-kernel Python / driver overhead).  `run(x)` copies x (device or pinned host, (B, C, N))
     into the static input and returns the static output tensor (valid until the next run)."""
 
-    def __init__(self, model, example_xyz, example_points, warmup=3, labels=False):
+    def __init__(self, model, example_xyz, example_points, warmup=3, labels=False, logits_dtype=None):
         self.model = model
         self.xyz = example_xyz.clone()
         self.points = example_points.clone()
         kw = {"labels": True} if labels else {}  # labels: (B, N) uint8 predictions instead of logits (PointNet2SemSeg.predict)
+        if logits_dtype is not None:
+            kw["logits_dtype"] = logits_dtype
         side = torch.cuda.Stream(example_xyz.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
@@ -480,7 +483,7 @@ class PipelinedForward:
     on SMs that the latency-bound sampling of a single batch leaves idle).  submit() returns the static output of the
     slot it used together with an event; the output stays valid until that slot is submitted again."""
 
-    def __init__(self, model, example_xyz, example_points, depth=2, labels=False):
+    def __init__(self, model, example_xyz, example_points, depth=2, labels=False, logits_dtype=None):
         self.depth = depth
         self.streams = [torch.cuda.Stream(example_xyz.device) for _ in range(depth)]
         self.slots = []
@@ -489,7 +492,7 @@ class PipelinedForward:
             for st in self.streams:
                 st.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(st):
-                    self.slots.append(GraphedForward(model, example_xyz, example_points, labels=labels))
+                    self.slots.append(GraphedForward(model, example_xyz, example_points, labels=labels, logits_dtype=logits_dtype))
                 torch.cuda.current_stream().wait_stream(st)
         self.kernels_per_replay = self.slots[0].kernels_per_replay
         self.i = 0

@@ -289,3 +289,22 @@ def test_backbone_nuscenes_raw_sweep_size_batch2(cuda, precision):
         got = copy.deepcopy(model).to(cuda)(xyz.to(cuda), feat.to(cuda))
     assert got.shape == (2, 128, n)
     assert_close(got, want, tol(precision, 2e-5))
+
+
+def test_bf16_logits_match_fp32_logits(cuda):
+    """forward_fused(logits_dtype=torch.bfloat16): the same logits rounded once to bf16 (odd 42-byte row pitch)."""
+    from pn2_b200 import pointnet_util
+    prev = pointnet_util.set_mlp_precision("bf16")
+    try:
+        torch.manual_seed(3)
+        model = PointNet2SemSeg(21).eval()
+        randomize_bn(model, 7)
+        model = model.to(cuda)
+        pts = torch.from_numpy(scenes.scannet_batch(5, 2, 4096)).permute(0, 2, 1).contiguous().to(cuda)
+        with torch.no_grad():
+            full = model.forward_fused(pts[:, :3], pts[:, 3:])
+            half = model.forward_fused(pts[:, :3], pts[:, 3:], logits_dtype=torch.bfloat16)
+        assert half.dtype == torch.bfloat16 and half.shape == full.shape
+        assert torch.equal(half, full.to(torch.bfloat16))
+    finally:
+        pointnet_util.set_mlp_precision(prev)
