@@ -159,6 +159,33 @@ int pn2_fp_mlp(int b, int n, int m, int d1, int d2, const float *feat1, const fl
  * (layer count, nsample a power of two <= 128, widths within shared memory); 0 otherwise.  No CUDA call. */
 int pn2_mlp_fp32_supported(const pn2_mlp *mlp, int c0, int nsample);
 
+/* ---- the shared-MLP layer in TRAINING mode (batch-statistics BatchNorm; model/pointnet_util.py:105-107,162-165,218-220
+ * under autograd), fp32, channel-last row matrices (rows x channels).  See csrc/train_mlp.cu for the algebra. ----
+ * forward: z (rows,cout) = act_in(x) W^T + bias, act_in(v) = relu(in_scale v + in_shift) per input channel (the previous
+ *   layer's BatchNorm + ReLU; NULL/NULL = identity), w (cout,cin); stats (2,cout) float64, PRE-ZEROED: += sum_r z, sum_r z^2. */
+int pn2_train_linear_fwd(long long rows, int cin, int cout, const float *x, const float *in_scale, const float *in_shift,
+                         const float *w, const float *bias, float *z, double *stats, void *stream);
+/* Per-channel BatchNorm quantities from the forward sums (one tiny launch): scale = gamma rstd, shift = beta - mean scale
+ * (fp32, the next layer's act_in), mean_rstd (2,c) float64 for the backward; running_mean / running_var (may both be NULL)
+ * are updated like torch.nn.BatchNorm in training mode (momentum, unbiased variance). */
+int pn2_train_bn_finalize(long long rows, int c, const double *stats, const float *gamma, const float *beta, double eps,
+                          double momentum, float *scale, float *shift, double *mean_rstd, float *running_mean,
+                          float *running_var, void *stream);
+/* Coefficients of dz = ca dy + cb + cc z from the backward sums: coef (3,c) = ca | cb | cc; dgamma (c), dbeta (c). */
+int pn2_train_bn_bwd_coeffs(long long rows, int c, const double *sums, const double *mean_rstd, const float *gamma, float *coef,
+                            float *dgamma, float *dbeta, void *stream);
+/* a (rows,c) = relu(scale z + shift): the materialised output of the last layer of a stack. */
+int pn2_train_bn_relu(long long rows, int c, const float *z, const float *scale, const float *shift, float *a, void *stream);
+/* BatchNorm backward reductions: dy = g [scale z + shift > 0]; sums (2,c) float64, PRE-ZEROED: += sum_r dy, sum_r dy z. */
+int pn2_train_bn_bwd_reduce(long long rows, int c, const float *g, const float *z, const float *scale, const float *shift,
+                            double *sums, void *stream);
+/* backward of one layer: dz = ca dy + cb + cc z (per output channel); g_in (rows,cin) = dz W (NULL = not needed; wt = W^T,
+ * (cin,cout) row-major); dw (cout,cin), PRE-ZEROED, += dz^T act_in(x) (fp32 atomics: accumulation order unspecified, as in
+ * the reference's backward kernels). */
+int pn2_train_linear_bwd(long long rows, int cin, int cout, const float *x, const float *in_scale, const float *in_shift,
+                         const float *wt, const float *g, const float *z, const float *scale, const float *shift,
+                         const float *ca, const float *cb, const float *cc, float *g_in, float *dw, void *stream);
+
 /* ---- the same two blocks on the tcgen05 tensor cores: bf16 operands, fp32 accumulation in TMEM ----
  * Outputs agree with the fp32 entry points within bf16 rounding (2e-2 relative).  Weights are packed once
  * (bf16, pre-swizzled UMMA tiles) with pn2_mlp_pack_bf16; biases are still read from `mlp`.

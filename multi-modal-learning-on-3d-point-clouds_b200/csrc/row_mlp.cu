@@ -19,13 +19,10 @@
 //
 // fp32 FFMA throughout (the 1e-5 parity path).  The bf16 tcgen05 variant lives in row_mlp_tc.cu.
 #include "common.cuh"
+#include "row_mlp_tile.cuh"
 
 namespace pn2 {
 namespace {
-
-constexpr int RM_THREADS = 256;
-constexpr int KC = 16;          // k-chunk of the staged weight tile
-constexpr int WSP = 128 + 4;    // row stride of the weight tile (floats)
 
 enum { MODE_SA = 0, MODE_FP = 1 };
 
@@ -48,113 +45,6 @@ struct RowMlpParams {
     int d1, d2, fp_m;
     const float *feat1, *feat2, *weight;
 };
-
-// n-tile width of a layer; the 16-row tile has 64 thread columns, so its tiles are at least 64 wide
-__host__ __device__ inline int pick_nt(int cout, int tr) { return cout <= 32 ? (tr == 16 ? 64 : 32) : (cout <= 64 ? 64 : 128); }
-__host__ __device__ inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
-
-// One n-tile of one layer: acc = X_in[.,rows] * W[n0 + cols, .]^T, then bias/ReLU and a k-major store.
-template <int TR, int NT>
-__device__ __forceinline__ void layer_tile(const float *__restrict__ xin, float *__restrict__ xout, int out_ch0,
-                                           const float *__restrict__ W, const float *__restrict__ bias, int cin,
-                                           int cout, int n0, int relu, float *ws) {
-    constexpr int TRP = TR + 4;
-    constexpr int TM = (TR == 128 && NT >= 64) ? 8 : 4;
-    constexpr int TY = TR / TM;
-    constexpr int TXN = RM_THREADS / TY;
-    constexpr int TN = NT / TXN;
-    constexpr int EPT = KC * NT / RM_THREADS;  // weight elements staged per thread per chunk
-    static_assert(TN >= 1 && EPT >= 1, "bad tile");
-    const int tid = threadIdx.x;
-    const int tx = tid % TXN, ty = tid / TXN;
-
-    // staging coordinates: smem position p <-> logical column (p / TN) + TXN * (p % TN)
-    const int sp = tid % NT, sg = tid / NT;
-    const int scol = n0 + (sp / TN) + TXN * (sp % TN);
-    const float *wrow = W + (size_t)scol * cin;
-    const bool col_ok = scol < cout;
-
-    float acc[TM][TN];
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-
-    float wreg[EPT];
-    const int nchunks = (cin + KC - 1) / KC;
-    // prologue: stage chunk 0
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        const int k = sg * EPT + e;
-        wreg[e] = (col_ok && k < cin) ? __ldg(wrow + k) : 0.f;
-    }
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) ws[(sg * EPT + e) * WSP + sp] = wreg[e];
-    __syncthreads();
-
-    for (int c = 0; c < nchunks; ++c) {
-        float *wcur = ws + (c & 1) * (KC * WSP);
-        float *wnxt = ws + ((c + 1) & 1) * (KC * WSP);
-        const bool more = (c + 1) < nchunks;
-        if (more) {
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) {
-                const int k = (c + 1) * KC + sg * EPT + e;
-                wreg[e] = (col_ok && k < cin) ? __ldg(wrow + k) : 0.f;
-            }
-        }
-        const float *xa = xin + (size_t)(c * KC) * TRP + ty * TM;
-        const int kk_end = min(KC, cin - c * KC);
-#pragma unroll 4
-        for (int kk = 0; kk < kk_end; ++kk) {
-            float a[TM], b[TN];
-#pragma unroll
-            for (int i = 0; i < TM; i += 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(xa + kk * TRP + i);
-                a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
-            }
-            const float *wb = wcur + kk * WSP + tx * TN;
-            if constexpr (TN >= 4) {
-#pragma unroll
-                for (int j = 0; j < TN; j += 4) {
-                    const float4 v = *reinterpret_cast<const float4 *>(wb + j);
-                    b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
-                }
-            } else if constexpr (TN == 2) {
-                const float2 v = *reinterpret_cast<const float2 *>(wb);
-                b[0] = v.x; b[1] = v.y;
-            } else {
-                b[0] = wb[0];
-            }
-#pragma unroll
-            for (int i = 0; i < TM; ++i)
-#pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-        }
-        if (more) {
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) wnxt[(sg * EPT + e) * WSP + sp] = wreg[e];
-        }
-        __syncthreads();
-    }
-
-    // epilogue: bias + activation, k-major store (channel = out_ch0 + logical column offset)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-        const int col = n0 + tx + TXN * j;
-        const float bv = col < cout ? __ldg(bias + col) : 0.f;
-        float *dst = xout + (size_t)(out_ch0 + tx + TXN * j) * TRP + ty * TM;
-#pragma unroll
-        for (int i = 0; i < TM; i += 4) {
-            float4 v;
-            v.x = acc[i][j] + bv; v.y = acc[i + 1][j] + bv; v.z = acc[i + 2][j] + bv; v.w = acc[i + 3][j] + bv;
-            if (relu) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-            }
-            *reinterpret_cast<float4 *>(dst + i) = v;
-        }
-    }
-}
 
 template <int TR>
 __device__ __forceinline__ void gather_sa(const RowMlpParams &p, float *x0, long long tile) {

@@ -62,6 +62,12 @@ _SIGNATURES = {
     "pn2_three_nn_grid": [_c_int, _c_int, _c_int] + [_vp] * 10,
     "pn2_three_nn_weights": [_c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "pn2_transpose": [_c_int, _c_int, _c_int, _vp, _vp, _vp],
+    "pn2_train_linear_fwd": [ctypes.c_longlong, _c_int, _c_int] + [_vp] * 8,
+    "pn2_train_bn_finalize": [ctypes.c_longlong, _c_int, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double] + [_vp] * 6,
+    "pn2_train_bn_bwd_coeffs": [ctypes.c_longlong, _c_int] + [_vp] * 7,
+    "pn2_train_bn_relu": [ctypes.c_longlong, _c_int] + [_vp] * 5,
+    "pn2_train_bn_bwd_reduce": [ctypes.c_longlong, _c_int] + [_vp] * 6,
+    "pn2_train_linear_bwd": [ctypes.c_longlong, _c_int, _c_int] + [_vp] * 14,
 }
 _OTHER = {
     "pn2_last_error": ([], ctypes.c_char_p),

@@ -22,6 +22,22 @@ from .pointnet_util import (PointNetFeaturePropagation, PointNetSetAbstraction, 
                             to_channel_last)
 
 
+def _semseg_head(model, l0_points):
+    """conv1 -> bn1 -> ReLU -> dropout -> conv2 -> (B, N, classes) (model/pointnet2.py:158-161).  In training mode on the
+    fused training kernels: conv1 + BatchNorm + ReLU as one row chain, conv2 as a row GEMM (no 1x1 cuDNN convolutions)."""
+    from . import pointnet_util, train_mlp
+    if pointnet_util._train_fused(model, l0_points, [model.conv1], [model.bn1]):
+        B, C, N = l0_points.shape
+        rows = l0_points.permute(0, 2, 1).reshape(B * N, C)
+        x = train_mlp.fused_mlp_train(rows, [model.conv1], [model.bn1])
+        x = model.drop1(x)
+        x = F.linear(x, model.conv2.weight.reshape(model.conv2.out_channels, -1), model.conv2.bias)
+        return x.view(B, N, -1)
+    x = model.drop1(F.relu(model.bn1(model.conv1(l0_points))))
+    x = model.conv2(x)
+    return x.permute(0, 2, 1)
+
+
 class PointNet2SemSeg(nn.Module):
     def __init__(self, num_classes):
         super().__init__()
@@ -221,9 +237,7 @@ class PointNet2SemSeg(nn.Module):
         l2_points = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points)
         l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
         l0_points = self.fp1(xyz, l1_xyz, points, l1_points)
-        x = self.drop1(F.relu(self.bn1(self.conv1(l0_points))))
-        x = self.conv2(x)
-        return x.permute(0, 2, 1)
+        return _semseg_head(self, l0_points)
 
 
 class PointNet2Backbone(nn.Module):
@@ -300,8 +314,7 @@ class _MultiviewStackBase(nn.Module):
         return super().train(mode)
 
     def _head(self, l0_points):
-        x = self.drop1(F.relu(self.bn1(self.conv1(l0_points))))
-        return self.conv2(x).permute(0, 2, 1)
+        return _semseg_head(self, l0_points)
 
     def _fp1_with_head(self):
         convs = list(self.fp1.mlp_convs) + [self.conv1, self.conv2]

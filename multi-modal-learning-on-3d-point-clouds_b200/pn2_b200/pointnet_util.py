@@ -26,8 +26,22 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib, pointnet2_utils
+from . import _lib, pointnet2_utils, train_mlp
 from ._lib import Pn2Mlp, ptr
+
+_FUSED_TRAINING = True
+
+
+def set_fused_training(enabled):
+    """Training-mode shared MLPs on the kernels of csrc/train_mlp.cu (default) or as torch.nn conv / BatchNorm / ReLU
+    modules under autograd (the reference's composition).  Returns the previous setting."""
+    global _FUSED_TRAINING
+    prev, _FUSED_TRAINING = _FUSED_TRAINING, bool(enabled)
+    return prev
+
+
+def _train_fused(module, x0, convs, bns):
+    return _FUSED_TRAINING and module.training and train_mlp.fusable_training(x0, convs, bns)
 
 
 def timeit(tag, t):
@@ -480,6 +494,12 @@ class PointNetSetAbstraction(nn.Module):
             new_xyz, new_points = sample_and_group_all(xyz_t, pts_t)
         else:
             new_xyz, new_points = sample_and_group(self.npoint, self.radius, self.nsample, xyz_t, pts_t)
+        if _train_fused(self, new_points, self.mlp_convs, self.mlp_bns):
+            # (B, S, K, C) rows through the fused training chain, then the max over nsample (:109)
+            Bq, S, K, C0 = new_points.shape
+            a = train_mlp.fused_mlp_train(new_points.reshape(Bq * S * K, C0), self.mlp_convs, self.mlp_bns)
+            new_points = a.view(Bq, S, K, -1).max(dim=2)[0].permute(0, 2, 1)
+            return new_xyz.permute(0, 2, 1), new_points
         new_points = new_points.permute(0, 3, 2, 1)  # (B, C+D, nsample, npoint)
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
             new_points = F.relu(bn(conv(new_points)))
@@ -557,6 +577,10 @@ class PointNetSetAbstractionMsg(nn.Module):
                 grouped = torch.cat([gp, grouped_xyz], dim=-1)
             else:
                 grouped = grouped_xyz
+            if _train_fused(self, grouped, self.conv_blocks[i], self.bn_blocks[i]):
+                a = train_mlp.fused_mlp_train(grouped.reshape(B * S * K, grouped.shape[-1]), self.conv_blocks[i], self.bn_blocks[i])
+                outs.append(a.view(B, S, K, -1).max(dim=2)[0].permute(0, 2, 1))
+                continue
             grouped = grouped.permute(0, 3, 2, 1)  # (B, D, K, S)
             for conv, bn in zip(self.conv_blocks[i], self.bn_blocks[i]):
                 grouped = F.relu(bn(conv(grouped)))
@@ -626,6 +650,9 @@ class PointNetFeaturePropagation(nn.Module):
             new_points = torch.cat([points1.permute(0, 2, 1), interpolated], dim=-1)  # skip features FIRST (:213)
         else:
             new_points = interpolated
+        if _train_fused(self, new_points, self.mlp_convs, self.mlp_bns):
+            a = train_mlp.fused_mlp_train(new_points.reshape(B * N, new_points.shape[-1]), self.mlp_convs, self.mlp_bns)
+            return a.view(B, N, -1).permute(0, 2, 1)
         new_points = new_points.permute(0, 2, 1)
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
             new_points = F.relu(bn(conv(new_points)))
