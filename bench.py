@@ -693,7 +693,8 @@ def run_ours(args):
                 "value": world * 4 / train_ms * 1e3, "unit": "scenes/s", "ms_per_step": train_ms, "batch_per_gpu": 4, "n_gpus": world,
                 "what": "BASELINE configs[1]: PointNet2Multiview2Msg point branch (model/pointnet2multiview.py:179-233), forward + "
                         "backward + Adam, 4 scenes per GPU, scene-sharded" + (", DDP gradient all-reduce over NCCL" if world > 1 else "")
-                        + "; geometry and its backwards on our kernels, conv / BatchNorm(train) / autograd torch"}
+                        + "; geometry and its backwards AND the shared MLPs (conv + batch-statistics BatchNorm + ReLU, forward and "
+                          "backward: csrc/train_mlp.cu) on our kernels"}
         if dom_ms:
             ms = float(np.mean(dom_ms))
             achieved = B * FP1_HEAD_FLOPS_PER_SCENE / (ms / 1e3) / 1e12

@@ -29,27 +29,33 @@ constexpr int TG_THREADS = 256;
 constexpr int TG_KC = 16;
 constexpr int TG_M = 128;
 
-template <int NT>
+template <int NT, int MT = TG_M>
 struct TileShape {
     static constexpr int TX = NT / 4;             // threads along n (4 columns each)
     static constexpr int TY = TG_THREADS / TX;    // threads along m
-    static constexpr int TM = TG_M / TY;          // rows per thread
-    static constexpr int AS = TG_M + 4, BS = NT + 4;
+    static constexpr int TM = MT / TY;            // rows per thread (1, 2 or a multiple of 4)
+    static constexpr int AS = MT + 4, BS = NT + 4;
     static constexpr size_t smem_floats = 2 * TG_KC * (AS + BS);
+    static_assert(TM >= 1 && (TM < 4 || TM % 4 == 0), "tile shape");
 };
 
 // acc[TM][4] += As[k][ty*TM .. ] * Bs[k][tx*4 ..] over one staged k-chunk
-template <int NT>
-__device__ __forceinline__ void mma_chunk(const float *__restrict__ As, const float *__restrict__ Bs, float (&acc)[TileShape<NT>::TM][4],
+template <int NT, int MT = TG_M>
+__device__ __forceinline__ void mma_chunk(const float *__restrict__ As, const float *__restrict__ Bs, float (&acc)[TileShape<NT, MT>::TM][4],
                                           int ty, int tx) {
-    using S = TileShape<NT>;
+    using S = TileShape<NT, MT>;
 #pragma unroll
     for (int kk = 0; kk < TG_KC; ++kk) {
         float a[S::TM], b[4];
+        if constexpr (S::TM >= 4) {
 #pragma unroll
-        for (int i = 0; i < S::TM; i += 4) {
-            const float4 v = *reinterpret_cast<const float4 *>(As + kk * S::AS + ty * S::TM + i);
-            a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+            for (int i = 0; i < S::TM; i += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(As + kk * S::AS + ty * S::TM + i);
+                a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < S::TM; ++i) a[i] = As[kk * S::AS + ty * S::TM + i];
         }
         const float4 w = *reinterpret_cast<const float4 *>(Bs + kk * S::BS + tx * 4);
         b[0] = w.x; b[1] = w.y; b[2] = w.z; b[3] = w.w;
@@ -303,10 +309,10 @@ train_linear_bwd_input_kernel(DzIn dz, WeightIn wt, float *__restrict__ g_in, lo
 // ---- backward, weight gradient: dW[co][ci] += sum_r dz[r][co] act_in(x)[r][ci] over a row range per CTA -----------------------
 // Both operands are contiguous along their channel (row-major activations), so the k-chunk (16 rows) is staged as it lies:
 // As[k][co], Bs[k][ci].  Output tile 128 (co) x NT (ci); the CTA walks its rows once per output tile.
-template <int NT>
+template <int NT, int MT>
 __global__ void __launch_bounds__(TG_THREADS, 2)
 train_linear_bwd_weight_kernel(DzIn dz, ActIn xin, float *__restrict__ dw, long long rows_per_cta) {
-    using S = TileShape<NT>;
+    using S = TileShape<NT, MT>;
     extern __shared__ __align__(16) float smem[];
     float *As = smem, *Bs = smem + 2 * TG_KC * S::AS;
     const int cout = dz.c, cin = xin.c;
@@ -319,20 +325,21 @@ train_linear_bwd_weight_kernel(DzIn dz, ActIn xin, float *__restrict__ dw, long 
     // blockIdx.y = output tile (m0, n0): deep layers have few rows but many tiles, shallow ones the opposite
     const int ntn = (cin + NT - 1) / NT;
         {
-            const int m0 = (int)(blockIdx.y / ntn) * TG_M, n0 = (int)(blockIdx.y % ntn) * NT;
+            const int m0 = (int)(blockIdx.y / ntn) * MT, n0 = (int)(blockIdx.y % ntn) * NT;
             float acc[S::TM][4];
 #pragma unroll
             for (int i = 0; i < S::TM; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-            float4 ra[2], rb[BQ];
-            // A chunk: 16 rows x 128 co = 512 float4: q -> (k = q / 32, co4 = q % 32);  B chunk: 16 rows x NT ci
+            constexpr int AQ = (MT * 4 + TG_THREADS - 1) / TG_THREADS;
+            float4 ra[AQ], rb[BQ];
+            // A chunk: 16 rows x MT co = MT * 4 float4: q -> (k = q / (MT / 4), co4 = q % (MT / 4));  B chunk: 16 rows x NT ci
             auto load = [&](long long r0) {
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < AQ; ++u) {
                     const int q = tid + u * TG_THREADS;
-                    const long long r = r0 + (q >> 5);
-                    ra[u] = r < r_end ? dz.four(r, m0 + 4 * (q & 31)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const long long r = r0 + q / (MT / 4);
+                    ra[u] = (q < MT * 4 && r < r_end) ? dz.four(r, m0 + 4 * (q % (MT / 4))) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int u = 0; u < BQ; ++u) {
@@ -344,9 +351,9 @@ train_linear_bwd_weight_kernel(DzIn dz, ActIn xin, float *__restrict__ dw, long 
             auto store = [&](int buf) {
                 float *a = As + buf * TG_KC * S::AS, *b = Bs + buf * TG_KC * S::BS;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < AQ; ++u) {
                     const int q = tid + u * TG_THREADS;
-                    *reinterpret_cast<float4 *>(a + (q >> 5) * S::AS + 4 * (q & 31)) = ra[u];
+                    if (q < MT * 4) *reinterpret_cast<float4 *>(a + (q / (MT / 4)) * S::AS + 4 * (q % (MT / 4))) = ra[u];
                 }
 #pragma unroll
                 for (int u = 0; u < BQ; ++u) {
@@ -360,7 +367,7 @@ train_linear_bwd_weight_kernel(DzIn dz, ActIn xin, float *__restrict__ dw, long 
             __syncthreads();
             for (int c = 0; c < nchunks; ++c) {
                 if (c + 1 < nchunks) load(r_begin + (long long)(c + 1) * TG_KC);
-                mma_chunk<NT>(As + (c & 1) * TG_KC * S::AS, Bs + (c & 1) * TG_KC * S::BS, acc, ty, tx);
+                mma_chunk<NT, MT>(As + (c & 1) * TG_KC * S::AS, Bs + (c & 1) * TG_KC * S::BS, acc, ty, tx);
                 if (c + 1 < nchunks) store((c + 1) & 1);
                 __syncthreads();
             }
@@ -516,8 +523,8 @@ extern "C" int pn2_train_linear_bwd(long long rows, int cin, int cout, const flo
     {
         // grid = (row ranges, output tiles): about four CTAs per SM in total, at least 128 rows per range (the partial sums
         // go to dW with atomics)
-        const int nt = pick_nt(cin);
-        const long long out_tiles = (long long)((cout + TG_M - 1) / TG_M) * ((cin + nt - 1) / nt);
+        const int nt = pick_nt(cin), mt = pick_nt(cout);  // output tile (cout x cin) = mt x nt: no padded FMAs for narrow layers
+        const long long out_tiles = (long long)((cout + mt - 1) / mt) * ((cin + nt - 1) / nt);
         PN2_REQUIRE(out_tiles <= 65535, "train_linear_bwd: too many output tiles");
         long long ranges = (4ll * sm_count() + out_tiles - 1) / out_tiles;
         long long per = (rows + ranges - 1) / ranges;
@@ -525,9 +532,15 @@ extern "C" int pn2_train_linear_bwd(long long rows, int cin, int cout, const flo
         per = (per + TG_KC - 1) / TG_KC * TG_KC;
         ranges = (rows + per - 1) / per;
         const dim3 grid((unsigned)ranges, (unsigned)out_tiles);
-        if (nt == 32) train_linear_bwd_weight_kernel<32><<<grid, TG_THREADS, tile_smem<32>(), s>>>(dz, a, dw, per);
-        else if (nt == 64) train_linear_bwd_weight_kernel<64><<<grid, TG_THREADS, tile_smem<64>(), s>>>(dz, a, dw, per);
-        else train_linear_bwd_weight_kernel<128><<<grid, TG_THREADS, tile_smem<128>(), s>>>(dz, a, dw, per);
+#define PN2_WG(NTV, MTV) train_linear_bwd_weight_kernel<NTV, MTV><<<grid, TG_THREADS, TileShape<NTV, MTV>::smem_floats * sizeof(float), s>>>(dz, a, dw, per)
+        if (mt == 32) {
+            if (nt == 32) PN2_WG(32, 32); else if (nt == 64) PN2_WG(64, 32); else PN2_WG(128, 32);
+        } else if (mt == 64) {
+            if (nt == 32) PN2_WG(32, 64); else if (nt == 64) PN2_WG(64, 64); else PN2_WG(128, 64);
+        } else {
+            if (nt == 32) PN2_WG(32, 128); else if (nt == 64) PN2_WG(64, 128); else PN2_WG(128, 128);
+        }
+#undef PN2_WG
         PN2_LAUNCH_OK("train_linear_bwd_weight_kernel");
     }
     return PN2_OK;

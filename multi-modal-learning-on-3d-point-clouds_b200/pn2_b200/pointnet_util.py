@@ -41,7 +41,11 @@ def set_fused_training(enabled):
 
 
 def _train_fused(module, x0, convs, bns):
-    return _FUSED_TRAINING and module.training and train_mlp.fusable_training(x0, convs, bns)
+    # the weight gradients are accumulated with fp32 atomics (order unspecified, like the reference's backward kernels):
+    # bit-reproducible training (pointnet2_utils.set_deterministic / torch.use_deterministic_algorithms) keeps torch's modules
+    if not (_FUSED_TRAINING and module.training) or pointnet2_utils._deterministic():
+        return False
+    return train_mlp.fusable_training(x0, convs, bns)
 
 
 def timeit(tag, t):
