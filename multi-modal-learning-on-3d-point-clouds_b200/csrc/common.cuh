@@ -14,6 +14,19 @@ int sm_count();
 // Stream-ordered scratch (cudaMallocAsync).  The first call on a device raises the pool's release threshold so that the
 // memory stays in the pool between calls instead of going back to the driver at every synchronisation.
 cudaError_t scratch_alloc(void **ptr, size_t bytes, cudaStream_t stream);
+// Owner of one stream-ordered scratch block: the block goes back to the pool (cudaFreeAsync on the same stream) on EVERY
+// way out of the entry point, error returns included.
+struct Scratch {
+    void *ptr = nullptr;
+    cudaStream_t stream;
+    explicit Scratch(cudaStream_t s) : stream(s) {}
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+    ~Scratch() {
+        if (ptr) cudaFreeAsync(ptr, stream);
+    }
+    cudaError_t alloc(size_t bytes) { return scratch_alloc(&ptr, bytes, stream); }
+};
 
 #define PN2_REQUIRE(cond, ...)                                             \
     do {                                                                   \

@@ -493,8 +493,9 @@ extern "C" int pn2_grid_build(int b, int n, const float *xyz, float cell, float 
         PN2_REQUIRE(b <= 65535, "grid_build: b exceeds the grid limit");
         cudaStream_t s = (cudaStream_t)stream;
         const size_t bytes = (size_t)b * (GRID_MAX_CELLS + 1) * sizeof(int32_t);
-        int32_t *cursor = nullptr;
-        PN2_CUDA(scratch_alloc((void **)&cursor, bytes, s));
+        Scratch cursor_mem(s);  // released on every return below
+        PN2_CUDA(cursor_mem.alloc(bytes));
+        int32_t *cursor = (int32_t *)cursor_mem.ptr;
         PN2_CUDA(cudaMemsetAsync(cursor, 0, bytes, s));
         GridMeta *gm = reinterpret_cast<GridMeta *>(meta);
         grid_meta_kernel<<<b, 1024, 0, s>>>(n, cell, xyz, gm);
@@ -506,7 +507,6 @@ extern "C" int pn2_grid_build(int b, int n, const float *xyz, float cell, float 
         PN2_LAUNCH_OK("grid_scan_kernel");
         grid_scatter_kernel<<<pts, 256, 0, s>>>(n, xyz, gm, cursor, reinterpret_cast<float4 *>(sorted), order);
         PN2_LAUNCH_OK("grid_scatter_kernel");
-        PN2_CUDA(cudaFreeAsync(cursor, s));
         return PN2_OK;
     }
     int np2 = 1;

@@ -646,8 +646,9 @@ static int lift_views_impl(int b, int n, int v, int c, int h, int w, const float
         const size_t pix16_bytes = pm_ok ? ((size_t)b * v * n * sizeof(int16_t) + 255) / 256 * 256 : 0;
         const size_t sel_bytes = first ? ((size_t)b * n + 255) / 256 * 256 : 0;
         const size_t nz_bytes = first ? ((size_t)b * v * hw + 255) / 256 * 256 : 0;
-        unsigned char *scratch = nullptr;
-        PN2_CUDA(scratch_alloc((void **)&scratch, pix_bytes + pix16_bytes + sel_bytes + nz_bytes + 256, s));
+        Scratch scratch_mem(s);  // released on every return below
+        PN2_CUDA(scratch_mem.alloc(pix_bytes + pix16_bytes + sel_bytes + nz_bytes + 256));
+        unsigned char *scratch = (unsigned char *)scratch_mem.ptr;
         unsigned char *cur = scratch;
         int32_t *pixbuf = pix;
         if (need32) {
@@ -673,7 +674,6 @@ static int lift_views_impl(int b, int n, int v, int c, int h, int w, const float
         else if (chunk == 4) st = launch_lift_gather<4>(b, n, v, c, hw, feats, pixbuf, sel, out, s);
         else if (chunk == 2) st = launch_lift_gather<2>(b, n, v, c, hw, feats, pixbuf, sel, out, s);
         else if (chunk == 1) st = launch_lift_gather<1>(b, n, v, c, hw, feats, pixbuf, sel, out, s);
-        PN2_CUDA(cudaFreeAsync(scratch, s));
         return st;
     }
     // feature maps too large for a shared-memory slab: one kernel, per-element gathers

@@ -96,8 +96,9 @@ extern "C" int pn2_inverse_index(int b, int n, long long j, const int32_t *idx, 
     PN2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int32_t *)nullptr,
                                              (int32_t *)nullptr, (int)total, 0, end_bit, s));
     const size_t key_bytes = ((size_t)total * sizeof(uint32_t) + 255) / 256 * 256;
-    unsigned char *scratch = nullptr;  // [keys in | keys out | positions in | cub temp]
-    PN2_CUDA(scratch_alloc((void **)&scratch, 3 * key_bytes + tmp_bytes, s));
+    Scratch scratch_mem(s);  // [keys in | keys out | positions in | cub temp], released on every return below
+    PN2_CUDA(scratch_mem.alloc(3 * key_bytes + tmp_bytes));
+    unsigned char *scratch = (unsigned char *)scratch_mem.ptr;
     uint32_t *keys_in = (uint32_t *)scratch, *keys_out = (uint32_t *)(scratch + key_bytes);
     int32_t *pos_in = (int32_t *)(scratch + 2 * key_bytes);
     const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
@@ -107,7 +108,6 @@ extern "C" int pn2_inverse_index(int b, int n, long long j, const int32_t *idx, 
     PN2_CUDA(cub::DeviceRadixSort::SortPairs(scratch + 3 * key_bytes, tmp_bytes, keys_in, keys_out, pos_in, pos, (int)total, 0, end_bit, s));
     seg_start_kernel<<<blocks, 256, 0, s>>>(total, nkeys, keys_out, seg_start);
     PN2_LAUNCH_OK("seg_start_kernel");
-    PN2_CUDA(cudaFreeAsync(scratch, s));
     return PN2_OK;
 }
 

@@ -183,8 +183,9 @@ extern "C" int pn2_voxel_first_index(int b, int n, const float *xyz, const unsig
     PN2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                              (const int32_t *)nullptr, (int32_t *)nullptr, (int)total, 0, end_bit, s));
     const size_t kb = ((size_t)total * 8 + 255) / 256 * 256, vb = ((size_t)total * 4 + 255) / 256 * 256;
-    unsigned char *scratch = nullptr;  // [keys in | keys out | vals in | vals out | cub temp]
-    PN2_CUDA(scratch_alloc((void **)&scratch, 2 * kb + 2 * vb + tmp_bytes, s));
+    Scratch scratch_mem(s);  // [keys in | keys out | vals in | vals out | cub temp], released on every return below
+    PN2_CUDA(scratch_mem.alloc(2 * kb + 2 * vb + tmp_bytes));
+    unsigned char *scratch = (unsigned char *)scratch_mem.ptr;
     unsigned long long *k_in = (unsigned long long *)scratch, *k_out = (unsigned long long *)(scratch + kb);
     int32_t *v_in = (int32_t *)(scratch + 2 * kb), *v_out = (int32_t *)(scratch + 2 * kb + vb);
     voxel_keys_kernel<<<b, VX_THREADS, 0, s>>>(n, xyz, mask, res, k_in, v_in, nvox);
@@ -193,6 +194,5 @@ extern "C" int pn2_voxel_first_index(int b, int n, const float *xyz, const unsig
     PN2_CUDA(cub::DeviceRadixSort::SortPairs(scratch + 2 * kb + 2 * vb, tmp_bytes, k_in, k_out, v_in, v_out, (int)total, 0, end_bit, s));
     voxel_heads_kernel<<<b, VX_THREADS, 0, s>>>(n, k_out, v_out, uvidx, first, count);
     PN2_LAUNCH_OK("voxel_heads_kernel");
-    PN2_CUDA(cudaFreeAsync(scratch, s));
     return PN2_OK;
 }
