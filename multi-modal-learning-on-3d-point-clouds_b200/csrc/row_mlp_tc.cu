@@ -38,6 +38,12 @@ constexpr int TC_ROWS = 128;
 constexpr int KBLK = 64;                       // bf16 elements per 128-byte swizzle row
 constexpr int A_BLOCK_BYTES = TC_ROWS * 128;   // one k-block of A: 128 rows x 128 B
 constexpr int MAX_STAGES = 4;
+#ifndef PN2_FP_GATHER_U
+#define PN2_FP_GATHER_U 2
+#endif
+// FP gather: 16-byte items per lane and batch (x3 neighbour rows in flight).  Measured, fp1+head: 2 -> 107 us, 4 -> 117 us
+// (the 96-register budget of 3 CTAs x 6 warps spills inside the loop); weights shuffled before the loads: 125 us.
+constexpr int FP_GATHER_U = PN2_FP_GATHER_U;
 
 enum { MODE_SA = 0, MODE_FP = 1 };
 
@@ -79,6 +85,9 @@ struct TcParams {
     int kchunk;        // k-blocks of the first layer's operand produced per pass (see gather_chunk_tc)
     int pool_t;        // SA: the last layer is computed TRANSPOSED (channels on TMEM lanes, samples on columns; see kernel)
     int thin;          // the first layer's last k-block holds only 16 columns and lives in its own 4 KB region (see Plan)
+    int pool_dup;      // SA, transposed last layer of <= 64 channels: its weight block is loaded 128 / npad times into the
+                       // 128-row M operand, so every TMEM lane quarter holds real channels and each worker warp pools
+                       // 128 / pool_dup of the tile's samples (otherwise only npad / 32 of the four warps would work)
     long long *dbg;    // optional phase timestamps of CTA 0 / warp 0 (developer profiling; NULL in production)
 };
 
@@ -198,6 +207,32 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi, int relu) {
     return d;
 }
 
+// One 32-column chunk of a hidden layer's epilogue for one row: acc + bias -> (ReLU) -> bf16, written as four 16-byte
+// slots of the next layer's swizzled operand (dst0 = row base + k-block, x0 = swizzle term of the chunk's first slot).
+__device__ __forceinline__ void lds128(uint32_t addr, float4 &v) {
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <bool kRelu>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], uint32_t bsrc, uint32_t dst0, uint32_t x0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 b0, b1;
+        lds128(bsrc + 32u * q, b0);
+        lds128(bsrc + 32u * q + 16u, b1);
+        const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 0]), __uint_as_float(acc[8 * q + 1])), make_float2(b0.x, b0.y));
+        const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 2]), __uint_as_float(acc[8 * q + 3])), make_float2(b0.z, b0.w));
+        const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 4]), __uint_as_float(acc[8 * q + 5])), make_float2(b1.x, b1.y));
+        const float2 s3 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 6]), __uint_as_float(acc[8 * q + 7])), make_float2(b1.z, b1.w));
+        uint4 pk;
+        pk.x = cvt_bf16x2(s0.x, s0.y, kRelu); pk.y = cvt_bf16x2(s1.x, s1.y, kRelu);
+        pk.z = cvt_bf16x2(s2.x, s2.y, kRelu); pk.w = cvt_bf16x2(s3.x, s3.y, kRelu);
+        sts128(dst0 + (x0 ^ (uint32_t)(q << 4)), pk);
+    }
+}
+
 // byte offset of the 16-byte chunk holding elements [8*c8, 8*c8+8) of row r in a [rows x K] operand
 __device__ __forceinline__ uint32_t swz_chunk(int r, int c8, int rows) {
     const int kb = c8 >> 3, c = c8 & 7;
@@ -258,10 +293,11 @@ struct RowPre {
     long long row;      // FP: destination row (after the optional permutation)
 };
 
+template <int kMode>
 __device__ __forceinline__ RowPre row_prefetch(const TcParams &p, long long tile, int r) {
     RowPre c = {};
     if (tile >= p.tiles) return c;
-    if (p.mode == MODE_SA) {
+    if ((kMode == MODE_SA)) {
         const int K = p.k;
         const int lgK = 31 - __clz(K);  // nsample is a power of two
         const int gpt = TC_ROWS >> lgK;  // groups per tile
@@ -304,10 +340,11 @@ __device__ __forceinline__ RowPre row_prefetch(const TcParams &p, long long tile
     return c;
 }
 
+template <int kMode>
 __device__ __forceinline__ RowCtx row_expand(const TcParams &p, const RowPre &q) {
     RowCtx c = {};
     c.ok = q.ok;
-    if (p.mode == MODE_SA) {
+    if ((kMode == MODE_SA)) {
         c.src0 = (long long)q.i0 * p.d;
         c.f = p.feat + c.src0;
         c.dx = q.a; c.dy = q.b; c.dz = q.c;
@@ -322,16 +359,16 @@ __device__ __forceinline__ RowCtx row_expand(const TcParams &p, const RowPre &q)
     return c;
 }
 
-template <bool kInBf16>
+template <bool kInBf16, int kMode>
 __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &x, const ADst &dst, int c8_from, int c8_end,
                                                const float (&sk)[8], bool sk_valid) {
     const bool ok = x.ok;
     if constexpr (kInBf16) {
         // bf16 activations: a 16-byte load is a whole 8-column chunk.  SA: the chunk IS the operand chunk (pure copy,
         // bit-identical to converting fp32 features here); FP: three chunks are unpacked, interpolated in fp32, repacked.
-        const int Dm = p.mode == MODE_SA ? p.d : p.d2;
-        const __nv_bfloat16 *b0 = reinterpret_cast<const __nv_bfloat16 *>(p.mode == MODE_SA ? (const void *)p.feat : (const void *)p.feat2);
-        const bool fp3 = p.mode != MODE_SA && p.fp_m != 1;
+        const int Dm = (kMode == MODE_SA) ? p.d : p.d2;
+        const __nv_bfloat16 *b0 = reinterpret_cast<const __nv_bfloat16 *>((kMode == MODE_SA) ? (const void *)p.feat : (const void *)p.feat2);
+        const bool fp3 = (kMode != MODE_SA) && p.fp_m != 1;
         int c8 = c8_from;
         const int c8_blk0 = min(c8_end, Dm / 8);
         for (; c8 < c8_blk0; c8 += 4) {
@@ -374,7 +411,7 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
             }
         }
         // skip features stored as bf16 and chunk aligned: pure copies as well
-        if (p.mode != MODE_SA && p.skip_bf16 && (Dm & 7) == 0 && (p.d1 & 7) == 0) {
+        if ((kMode != MODE_SA) && p.skip_bf16 && (Dm & 7) == 0 && (p.d1 & 7) == 0) {
             const __nv_bfloat16 *b1 = reinterpret_cast<const __nv_bfloat16 *>(p.feat1);
             const int c8_skip_end = min(c8_end, (Dm + p.d1) / 8);
             for (; c8 < c8_skip_end; ++c8) {
@@ -391,7 +428,7 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
                 const int c = c8 * 8 + j;
                 float y = 0.f;
                 if (ok) {
-                    if (p.mode == MODE_SA) {
+                    if ((kMode == MODE_SA)) {
                         if (c < Dm) y = __bfloat162float(b0[x.src0 + c]);
                         else if (c == Dm) y = x.dx;
                         else if (c == Dm + 1) y = x.dy;
@@ -412,9 +449,25 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
             st_chunk(dst(c8), v);
         }
         return;
-    } else if (p.mode == MODE_SA) {
+    } else if ((kMode == MODE_SA)) {
         const int D = p.d;
         const float *f = x.f;
+        if (D <= 5) {
+            // narrow input (xyz-only or xyz + colour levels): features and centred xyz fit the first 8-column chunk and
+            // every other chunk is zero padding -- no per-element branches
+            for (int c8 = c8_from; c8 < c8_end; ++c8) {
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (c8 == 0 && ok) {
+#pragma unroll
+                    for (int j = 0; j < 5; ++j)
+                        if (j < D) v[j] = __ldg(f + j);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = j == D ? x.dx : (j == D + 1 ? x.dy : (j == D + 2 ? x.dz : v[j]));
+                }
+                st_chunk(dst(c8), v);
+            }
+            return;
+        }
         const bool vec = ok && (D % 4 == 0) && p.feat_aligned;
         int c8 = c8_from;
         if (vec) {
@@ -533,54 +586,52 @@ __device__ __forceinline__ void gather_tail_tc(const TcParams &p, const RowCtx &
 // wavefronts instead of 16 scattered ones -- the per-thread-row gather is L1-wavefront bound).  A lane gets the source
 // row (and the interpolation weights) of the row it serves from that row's owner lane with shuffles.  U steps are
 // batched so U (SA: copy) or 3U (FP: three neighbours) 128-bit loads are in flight per lane.
-template <int U>
+template <int U, int kMode>
 __device__ __forceinline__ void coop_gather_bf16(const TcParams &p, const RowPre &pre, unsigned char *a, int warp, int lane,
                                                  int c8_begin, int c8_from, int c8_to) {
-    const bool sa = p.mode == MODE_SA;
+    const bool sa = (kMode == MODE_SA);
     // rows are addressed in 16-byte units with 32-bit row index x 32-bit pitch (one IMAD.WIDE.U32 per row pointer)
-    const uint4 *base = reinterpret_cast<const uint4 *>(sa ? (const void *)p.feat : (const void *)p.feat2) + c8_from;
+    const uint4 *base = reinterpret_cast<const uint4 *>(sa ? (const void *)p.feat : (const void *)p.feat2);
     const uint32_t pitch = (uint32_t)(sa ? p.d : p.d2) >> 3;
     const bool fp3 = !sa && p.fp_m != 1;
     const int nc = c8_to - c8_from;  // power of two, >= 4
     const int lg = 31 - __clz(nc);
-    const int my0 = pre.ok ? pre.i0 : -1, my1 = pre.i1, my2 = pre.i2;
+    // rows past the end of the launch carry index 0 and weight 0 (row_prefetch): they read a valid row and produce finite
+    // operand rows whose results are never stored, so the loads need no predicate and the registers no clearing
+    const int my0 = pre.i0, my1 = pre.i1, my2 = pre.i2;
     for (int base_item = 0; base_item < 32 * nc; base_item += 32 * U) {
+        // phase 1: every load of the batch is issued before the first use (3U x 128 bit in flight per lane for FP)
         uint4 q0[U], q1[U], q2[U];
-        float w0[U], w1[U], w2[U];
-        int rw[U], ch[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int item = base_item + 32 * u + lane;
-            rw[u] = item >> lg;
-            ch[u] = item & (nc - 1);
-            const int s0 = __shfl_sync(0xffffffffu, my0, rw[u]);
-            q0[u] = make_uint4(0u, 0u, 0u, 0u);
-            q1[u] = q0[u];
-            q2[u] = q0[u];
+            const int rw = item >> lg;
+            // 16-byte units, 32-bit unit index (launch_tc bounds rows x pitch): one IMAD + one wide IMAD per address
+            const uint32_t col = (uint32_t)((item & (nc - 1)) + c8_from);
+            const uint32_t s0 = (uint32_t)__shfl_sync(0xffffffffu, my0, rw);
+            q0[u] = __ldg(base + (s0 * pitch + col));
             if (fp3) {
-                const int s1 = __shfl_sync(0xffffffffu, my1, rw[u]);
-                const int s2 = __shfl_sync(0xffffffffu, my2, rw[u]);
-                w0[u] = __shfl_sync(0xffffffffu, pre.a, rw[u]);
-                w1[u] = __shfl_sync(0xffffffffu, pre.b, rw[u]);
-                w2[u] = __shfl_sync(0xffffffffu, pre.c, rw[u]);
-                if (s0 >= 0) {
-                    q0[u] = __ldg(base + (size_t)((unsigned long long)(uint32_t)s0 * pitch) + ch[u]);
-                    q1[u] = __ldg(base + (size_t)((unsigned long long)(uint32_t)s1 * pitch) + ch[u]);
-                    q2[u] = __ldg(base + (size_t)((unsigned long long)(uint32_t)s2 * pitch) + ch[u]);
-                }
-            } else if (s0 >= 0) {
-                q0[u] = __ldg(base + (size_t)((unsigned long long)(uint32_t)s0 * pitch) + ch[u]);
+                const uint32_t s1 = (uint32_t)__shfl_sync(0xffffffffu, my1, rw);
+                const uint32_t s2 = (uint32_t)__shfl_sync(0xffffffffu, my2, rw);
+                q1[u] = __ldg(base + (s1 * pitch + col));
+                q2[u] = __ldg(base + (s2 * pitch + col));
             }
         }
+        // phase 2: the weights of the served row arrive by shuffle only now, so they are not live across the loads
 #pragma unroll
         for (int u = 0; u < U; ++u) {
+            const int item = base_item + 32 * u + lane;
+            const int rw = item >> lg, ch = item & (nc - 1);
             uint4 o = q0[u];
             if (fp3) {
+                const float w0 = __shfl_sync(0xffffffffu, pre.a, rw);
+                const float w1 = __shfl_sync(0xffffffffu, pre.b, rw);
+                const float w2 = __shfl_sync(0xffffffffu, pre.c, rw);
                 const uint32_t *u0 = reinterpret_cast<const uint32_t *>(&q0[u]);
                 const uint32_t *u1 = reinterpret_cast<const uint32_t *>(&q1[u]);
                 const uint32_t *u2 = reinterpret_cast<const uint32_t *>(&q2[u]);
                 uint32_t *uo = reinterpret_cast<uint32_t *>(&o);
-                const float2 ww0 = make_float2(w0[u], w0[u]), ww1 = make_float2(w1[u], w1[u]), ww2 = make_float2(w2[u], w2[u]);
+                const float2 ww0 = make_float2(w0, w0), ww1 = make_float2(w1, w1), ww2 = make_float2(w2, w2);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     // bf16 -> fp32 is a 16-bit shift; packed f32x2 = the scalar rn sequence of three_interpolate per lane
@@ -591,14 +642,14 @@ __device__ __forceinline__ void coop_gather_bf16(const TcParams &p, const RowPre
                     uo[e] = pack_bf16(y.x, y.y);
                 }
             }
-            *reinterpret_cast<uint4 *>(a + swz_chunk(warp * 32 + rw[u], c8_from + ch[u] - c8_begin, TC_ROWS)) = o;
+            *reinterpret_cast<uint4 *>(a + swz_chunk(warp * 32 + rw, c8_from + ch - c8_begin, TC_ROWS)) = o;
         }
     }
 }
 
 // Two instantiations (kernels below): fp32 gathered features (lean: 80 registers, 4 CTAs/SM) and bf16 gathered features
 // (96 registers, 3 CTAs/SM).
-template <bool kInBf16, int NWW>
+template <bool kInBf16, int NWW, int kMode>
 __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
     // NWW worker warps: warp w serves TMEM lane quarter (w & 3), i.e. tile rows 32 (w & 3) .. +31; with NWW == 8 the warps
     // w and w + 4 share a quarter and split its work by columns (half = w >> 2): the gather of a tile has twice the loads
@@ -661,7 +712,7 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                 for (int l = 0; l < p.num_layers; ++l) {
                     const TcLayer &L = p.layer[l];
                     const int nkb = L.nkb;
-                    const bool tr = p.pool_t && l == p.num_layers - 1;
+                    const bool tr = (kMode == MODE_SA) && l == p.num_layers - 1;
                     // normal layers: one [nblk x 64] tile per stage.  Transposed last layer: a 128-row block of W (the
                     // M operand) per stage, assembled from the same packed tiles.
                     const int nnb = tr ? (L.npad + 127) / 128 : L.nnb;
@@ -677,6 +728,11 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                                 if (!tr) {
                                     mbar_expect_tx(bar_full + 8 * stage, tile_bytes);
                                     bulk_g2s(dst, src + (size_t)(nb * nkb + kb) * tile_bytes, tile_bytes, bar_full + 8 * stage);
+                                } else if (p.pool_dup > 1) {
+                                    // the whole layer is one tile of npad <= 64 rows: pool_dup copies fill the 128 rows
+                                    mbar_expect_tx(bar_full + 8 * stage, 128u * 128u);
+                                    for (int q = 0; q < p.pool_dup; ++q)
+                                        bulk_g2s(dst + (uint32_t)q * tile_bytes, src + (size_t)kb * tile_bytes, tile_bytes, bar_full + 8 * stage);
                                 } else {
                                     const int row0 = nb * 128, rows = min(128, L.npad - row0);
                                     mbar_expect_tx(bar_full + 8 * stage, (uint32_t)rows * 128u);
@@ -714,7 +770,7 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
             int dm = 0;
             for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 for (int l = 0; l < p.num_layers; ++l) {
-                    const bool tr = p.pool_t && l == p.num_layers - 1;  // D^T = W * A^T: W is the M operand, 128 samples are N
+                    const bool tr = (kMode == MODE_SA) && l == p.num_layers - 1;  // D^T = W * A^T: W is the M operand, 128 samples are N
                     const int kpad = p.layer[l].kpad, nblk = tr ? 128 : p.layer[l].nblk;
                     const int nkb = p.layer[l].nkb;
                     const int nnb = tr ? (p.layer[l].npad + 127) / 128 : p.layer[l].nnb;
@@ -782,25 +838,30 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
         const int wq = warp & 3;                     // lane quarter
         const int half = warp >> 2;                  // which share of the columns (NWW == 8)
         const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+        const uint32_t a_row = smem_u32(a_buf) + (uint32_t)r * 128u;  // this row of a k-block, shared-window address
+        const uint32_t r7s = (uint32_t)(r & 7) << 4;                  // swizzle term of the row
+        const uint32_t sbias_u32 = smem_u32(sbias);
         uint32_t it = 0;
         long long out_row = 0;
         bool srow_ok = false;
         long long *dbg = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? p.dbg : nullptr;
         int di = 0;
         uint32_t afree_it = 0, tile_it = 0;
-        RowPre pre = row_prefetch(p, blockIdx.x, r);
+        RowPre pre = row_prefetch<kMode>(p, blockIdx.x, r);
         for (long long tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             if (dbg && di < 240) dbg[di++] = clock64();
             {
-                const RowCtx ctx = row_expand(p, pre);
+                const RowCtx ctx = row_expand<kMode>(p, pre);
                 out_row = ctx.out_row;
                 srow_ok = ctx.ok;
-                if (p.mode == MODE_FP) srow[r] = ctx.ok ? ctx.out_row : -1;  // read after the layer barriers, same warp
+                // FP: element offset of each tile row's destination (-1 = past the end); read after the layer barriers by
+                // the same warp (odd-width store below)
+                if ((kMode == MODE_FP)) srow[r] = ctx.ok ? ctx.out_row * p.layer[p.num_layers - 1].cout : -1;
                 const int nkb0 = (p.layer[0].kpad + KBLK - 1) / KBLK;
                 const int c8_total = p.layer[0].kpad / 8;
                 // a narrow fp32 skip block (the xyz/colour rows of fp1) is fetched now, not after the first chunk's MMAs
                 float sk[8];
-                const bool sk_valid = kInBf16 && p.mode == MODE_FP && !p.skip_bf16 && p.d1 <= 8 && (p.d2 & 7) == 0;
+                const bool sk_valid = kInBf16 && (kMode == MODE_FP) && !p.skip_bf16 && p.d1 <= 8 && (p.d2 & 7) == 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) sk[j] = (sk_valid && ctx.ok && j < p.d1) ? __ldg(ctx.f1 + j) : 0.f;
                 const int nfull0 = nkb0 - p.thin;  // whole 64-column k-blocks; a thin last block rides with the last pass
@@ -821,7 +882,7 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                     if constexpr (kInBf16) {
                         // bf16 feature block: coalesced warp-cooperative gather when its chunk count in this pass is a
                         // power of two (>= 4) and the block ends on a k-block boundary; the tail stays one thread per row
-                        const int Dm = p.mode == MODE_SA ? p.d : p.d2;
+                        const int Dm = (kMode == MODE_SA) ? p.d : p.d2;
                         const int blk0_end = min(ce, Dm >> 3);
                         const int nc = blk0_end - cb;
                         if ((Dm & 63) == 0 && nc >= 4 && (nc & (nc - 1)) == 0) {
@@ -830,8 +891,8 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                             const int ncw = split ? nc >> 1 : nc;
                             const int c_lo = cb + (split ? half * ncw : 0);
                             if (split || half == 0) {
-                                if (p.mode == MODE_SA) coop_gather_bf16<4>(p, pre, a_buf, wq, lane, cb, c_lo, c_lo + ncw);
-                                else coop_gather_bf16<2>(p, pre, a_buf, wq, lane, cb, c_lo, c_lo + ncw);
+                                if ((kMode == MODE_SA)) coop_gather_bf16<4, kMode>(p, pre, a_buf, wq, lane, cb, c_lo, c_lo + ncw);
+                                else coop_gather_bf16<FP_GATHER_U, kMode>(p, pre, a_buf, wq, lane, cb, c_lo, c_lo + ncw);
                             }
                             from = blk0_end;
                         }
@@ -844,14 +905,14 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                             if (half == 0) t_hi = mid < ce ? mid : ce;
                             else t_lo = mid < ce ? mid : ce;
                         }
-                        if (t_lo < t_hi) gather_tail_tc<kInBf16>(p, ctx, dst, t_lo, t_hi, sk, sk_valid);
+                        if (t_lo < t_hi) gather_tail_tc<kInBf16, kMode>(p, ctx, dst, t_lo, t_hi, sk, sk_valid);
                     }
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_a);
                 }
             }
-            pre = row_prefetch(p, tile + gridDim.x, r);  // next tile's index-level loads fly while this tile's layers run
+            pre = row_prefetch<kMode>(p, tile + gridDim.x, r);  // next tile's index-level loads fly while this tile's layers run
             if (dbg && di < 240) dbg[di++] = clock64();
             for (int l = 0; l < p.num_layers; ++l) {
                 const TcLayer &L = p.layer[l];
@@ -860,7 +921,7 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                 const float *bl = sbias + L.bias_off;
                 // the transposed last layer hands its accumulators over per 128-channel block (when it is one pass)
                 bool per_block = false;
-                if (last && p.pool_t) {
+                if (last && (kMode == MODE_SA)) {
                     const int nkb = (L.kpad + KBLK - 1) / KBLK;
                     per_block = (l == 0 ? nkb - p.thin : nkb) <= (l == 0 ? p.kchunk : nkb);
                 }
@@ -870,7 +931,7 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                     tc_fence_after();
                 }
                 if (dbg && di < 240) dbg[di++] = clock64();
-                if (last && p.pool_t) {
+                if (last && (kMode == MODE_SA)) {
                     // Transposed last layer of an SA block: TMEM lane = output channel, column = sample, so the max over
                     // the nsample rows of a group is a register-local tree (no shuffles / CREDUX), bias and ReLU are
                     // applied once per group (max(x)+b == max(x+b) in fp32: rounding is monotone), and the 32 lanes of a
@@ -884,12 +945,23 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                             mbar_wait(bar_blk + 8 * cb, tile_it & 1);
                             tc_fence_after();
                         }
-                        const int ch0 = cb * 128 + wq * 32;
-                        if (ch0 >= cout) continue;  // warp-uniform: e.g. 64 channels keep two warps busy
+                        int ch0 = cb * 128 + wq * 32;
+                        int s_lo = 0, s_hi = TC_ROWS;
+                        if (p.pool_dup > 1) {
+                            // lanes 32 wq .. +31 hold channel quarter (wq mod nq) again: this warp pools sample part wq / nq
+                            const int nq = npad >> 5;  // 1 or 2
+                            ch0 = (wq & (nq - 1)) * 32;
+                            s_lo = (wq >> (nq - 1)) * (32 * nq);
+                            s_hi = s_lo + 32 * nq;
+                        }
+                        if (ch0 >= cout) continue;  // warp-uniform: e.g. 64 un-duplicated channels keep two warps busy
                         // two warps per quarter: samples [0, 64) and [64, 128) (whole groups while nsample <= 64)
                         const bool tsplit = NHALF == 2 && K <= 64;
                         if (!tsplit && half != 0) continue;
-                        const int s_lo = tsplit ? half * 64 : 0, s_hi = tsplit ? s_lo + 64 : TC_ROWS;
+                        if (tsplit) {
+                            s_lo = half * 64;
+                            s_hi = s_lo + 64;
+                        }
                         const int ch = ch0 + lane;
                         const float bias = bl[ch];
                         float run = 0.f;
@@ -944,22 +1016,14 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                     uint32_t acc[32];
                     tmem_ld32(lane_base + (uint32_t)c0, acc);
                     if (!last) {
-                        // bias add as packed f32x2, conversion to bf16x2, ReLU on the packed pair (max(bf16(x), 0) ==
-                        // bf16(max(x, 0))): ~70 instructions per 32 columns instead of ~130
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 b0 = *reinterpret_cast<const float4 *>(bl + c0 + 8 * q);
-                            const float4 b1 = *reinterpret_cast<const float4 *>(bl + c0 + 8 * q + 4);
-                            const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 0]), __uint_as_float(acc[8 * q + 1])), make_float2(b0.x, b0.y));
-                            const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 2]), __uint_as_float(acc[8 * q + 3])), make_float2(b0.z, b0.w));
-                            const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 4]), __uint_as_float(acc[8 * q + 5])), make_float2(b1.x, b1.y));
-                            const float2 s3 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 6]), __uint_as_float(acc[8 * q + 7])), make_float2(b1.z, b1.w));
-                            // conversion to bf16x2 with the ReLU folded into the instruction (cvt.rn.relu.bf16x2.f32)
-                            uint4 pk;
-                            pk.x = cvt_bf16x2(s0.x, s0.y, relu); pk.y = cvt_bf16x2(s1.x, s1.y, relu);
-                            pk.z = cvt_bf16x2(s2.x, s2.y, relu); pk.w = cvt_bf16x2(s3.x, s3.y, relu);
-                            *reinterpret_cast<uint4 *>(a_buf + swz_chunk(r, (c0 >> 3) + q, TC_ROWS)) = pk;
-                        }
+                        // hidden layer: bias (packed f32x2), ReLU folded into the bf16x2 conversion, 128-bit stores of the
+                        // next layer's operand.  Addresses are 32-bit shared-window values: row base + k-block + the
+                        // swizzled 16-byte slot, where slot(c) = (c << 4) ^ ((r & 7) << 4) and c = 4 * (c0/32 & 1) + q.
+                        const uint32_t dst0 = a_row + (uint32_t)(c0 >> 6) * A_BLOCK_BYTES;
+                        const uint32_t x0 = (uint32_t)((c0 >> 3) & 4) << 4 ^ r7s;
+                        const uint32_t bsrc = sbias_u32 + (uint32_t)(L.bias_off + c0) * 4u;
+                        if (relu) epilogue_chunk<true>(acc, bsrc, dst0, x0);
+                        else epilogue_chunk<false>(acc, bsrc, dst0, x0);
                         continue;
                     }
                     float v[32];
@@ -1019,12 +1083,23 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                             __syncwarp();
                             const int col = c0 + lane;
                             if (col < cout) {
+                                // lane <-> column: a row leaves as one contiguous run of `cout` elements.  The per-row
+                                // destination offsets were multiplied out when the tile started.
+                                const long long *so = srow + wq * 32;
+                                const float *sv = stg + lane;
+                                if (p.out_bf16) {
+                                    __nv_bfloat16 *oc = reinterpret_cast<__nv_bfloat16 *>(p.out) + col;
 #pragma unroll 8
-                                for (int rr = 0; rr < 32; ++rr) {
-                                    const long long dst = srow[wq * 32 + rr];
-                                    if (dst >= 0) {
-                                        if (p.out_bf16) reinterpret_cast<__nv_bfloat16 *>(p.out)[(size_t)dst * cout + col] = __float2bfloat16_rn(stg[rr * 33 + lane]);
-                                        else p.out[(size_t)dst * cout + col] = stg[rr * 33 + lane];
+                                    for (int rr = 0; rr < 32; ++rr) {
+                                        const long long off = so[rr];
+                                        if (off >= 0) oc[off] = __float2bfloat16_rn(sv[rr * 33]);
+                                    }
+                                } else {
+                                    float *oc = p.out + col;
+#pragma unroll 8
+                                    for (int rr = 0; rr < 32; ++rr) {
+                                        const long long off = so[rr];
+                                        if (off >= 0) oc[off] = sv[rr * 33];
                                     }
                                 }
                             }
@@ -1056,12 +1131,16 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
 // 3 CTAs x 6 warps allow -- the 18 warps spread 5/5/4/4 over the four 16 K-register partitions (__maxnreg__(112) removes
 // the spills and drops to 2 CTAs/SM: fp1+head 120 -> 164 us); blocks that shared memory or TMEM limit to <= 2 CTAs/SM
 // anyway use the un-spilled build.
-__global__ void __launch_bounds__(TC_THREADS, 4) row_mlp_tc_kernel_f32(const __grid_constant__ TcParams p) { row_mlp_tc_body<false, 4>(p); }
-__global__ void __launch_bounds__(TC_THREADS, 3) row_mlp_tc_kernel_bf16(const __grid_constant__ TcParams p) { row_mlp_tc_body<true, 4>(p); }
-__global__ void __launch_bounds__(TC_THREADS, 2) row_mlp_tc_kernel_bf16_wide(const __grid_constant__ TcParams p) { row_mlp_tc_body<true, 4>(p); }
+#define PN2_TC_KERNEL(name, threads, ctas, bf16, nww)                                                                       \
+    __global__ void __launch_bounds__(threads, ctas) name##_sa(const __grid_constant__ TcParams p) { row_mlp_tc_body<bf16, nww, MODE_SA>(p); } \
+    __global__ void __launch_bounds__(threads, ctas) name##_fp(const __grid_constant__ TcParams p) { row_mlp_tc_body<bf16, nww, MODE_FP>(p); }
+// One build per block kind (SA / FP): the mode is a compile-time constant in the gather and the epilogues.
+PN2_TC_KERNEL(row_mlp_tc_kernel_f32, TC_THREADS, 4, false, 4)
+PN2_TC_KERNEL(row_mlp_tc_kernel_bf16, TC_THREADS, 3, true, 4)
+PN2_TC_KERNEL(row_mlp_tc_kernel_bf16_wide, TC_THREADS, 2, true, 4)
 // Eight worker warps per 128-row tile, at most two CTAs per SM (102 registers): half the per-tile latency chain.
-__global__ void __launch_bounds__(TC_THREADS_W8, 2) row_mlp_tc_kernel_f32_w8(const __grid_constant__ TcParams p) { row_mlp_tc_body<false, 8>(p); }
-__global__ void __launch_bounds__(TC_THREADS_W8, 2) row_mlp_tc_kernel_bf16_w8(const __grid_constant__ TcParams p) { row_mlp_tc_body<true, 8>(p); }
+PN2_TC_KERNEL(row_mlp_tc_kernel_f32_w8, TC_THREADS_W8, 2, false, 8)
+PN2_TC_KERNEL(row_mlp_tc_kernel_bf16_w8, TC_THREADS_W8, 2, true, 8)
 
 // ---- weight packing -----------------------------------------------------------------------------------
 // Packed image of one layer: for nb in n-blocks, for kb in k-blocks: a [nblk rows x 64 bf16] tile, row n at n*128 B,
@@ -1259,15 +1338,27 @@ int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, c
     // persistent grid: as many CTAs as can be resident (shared memory, 512 TMEM columns, registers), at most one per tile
     int per_sm = ctas_per_sm(P);
     if (p.in_bf16 && per_sm > 3) per_sm = 3;  // register budget of the bf16-input build
-    void (*kernel)(TcParams) = !p.in_bf16 ? row_mlp_tc_kernel_f32 : (per_sm <= 2 ? row_mlp_tc_kernel_bf16_wide : row_mlp_tc_kernel_bf16);
+    const bool sa = p.mode == MODE_SA;
+#define PN2_TC_PICK(name) (sa ? name##_sa : name##_fp)
+    void (*kernel)(TcParams) = !p.in_bf16 ? PN2_TC_PICK(row_mlp_tc_kernel_f32)
+                                          : (per_sm <= 2 ? PN2_TC_PICK(row_mlp_tc_kernel_bf16_wide) : PN2_TC_PICK(row_mlp_tc_kernel_bf16));
     int threads = TC_THREADS;
     // small launches (a few tiles per SM at most) cannot fill the SM with tiles in flight: split each tile over 8 worker
     // warps instead (measured, batch 32: sa3 31 -> 29, sa4 27 -> 25, fp4 40 -> 37, fp3 31 -> 28, fp2 31 -> 29 us; launches
     // with many tiles per SM are faster with 3-4 resident CTAs of 4 worker warps: sa1 93 vs 133 us)
     if (g_tc_workers == 8 || (g_tc_workers == 0 && tiles <= 4ll * sm_count())) {
         if (per_sm > 2) per_sm = 2;
-        kernel = p.in_bf16 ? row_mlp_tc_kernel_bf16_w8 : row_mlp_tc_kernel_f32_w8;
+        kernel = p.in_bf16 ? PN2_TC_PICK(row_mlp_tc_kernel_bf16_w8) : PN2_TC_PICK(row_mlp_tc_kernel_f32_w8);
         threads = TC_THREADS_W8;
+    }
+    p.pool_dup = 1;
+    if (p.pool_t && threads == TC_THREADS) {
+        const TcLayer &L = P.layer[P.num_layers - 1];
+        if (L.npad <= 64 && L.nblk == L.npad && p.k <= L.npad) p.pool_dup = 128 / L.npad;
+    }
+    if (p.in_bf16) {
+        const long long src_rows = p.mode == MODE_SA ? (p.groups / p.m) * (long long)p.n : (p.rows / p.n) * (long long)p.fp_m;
+        PN2_REQUIRE(src_rows * ((p.mode == MODE_SA ? p.d : p.d2) / 8) <= 4294967295ll, "row_mlp_tc: bf16 feature tensor exceeds 2^32 16-byte units");
     }
     PN2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
     long long grid = (long long)per_sm * sm_count();

@@ -44,6 +44,7 @@ def hooked(name, *args):
 _lib.call = hooked
 import pn2_b200.pointnet_util as U  # noqa: E402
 U._lib.call = hooked
+U.set_mlp_precision("bf16")  # the drop-in modules default to the fp32 path
 
 with torch.no_grad():
     for _ in range(2):
