@@ -35,6 +35,9 @@ def main():
     ap.add_argument("--deterministic", action="store_true",
                     help="bit-reproducible training: fixed-order backwards of gather / grouping / interpolation "
                          "(pn2_scatter_rows_det) and torch's deterministic algorithms")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the step as CUDA graphs (pn2_b200.models.GraphedTrainStep): zero-grad + forward + backward in one "
+                         "graph, one all-reduce of the flat gradient buffer, the Adam update in a second graph")
     args = ap.parse_args()
     if args.deterministic:
         os.environ.setdefault("CUBLAS_WORKSPACE_CONFIG", ":4096:8")
@@ -48,8 +51,9 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     torch.manual_seed(0)
     net = (PointNet2Multiview2Msg(21) if args.model == "msg" else PointNet2SemSeg(21)).to(device).train()
-    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local]) if world > 1 else net
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local]) if world > 1 and not args.graph else net
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, capturable=args.graph)
+    stepper = None
     B, N = args.batch_per_gpu, args.npoints
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     losses, t_steps = [], []
@@ -63,14 +67,23 @@ def main():
         weights = torch.ones_like(target, dtype=torch.float32)
         second = (torch.randn(B, 128, N, generator=g).to(device) if args.model == "msg"
                   else pts[:, :, 3:].permute(0, 2, 1).contiguous())
+        if args.graph and stepper is None:
+            from pn2_b200.models import GraphedTrainStep
+
+            def loss_fn(pred, tgt):
+                return F.cross_entropy(pred.reshape(-1, 21), tgt.reshape(-1), ignore_index=0)
+            stepper = GraphedTrainStep(net, opt, loss_fn, xyz, second, target)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        opt.zero_grad(set_to_none=True)
-        pred = model(xyz, second)                                    # (B, N, 21)
-        loss = F.cross_entropy(pred.reshape(-1, 21), target.reshape(-1), ignore_index=0, reduction="none")
-        loss = (loss * weights.reshape(-1)).mean()
-        loss.backward()                                              # DDP all-reduces the gradients here
-        opt.step()
+        if stepper is not None:
+            loss = stepper.step(xyz, second, target)                     # graphs + one flat all-reduce
+        else:
+            opt.zero_grad(set_to_none=True)
+            pred = model(xyz, second)                                    # (B, N, 21)
+            loss = F.cross_entropy(pred.reshape(-1, 21), target.reshape(-1), ignore_index=0, reduction="none")
+            loss = (loss * weights.reshape(-1)).mean()
+            loss.backward()                                              # DDP all-reduces the gradients here
+            opt.step()
         torch.cuda.synchronize()
         t_steps.append(time.perf_counter() - t0)
         losses.append(float(loss.detach()))

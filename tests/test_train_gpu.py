@@ -69,3 +69,46 @@ def test_sa_fp_train_step_matches_reference_gradients(cuda):
     before = sa_g.mlp_convs[0].weight.detach().clone()
     opt.step()
     assert not torch.equal(before, sa_g.mlp_convs[0].weight.detach())
+
+
+def test_graphed_train_step_reproduces_the_eager_loop(cuda):
+    """GraphedTrainStep (one CUDA graph of zero-grad + forward + loss + backward + Adam) against the eager loop of
+    train_scannet_semseg.py:135-146 from the same initial weights, fixed-order backwards: identical losses and weights."""
+    import torch.nn.functional as F
+    from pn2_b200 import pointnet2_utils as pu
+    from pn2_b200.models import GraphedTrainStep, PointNet2SemSeg
+    B, N = 2, 2048
+    pts = torch.from_numpy(scenes.scannet_batch(31, B, N)).to(cuda)
+    xyz = pts[:, :, :3].permute(0, 2, 1).contiguous()
+    rgb = pts[:, :, 3:].permute(0, 2, 1).contiguous()
+    target = (pts[:, :, 2].clamp(0, 2.69) / 2.7 * 20).long() + 1
+
+    def loss_fn(logits, tgt):
+        return F.cross_entropy(logits.reshape(-1, 21), tgt.reshape(-1), ignore_index=0)
+
+    def make():
+        torch.manual_seed(3)
+        net = PointNet2SemSeg(21).to(cuda).train()
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0  # the random stream of a replayed graph differs from the eager one
+        return net, torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4, capturable=True)
+
+    prev = pu.set_deterministic(True)
+    try:
+        net_e, opt_e = make()
+        eager = []
+        for _ in range(3):
+            opt_e.zero_grad(set_to_none=True)
+            loss = loss_fn(net_e(xyz, rgb), target)
+            loss.backward()
+            opt_e.step()
+            eager.append(float(loss.detach()))
+        net_g, opt_g = make()
+        stepper = GraphedTrainStep(net_g, opt_g, loss_fn, xyz, rgb, target)
+        graphed = [float(stepper.step(xyz, rgb, target)) for _ in range(3)]
+    finally:
+        pu.set_deterministic(prev)
+    assert graphed == eager, (graphed, eager)
+    for (k, a), (_, b) in zip(net_e.state_dict().items(), net_g.state_dict().items()):
+        assert torch.equal(a, b), k
