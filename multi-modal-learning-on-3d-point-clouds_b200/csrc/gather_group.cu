@@ -133,6 +133,36 @@ transpose_kernel(int r, int c, const float *__restrict__ in, float *__restrict__
     }
 }
 
+// Narrow transposes (the (B, 3, N) <-> (B, N, 3) conversions at the model boundary): one thread per long-axis element,
+// the <= 8 short-axis values in registers; reads and writes are coalesced along the long axis (the 32 x 32 tile kernel
+// would run 8192 CTAs with 3 of 32 rows active).
+template <bool kRowsNarrow>
+__global__ void __launch_bounds__(256)
+transpose_narrow_kernel(int r, int c, const float *__restrict__ in, float *__restrict__ out) {
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    in += (size_t)b * r * c;
+    out += (size_t)b * r * c;
+    float v[8];
+    if (kRowsNarrow) {  // (r <= 8, c) -> (c, r)
+        if (j >= c) return;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < r) v[i] = in[(size_t)i * c + j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < r) out[(size_t)j * r + i] = v[i];
+    } else {  // (r, c <= 8) -> (c, r)
+        if (j >= r) return;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < c) v[i] = in[(size_t)j * c + i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < c) out[(size_t)i * r + j] = v[i];
+    }
+}
+
 int check_common(const char *op, int b, int c, int n, long long J) {
     PN2_REQUIRE(b >= 0 && c >= 0 && n >= 1 && J >= 0, "%s: bad dims b=%d c=%d n=%d J=%lld", op, b, c, n, J);
     PN2_REQUIRE(b <= 65535 && ceil_div(c, GG_CH) <= 65535, "%s: b or c exceeds the grid limits", op);
@@ -210,6 +240,16 @@ extern "C" int pn2_transpose(int b, int r, int c, const float *in, float *out, v
     if (b == 0 || r == 0 || c == 0) return PN2_OK;
     PN2_REQUIRE(in && out, "transpose: null pointer");
     PN2_REQUIRE(b <= 65535 && ceil_div(c, 32) <= 65535, "transpose: dims exceed the grid limits");
+    if (r <= 8 && c >= 256) {
+        transpose_narrow_kernel<true><<<dim3(ceil_div(c, 256), b), 256, 0, (cudaStream_t)stream>>>(r, c, in, out);
+        PN2_LAUNCH_OK("transpose_narrow");
+        return PN2_OK;
+    }
+    if (c <= 8 && r >= 256) {
+        transpose_narrow_kernel<false><<<dim3(ceil_div(r, 256), b), 256, 0, (cudaStream_t)stream>>>(r, c, in, out);
+        PN2_LAUNCH_OK("transpose_narrow");
+        return PN2_OK;
+    }
     dim3 grid(ceil_div(r, 32), ceil_div(c, 32), b);
     transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(r, c, in, out);
     PN2_LAUNCH_OK("transpose");

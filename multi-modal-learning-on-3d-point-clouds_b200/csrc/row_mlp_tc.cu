@@ -1138,6 +1138,7 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
 PN2_TC_KERNEL(row_mlp_tc_kernel_f32, TC_THREADS, 4, false, 4)
 PN2_TC_KERNEL(row_mlp_tc_kernel_bf16, TC_THREADS, 3, true, 4)
 PN2_TC_KERNEL(row_mlp_tc_kernel_bf16_wide, TC_THREADS, 2, true, 4)
+__global__ void __launch_bounds__(TC_THREADS, 4) row_mlp_tc_kernel_bf16_x4_sa(const __grid_constant__ TcParams p) { row_mlp_tc_body<true, 4, MODE_SA>(p); }
 // Eight worker warps per 128-row tile, at most two CTAs per SM (102 registers): half the per-tile latency chain.
 PN2_TC_KERNEL(row_mlp_tc_kernel_f32_w8, TC_THREADS_W8, 2, false, 8)
 PN2_TC_KERNEL(row_mlp_tc_kernel_bf16_w8, TC_THREADS_W8, 2, true, 8)
@@ -1255,7 +1256,7 @@ int g_tc_max_ctas = 8;  // developer knob (pn2_debug_set_tc_max_ctas)
 int g_tc_workers = 0;   // worker warps per tile: 0 = by launch size, 4, or 8 (pn2_debug_set_tc_workers)
 
 int ctas_per_sm(const Plan &P) {
-    int per_sm = (int)((TC_SMEM_LIMIT + 1024) / P.smem_bytes);
+    int per_sm = (int)((TC_SMEM_LIMIT + 1024) / (P.smem_bytes + 1024));  // + 1 KB per CTA reserved by the system
     if (per_sm > 512 / P.tmem_cols) per_sm = 512 / P.tmem_cols;
     if (per_sm > g_tc_max_ctas) per_sm = g_tc_max_ctas;
     return per_sm < 1 ? 1 : per_sm;
@@ -1285,9 +1286,11 @@ Plan sa_plan(const Plan &P0, bool in_bf16) {
     if (P.stage_bytes < 128 * 128) P.stage_bytes = 128 * 128;
     P.fits = false;
     if (P.tmem_cols > 512) return P;
-    const size_t fixed = 1024 + (size_t)P.a_bytes + TC_TAIL_BYTES + (size_t)P.bias_floats * 4;
+    // (no alignment slack: the dynamic shared-memory base is 1024-byte aligned by declaration, and sa2-like blocks -- 20 KB
+    // operand, two 16 KB stages -- fit four CTAs per SM only without it)
+    const size_t fixed = (size_t)P.a_bytes + TC_TAIL_BYTES + (size_t)P.bias_floats * 4;
     int cmax = 512 / P.tmem_cols;
-    const int reg_cap = in_bf16 ? 3 : 4;
+    const int reg_cap = 4;  // both SA builds (fp32 and bf16 features) fit 80 registers
     if (cmax > reg_cap) cmax = reg_cap;
     for (int c = cmax; c >= 1 && !P.fits; --c)
         for (int st = MAX_STAGES; st >= 2 && !P.fits; --st)
@@ -1335,13 +1338,16 @@ int launch_tc(TcParams &p, const Plan &P, const void *packed, long long tiles, c
     p.kchunk = P.kchunk;
     p.thin = P.thin;
     p.tiles = tiles;
+    const bool sa = p.mode == MODE_SA;
     // persistent grid: as many CTAs as can be resident (shared memory, 512 TMEM columns, registers), at most one per tile
     int per_sm = ctas_per_sm(P);
-    if (p.in_bf16 && per_sm > 3) per_sm = 3;  // register budget of the bf16-input build
-    const bool sa = p.mode == MODE_SA;
+    // register budget of the bf16-input builds: the SA build fits 80 registers (4 CTAs/SM: sa2 39.3 -> 35.3 us), the FP
+    // build (three-row interpolating gather) needs 96 (at 80 it spills 164 bytes: fp1+head 107 -> 115 us)
+    if (p.in_bf16 && per_sm > (sa ? 4 : 3)) per_sm = sa ? 4 : 3;
 #define PN2_TC_PICK(name) (sa ? name##_sa : name##_fp)
     void (*kernel)(TcParams) = !p.in_bf16 ? PN2_TC_PICK(row_mlp_tc_kernel_f32)
-                                          : (per_sm <= 2 ? PN2_TC_PICK(row_mlp_tc_kernel_bf16_wide) : PN2_TC_PICK(row_mlp_tc_kernel_bf16));
+                                          : (per_sm <= 2 ? PN2_TC_PICK(row_mlp_tc_kernel_bf16_wide)
+                                                         : (per_sm >= 4 ? row_mlp_tc_kernel_bf16_x4_sa : PN2_TC_PICK(row_mlp_tc_kernel_bf16)));
     int threads = TC_THREADS;
     // small launches (a few tiles per SM at most) cannot fill the SM with tiles in flight: split each tile over 8 worker
     // warps instead (measured, batch 32: sa3 31 -> 29, sa4 27 -> 25, fp4 40 -> 37, fp3 31 -> 28, fp2 31 -> 29 us; launches

@@ -68,3 +68,15 @@ def test_contiguity_and_dtype_errors(cuda):
     lib = _lib.load()
     assert lib.pn2_sa_mlp_max(1, 8, 1, 3, 0, None, None, None, None, 0, None, None, 0, 0, None) != 0  # nsample not a power of two / null mlp
     assert len(lib.pn2_last_error()) > 0
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 8192), (3, 6, 1000), (1, 8, 256), (2, 8192, 3), (2, 300, 5), (2, 3, 100), (2, 64, 1024),
+                                   (1, 131, 777), (2, 9, 4096)])
+def test_transpose_matches_torch(cuda, shape):
+    """pn2_transpose ((B, C, N) <-> (B, N, C) at the module boundary): the narrow-axis kernels (<= 8 rows or columns,
+    long axis >= 256) and the tiled kernel give exactly torch's permuted copy."""
+    from pn2_b200.pointnet_util import to_channel_first, to_channel_last
+    g = torch.Generator(device="cpu").manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g).to(cuda)
+    assert torch.equal(to_channel_last(x), x.permute(0, 2, 1).contiguous())
+    assert torch.equal(to_channel_first(x), x.permute(0, 2, 1).contiguous())
