@@ -84,6 +84,33 @@ def test_fps_few_warp_kernels_agree_with_reference(cuda, mode, kind, B, N, M):
     np.testing.assert_array_equal(got, orc.furthest_point_sample(xyz, M))
 
 
+@pytest.mark.parametrize("mode", [1, 7])
+@pytest.mark.parametrize("kind,B,N,M", [("scannet", 4, 8192, 1024), ("dup", 2, 8192, 1024), ("lattice", 2, 8192, 1024), ("uniform", 2, 8192, 2048),
+                                        ("dup", 2, 5000, 5100), ("uniform", 2, 4097, 256), ("lattice", 2, 4096, 512), ("dup", 3, 2049, 300),
+                                        ("same", 2, 8192, 200), ("plane", 2, 6000, 700), ("line", 1, 8192, 400)])
+def test_fps_slab_kernel_bit_exact(cuda, mode, kind, B, N, M):
+    """One CTA per cloud with spatial slabs per warp and skipped rounds (mode 1 = the default single-CTA policy) against
+    the oracle and the index-interleaved kernel it replaced (developer mode 7): duplicates / lattices (frequent exact
+    ties, explicit tie keys), degenerate clouds (all points equal: zero extent; points on a plane / a line), padded slabs."""
+    from pn2_b200 import _lib
+    if kind == "same":
+        xyz = np.tile(np.float32([[0.25, -1.5, 3.0]]), (B, N, 1))
+    elif kind == "plane":
+        xyz = clouds("uniform", B, N, 11 * N + M)
+        xyz[:, :, 2] = np.float32(0.5)
+    elif kind == "line":
+        xyz = clouds("dup", B, N, 13 * N + M)
+        xyz[:, :, 1:] = np.float32(-2.0)
+    else:
+        xyz = clouds(kind, B, N, 9 * N + M)
+    _lib.load().pn2_debug_set_fps_mode(mode)
+    try:
+        got = pu.furthest_point_sample(dev(xyz, cuda), M).cpu().numpy()
+    finally:
+        _lib.load().pn2_debug_set_fps_mode(0)
+    np.testing.assert_array_equal(got, orc.furthest_point_sample(xyz, M))
+
+
 @pytest.mark.parametrize("kind,B,N,M", [("dup", 1, 49153, 60), ("lattice", 1, 60000, 48), ("dup", 2, 65536, 40), ("uniform", 1, 57000, 64),
                                         ("dup", 1, 70000, 40), ("dup", 2, 131072, 24), ("lattice", 1, 100000, 32), ("uniform", 1, 65537, 48)])
 def test_fps_large_clouds_bit_exact(cuda, kind, B, N, M):
