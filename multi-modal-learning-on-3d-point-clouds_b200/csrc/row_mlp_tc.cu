@@ -233,6 +233,44 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], uint32
     }
 }
 
+// 16-column TMEM loads with the wait split off, so the load of the NEXT piece is in flight while the current one is
+// processed (tcgen05.wait::ld waits for every outstanding load of the thread: it is issued for piece i, then the load of
+// piece i+1, then piece i is processed).  The wait takes the destination registers as in/out operands so that no use of
+// them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+// One 16-column piece of a hidden layer's epilogue for one row (two 16-byte slots of the next layer's operand).
+template <bool kRelu>
+__device__ __forceinline__ void epilogue_piece(const uint32_t (&acc)[16], uint32_t bsrc, uint32_t dst0, uint32_t x0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        float4 b0, b1;
+        lds128(bsrc + 32u * q, b0);
+        lds128(bsrc + 32u * q + 16u, b1);
+        const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 0]), __uint_as_float(acc[8 * q + 1])), make_float2(b0.x, b0.y));
+        const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 2]), __uint_as_float(acc[8 * q + 3])), make_float2(b0.z, b0.w));
+        const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 4]), __uint_as_float(acc[8 * q + 5])), make_float2(b1.x, b1.y));
+        const float2 s3 = __fadd2_rn(make_float2(__uint_as_float(acc[8 * q + 6]), __uint_as_float(acc[8 * q + 7])), make_float2(b1.z, b1.w));
+        uint4 pk;
+        pk.x = cvt_bf16x2(s0.x, s0.y, kRelu); pk.y = cvt_bf16x2(s1.x, s1.y, kRelu);
+        pk.z = cvt_bf16x2(s2.x, s2.y, kRelu); pk.w = cvt_bf16x2(s3.x, s3.y, kRelu);
+        sts128(dst0 + (x0 ^ (uint32_t)(q << 4)), pk);
+    }
+}
+
 // byte offset of the 16-byte chunk holding elements [8*c8, 8*c8+8) of row r in a [rows x K] operand
 __device__ __forceinline__ uint32_t swz_chunk(int r, int c8, int rows) {
     const int kb = c8 >> 3, c = c8 & 7;
@@ -1011,21 +1049,48 @@ __device__ __forceinline__ void row_mlp_tc_body(const TcParams &p) {
                 // two warps per quarter alternate 32-column chunks; outputs that need the whole row in one thread (arg-max)
                 // or the warp-private staging (odd row pitch) stay with the first warp
                 const bool csplit = NHALF == 2 && (!last || (!p.out_argmax && ((cout * (p.out_bf16 ? 2 : 4)) & 15) == 0));
+                if (!last) {
+                    // hidden layer: bias (packed f32x2), ReLU folded into the bf16x2 conversion, 128-bit stores of the next
+                    // layer's operand, in 16-column pieces with the TMEM load of the next piece in flight.  Addresses are
+                    // 32-bit shared-window values: row base + k-block + the swizzled 16-byte slot, where
+                    // slot(c) = (c << 4) ^ ((r & 7) << 4) and c = (column / 8) mod 8.
+                    if ((csplit || half == 0) && (kMode == MODE_SA || npad < 128)) {
+                        // SA builds and narrow layers: one x32 load per chunk.  (The split loads below pay in the FP builds --
+                        // fp1+head 107 -> 103 us, fp4 35 -> 33, fp2 27 -> 25 -- and cost in the SA builds: sa1 71.7 -> 74.6 us,
+                        // sa2 35.3 -> 37.4, sa4 21 -> 23, also with this branch in place, so they are compiled out there.)
+                        for (int c0 = csplit ? 32 * half : 0; c0 < npad; c0 += csplit ? 64 : 32) {
+                            uint32_t acc[32];
+                            tmem_ld32(lane_base + (uint32_t)c0, acc);
+                            const uint32_t dst0 = a_row + (uint32_t)(c0 >> 6) * A_BLOCK_BYTES;
+                            const uint32_t x0 = ((uint32_t)((c0 >> 3) & 4) << 4) ^ r7s;
+                            const uint32_t bsrc = sbias_u32 + (uint32_t)(L.bias_off + c0) * 4u;
+                            if (relu) epilogue_chunk<true>(acc, bsrc, dst0, x0);
+                            else epilogue_chunk<false>(acc, bsrc, dst0, x0);
+                        }
+                    } else if (kMode != MODE_SA && (csplit || half == 0)) {
+                        const int step = csplit ? 64 : 32;
+                        int c0 = csplit ? 32 * half : 0;
+                        uint32_t pa[16], pb[16];
+                        if (c0 < npad) tmem_ld16_issue(lane_base + (uint32_t)c0, pa);
+                        for (; c0 < npad; c0 += step) {
+                            const uint32_t dst0 = a_row + (uint32_t)(c0 >> 6) * A_BLOCK_BYTES;
+                            const uint32_t xa = ((uint32_t)((c0 >> 3) & 4) << 4) ^ r7s, xb = xa ^ 0x20u;
+                            const uint32_t bsrc = sbias_u32 + (uint32_t)(L.bias_off + c0) * 4u;
+                            tmem_ld16_wait(pa);
+                            tmem_ld16_issue(lane_base + (uint32_t)(c0 + 16), pb);
+                            if (relu) epilogue_piece<true>(pa, bsrc, dst0, xa);
+                            else epilogue_piece<false>(pa, bsrc, dst0, xa);
+                            tmem_ld16_wait(pb);
+                            if (c0 + step < npad) tmem_ld16_issue(lane_base + (uint32_t)(c0 + step), pa);
+                            if (relu) epilogue_piece<true>(pb, bsrc + 64u, dst0, xb);
+                            else epilogue_piece<false>(pb, bsrc + 64u, dst0, xb);
+                        }
+                    }
+                } else
                 if (csplit || half == 0)
                 for (int c0 = csplit ? 32 * half : 0; c0 < npad; c0 += csplit ? 64 : 32) {
                     uint32_t acc[32];
                     tmem_ld32(lane_base + (uint32_t)c0, acc);
-                    if (!last) {
-                        // hidden layer: bias (packed f32x2), ReLU folded into the bf16x2 conversion, 128-bit stores of the
-                        // next layer's operand.  Addresses are 32-bit shared-window values: row base + k-block + the
-                        // swizzled 16-byte slot, where slot(c) = (c << 4) ^ ((r & 7) << 4) and c = 4 * (c0/32 & 1) + q.
-                        const uint32_t dst0 = a_row + (uint32_t)(c0 >> 6) * A_BLOCK_BYTES;
-                        const uint32_t x0 = (uint32_t)((c0 >> 3) & 4) << 4 ^ r7s;
-                        const uint32_t bsrc = sbias_u32 + (uint32_t)(L.bias_off + c0) * 4u;
-                        if (relu) epilogue_chunk<true>(acc, bsrc, dst0, x0);
-                        else epilogue_chunk<false>(acc, bsrc, dst0, x0);
-                        continue;
-                    }
                     float v[32];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
