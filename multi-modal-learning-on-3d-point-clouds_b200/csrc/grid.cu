@@ -386,19 +386,14 @@ __device__ __forceinline__ void best3_insert(Best3 &t, float d, int k) {
     }
 }
 
-__global__ void __launch_bounds__(128)
-three_nn_grid_kernel(int n, int m, const float *__restrict__ unknown_all, const float *__restrict__ known_all,
-                     const float4 *__restrict__ sorted_all, const int32_t *__restrict__ cell_start_all,
-                     const GridMeta *__restrict__ meta_all, const int32_t *__restrict__ query_order,
-                     float *__restrict__ dist2_out, int32_t *__restrict__ idx_out, float *__restrict__ weight_out) {
-    const int b = blockIdx.y;
-    const int slot = blockIdx.x * 128 + threadIdx.x;
-    if (slot >= n) return;
+// One query of the 3-NN search; `sorted` / `cell_start` point to the cloud's cell list in global OR shared memory
+// (three_nn_grid_staged_kernel copies small coarse clouds there first).
+__device__ __forceinline__ void three_nn_grid_query(int n, int m, int b, int slot, const GridMeta &g, const float *__restrict__ unknown_all,
+                                                    const float *__restrict__ known_all, const float4 *sorted, const int32_t *cell_start,
+                                                    const int32_t *__restrict__ query_order, float *__restrict__ dist2_out,
+                                                    int32_t *__restrict__ idx_out, float *__restrict__ weight_out) {
     // optional spatially coherent processing order (neighbouring threads then walk the same cells)
     const int i = query_order ? __ldg(query_order + (size_t)b * n + slot) : slot;
-    const GridMeta g = meta_all[b];
-    const float4 *sorted = sorted_all + (size_t)b * m;
-    const int32_t *cell_start = cell_start_all + (size_t)b * (GRID_MAX_CELLS + 1);
     const float *u = unknown_all + ((size_t)b * n + i) * 3;
     const float ux = u[0], uy = u[1], uz = u[2];
     const float h = 1.0f / g.inv_h;
@@ -421,9 +416,9 @@ three_nn_grid_kernel(int n, int m, const float *__restrict__ unknown_all, const 
         for (int zc = z0; zc <= z1; ++zc)
             for (int yc = y0; yc <= y1; ++yc) {
                 const int base = g.dx * (yc + g.dy * zc);
-                const int s = __ldg(cell_start + base + x0), e = __ldg(cell_start + base + x1 + 1);
+                const int s = cell_start[base + x0], e = cell_start[base + x1 + 1];
                 for (int p = s; p < e; ++p) {
-                    const float4 v = __ldg(sorted + p);
+                    const float4 v = sorted[p];
                     best3_insert(t, dist_ref(ux, uy, uz, v.x, v.y, v.z), __float_as_int(v.w));
                 }
             }
@@ -470,6 +465,49 @@ three_nn_grid_kernel(int n, int m, const float *__restrict__ unknown_all, const 
         const float s = __fadd_rn(__fadd_rn(w1, w2), w3);
         weight_out[o] = __fdiv_rn(w1, s); weight_out[o + 1] = __fdiv_rn(w2, s); weight_out[o + 2] = __fdiv_rn(w3, s);
     }
+}
+
+
+__global__ void __launch_bounds__(128)
+three_nn_grid_kernel(int n, int m, const float *__restrict__ unknown_all, const float *__restrict__ known_all,
+                     const float4 *__restrict__ sorted_all, const int32_t *__restrict__ cell_start_all,
+                     const GridMeta *__restrict__ meta_all, const int32_t *__restrict__ query_order,
+                     float *__restrict__ dist2_out, int32_t *__restrict__ idx_out, float *__restrict__ weight_out) {
+    const int b = blockIdx.y;
+    const int slot = blockIdx.x * 128 + threadIdx.x;
+    if (slot >= n) return;
+    const GridMeta g = meta_all[b];
+    three_nn_grid_query(n, m, b, slot, g, unknown_all, known_all, sorted_all + (size_t)b * m,
+                        cell_start_all + (size_t)b * (GRID_MAX_CELLS + 1), query_order, dist2_out, idx_out, weight_out);
+}
+
+// Small coarse clouds (m <= TNS_MAX_M: the 1024 / 256 / 64-point levels of the semseg stacks): the CTA copies the cloud's
+// sorted points and -- when the grid has at most TNS_MAX_CELLS cells -- its cell-start table into shared memory once
+// and its 512 queries search there; every cell-table and candidate read is then a shared-memory load instead of a
+// dependent L1 / L2 access (a query makes ~18 table reads and ~30 candidate reads in a chain).
+constexpr int TNS_THREADS = 512, TNS_MAX_M = 2048, TNS_MAX_CELLS = 8192;
+
+__global__ void __launch_bounds__(TNS_THREADS)
+three_nn_grid_staged_kernel(int n, int m, const float *__restrict__ unknown_all, const float *__restrict__ known_all,
+                            const float4 *__restrict__ sorted_all, const int32_t *__restrict__ cell_start_all,
+                            const GridMeta *__restrict__ meta_all, const int32_t *__restrict__ query_order,
+                            float *__restrict__ dist2_out, int32_t *__restrict__ idx_out, float *__restrict__ weight_out) {
+    extern __shared__ __align__(16) unsigned char tns_smem[];
+    float4 *s_sorted = reinterpret_cast<float4 *>(tns_smem);
+    int32_t *s_cells = reinterpret_cast<int32_t *>(s_sorted + m);
+    const int b = blockIdx.y;
+    const GridMeta g = meta_all[b];
+    const float4 *sorted = sorted_all + (size_t)b * m;
+    const int32_t *cell_start = cell_start_all + (size_t)b * (GRID_MAX_CELLS + 1);
+    for (int e = threadIdx.x; e < m; e += TNS_THREADS) s_sorted[e] = __ldg(sorted + e);
+    const bool cells_fit = g.ncells <= TNS_MAX_CELLS;  // uniform over the CTA
+    if (cells_fit)
+        for (int e = threadIdx.x; e <= g.ncells; e += TNS_THREADS) s_cells[e] = __ldg(cell_start + e);
+    __syncthreads();
+    const int slot = blockIdx.x * TNS_THREADS + threadIdx.x;
+    if (slot >= n) return;
+    three_nn_grid_query(n, m, b, slot, g, unknown_all, known_all, s_sorted, cells_fit ? s_cells : cell_start, query_order, dist2_out,
+                        idx_out, weight_out);
 }
 
 }  // namespace
@@ -544,6 +582,15 @@ extern "C" int pn2_three_nn_grid(int b, int n, int m, const float *unknown, cons
     if (b == 0 || n == 0) return PN2_OK;
     PN2_REQUIRE(unknown && known && sorted && cell_start && meta && idx, "three_nn_grid: null pointer");
     PN2_REQUIRE(b <= 65535, "three_nn_grid: b exceeds the grid limit");
+    if (m <= TNS_MAX_M && n >= 2 * TNS_THREADS) {
+        const size_t smem = (size_t)m * sizeof(float4) + (size_t)(TNS_MAX_CELLS + 1) * sizeof(int32_t);
+        PN2_CUDA(cudaFuncSetAttribute(three_nn_grid_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        three_nn_grid_staged_kernel<<<dim3(ceil_div(n, TNS_THREADS), b), TNS_THREADS, smem, (cudaStream_t)stream>>>(
+            n, m, unknown, known, reinterpret_cast<const float4 *>(sorted), cell_start, reinterpret_cast<const GridMeta *>(meta), query_order,
+            dist2, idx, weight);
+        PN2_LAUNCH_OK("three_nn_grid_staged");
+        return PN2_OK;
+    }
     dim3 grid(ceil_div(n, 128), b);
     three_nn_grid_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n, m, unknown, known, reinterpret_cast<const float4 *>(sorted),
                                                                 cell_start, reinterpret_cast<const GridMeta *>(meta), query_order,
