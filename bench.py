@@ -308,7 +308,7 @@ def time_other_configs(device, B):
     return out
 
 
-def ncu_traffic(kernel_substr="row_mlp_tc_kernel_bf16(", grid=None):
+def ncu_traffic(kernel_substr="row_mlp_tc_kernel_bf16_fp(", grid=None):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` summary of this
     round (profiles/r2_tc_mlp_ncu_full_summary.csv, written by scripts/summarize_ncu_full.py from the .ncu-rep): the LAST
     matching launch of one forward (fp1 + head).  Returns (bytes or None, file name)."""
