@@ -30,9 +30,11 @@ struct ViewParams {  // 38 floats per view, staged in shared memory
     float nrm[18];
 };
 
-__device__ __forceinline__ int project_point(float px, float py, float pz, const ViewParams &vp, float fx, float fy,
-                                             float cx, float cy, int W, int H, const float *__restrict__ depth,
-                                             float dmin, float dmax, float acc) {
+// Geometry half of the per-(point, view) test: frustum planes, projection, nearest pixel.  Returns the pixel or -1 and the
+// camera-space depth; the depth-map test (project_depth_ok) needs one dependent random load and is kept apart so that a
+// caller can put the loads of all views in flight before the first comparison.
+__device__ __forceinline__ int project_pixel(float px, float py, float pz, const ViewParams &vp, float fx, float fy, float cx,
+                                             float cy, int W, int H, float &cam_z) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         const float *c = k < 3 ? vp.c2 : vp.c4;
@@ -53,10 +55,19 @@ __device__ __forceinline__ int project_point(float px, float py, float pz, const
     const float v = __fadd_rn(__fdiv_rn(__fmul_rn(cam[1], fy), cam[2]), cy);
     const float ur = rintf(u), vr = rintf(v);
     if (!(ur >= 0.0f && vr >= 0.0f && ur < (float)W && vr < (float)H)) return -1;
-    const int pix = (int)vr * W + (int)ur;
-    const float z = __ldg(depth + pix);
-    if (!(z >= dmin && z <= dmax && fabsf(__fsub_rn(z, cam[2])) <= acc)) return -1;
-    return pix;
+    cam_z = cam[2];
+    return (int)vr * W + (int)ur;
+}
+__device__ __forceinline__ bool project_depth_ok(float z, float cam_z, float dmin, float dmax, float acc) {
+    return z >= dmin && z <= dmax && fabsf(__fsub_rn(z, cam_z)) <= acc;
+}
+__device__ __forceinline__ int project_point(float px, float py, float pz, const ViewParams &vp, float fx, float fy,
+                                             float cx, float cy, int W, int H, const float *__restrict__ depth,
+                                             float dmin, float dmax, float acc) {
+    float cam_z = 0.f;
+    const int pix = project_pixel(px, py, pz, vp, fx, fy, cx, cy, W, H, cam_z);
+    if (pix < 0) return -1;
+    return project_depth_ok(__ldg(depth + pix), cam_z, dmin, dmax, acc) ? pix : -1;
 }
 
 __global__ void __launch_bounds__(LV_THREADS)
@@ -238,7 +249,7 @@ lift_nonzero_kernel(int c, int hw, const float *__restrict__ feats, unsigned cha
     nz[bv * hw + px] = any ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(LV_THREADS)
+__global__ void __launch_bounds__(LV_THREADS, 8)  // 64 registers: the dependent round trip per point is hidden by resident warps
 lift_project_kernel(int n, int nv, int h, int w, const float *__restrict__ points, const float *__restrict__ depth,
                     const float *__restrict__ w2c, const float *__restrict__ corner2, const float *__restrict__ corner4,
                     const float *__restrict__ normals, const float *__restrict__ c2w, CamCorners cam, float fx, float fy, float cx,
@@ -270,21 +281,47 @@ lift_project_kernel(int n, int nv, int h, int w, const float *__restrict__ point
     }
     __syncthreads();
     const int i = blockIdx.x * LV_THREADS + threadIdx.x;
-    if (i < n) {
+    const bool live = i < n;
+    // phase 1: geometry of every view; phase 2: the depth values of all candidate pixels are loaded together (one
+    // dependent round trip per point instead of one per view -- the kernel is bound by that latency: ncu showed the depth
+    // comparison as its largest stall); phase 3: depth tests, outputs
+    int cand[LV_MAXV];
+    float camz[LV_MAXV], zv[LV_MAXV];
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (live) {
         const float *p = points + ((size_t)b * n + i) * 3;
-        const float px = p[0], py = p[1], pz = p[2];
-        int chosen = -1;
-        for (int v = 0; v < nv; ++v) {
+        px = p[0]; py = p[1]; pz = p[2];
+    }
+#pragma unroll
+    for (int v = 0; v < LV_MAXV; ++v) {
+        cand[v] = -1;
+        camz[v] = 0.f;
+        if (v < nv && live) cand[v] = project_pixel(px, py, pz, vps[v], fx, fy, cx, cy, w, h, camz[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < LV_MAXV; ++v) {
+        zv[v] = 0.f;
+        if (v < nv && cand[v] >= 0) zv[v] = __ldg(depth + ((size_t)b * nv + v) * hw + cand[v]);
+    }
+    int chosen = -1;
+#pragma unroll
+    for (int v = 0; v < LV_MAXV; ++v) {
+        if (v < nv) {
             const size_t bv = (size_t)b * nv + v;
-            const int pix = project_point(px, py, pz, vps[v], fx, fy, cx, cy, w, h, depth + bv * hw, dmin, dmax, acc);
-            if (pix_out) pix_out[bv * n + i] = pix;
-            if (pix16) pix16[bv * n + i] = (int16_t)pix;  // what the gather kernel reads: half the index traffic (hw < 32768)
-            if (count && pix >= 0) atomicAdd(&vcount[v], 1);
+            const int pix = (cand[v] >= 0 && project_depth_ok(zv[v], camz[v], dmin, dmax, acc)) ? cand[v] : -1;
+            if (live) {
+                if (pix_out) pix_out[bv * n + i] = pix;
+                if (pix16) pix16[bv * n + i] = (int16_t)pix;  // what the gather kernel reads: half the index traffic (hw < 32768)
+            }
+            if (count) {  // one shared-memory atomic per warp and view
+                const unsigned m = __ballot_sync(0xffffffffu, pix >= 0);
+                if ((threadIdx.x & 31) == 0 && m) atomicAdd(&vcount[v], __popc(m));
+            }
             // first view, then only views that fill an all-zero column (model/pointnet2multiview.py:93-98)
             if (sel && chosen < 0 && pix >= 0 && nz[bv * hw + pix]) chosen = v;
         }
-        if (sel) sel[(size_t)b * n + i] = (signed char)chosen;
     }
+    if (live && sel) sel[(size_t)b * n + i] = (signed char)chosen;
     if (count) {
         __syncthreads();
         if (threadIdx.x < nv && vcount[threadIdx.x]) atomicAdd(count + (size_t)b * nv + threadIdx.x, vcount[threadIdx.x]);
