@@ -17,7 +17,7 @@
 namespace pn2 {
 namespace {
 
-constexpr int LV_THREADS = 128;
+constexpr int LV_THREADS = 256;
 constexpr int LV_MAXV = 8;
 
 struct CamCorners {
@@ -249,7 +249,7 @@ lift_nonzero_kernel(int c, int hw, const float *__restrict__ feats, unsigned cha
     nz[bv * hw + px] = any ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(LV_THREADS, 8)  // 64 registers: the dependent round trip per point is hidden by resident warps
+__global__ void __launch_bounds__(LV_THREADS, 4)  // 64 registers: the dependent round trip per point is hidden by resident warps
 lift_project_kernel(int n, int nv, int h, int w, const float *__restrict__ points, const float *__restrict__ depth,
                     const float *__restrict__ w2c, const float *__restrict__ corner2, const float *__restrict__ corner4,
                     const float *__restrict__ normals, const float *__restrict__ c2w, CamCorners cam, float fx, float fy, float cx,
