@@ -530,6 +530,36 @@ class PipelinedForward:
             torch.cuda.current_stream().wait_stream(st)
 
 
+class GraphedViews:
+    """CUDA-graph replay of `forward_views` (multi-view lifting + point branch, model/pointnet2multiview.py:83-121) for
+    fixed shapes: projection, slab gather and the ~30 launches of the point branch become one graph launch.  `run(...)`
+    copies the inputs (device or pinned host) into the static buffers and returns the static logits (valid until the next
+    run).  Several instances on several streams overlap consecutive batches like PipelinedForward."""
+
+    def __init__(self, model, xyz, feats, depth, poses, intrinsic, depth_min, depth_max, image_dims, accuracy, warmup=3):
+        self.model = model
+        self.xyz, self.feats, self.depth, self.poses = xyz.clone(), feats.clone(), depth.clone(), poses.clone()
+        self.args = (intrinsic, depth_min, depth_max, image_dims, accuracy)
+        side = torch.cuda.Stream(xyz.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                model.forward_views(self.xyz, self.feats, self.depth, self.poses, *self.args)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = model.forward_views(self.xyz, self.feats, self.depth, self.poses, *self.args)
+
+    def run(self, xyz, feats, depth, poses):
+        self.xyz.copy_(xyz, non_blocking=True)
+        self.feats.copy_(feats, non_blocking=True)
+        self.depth.copy_(depth, non_blocking=True)
+        self.poses.copy_(poses, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 class GraphedTrainStep:
     """One training step -- zero the gradients, forward, loss, backward, optimizer update -- replayed as CUDA graphs for a
     fixed batch shape (the reference's loop: train_scannet_semseg.py:135-146).  An eager MSG step issues ~1500 launches

@@ -270,3 +270,32 @@ def test_frustum_counts_and_best_views(cuda):
     if (got == want).all():
         assert views == gold["frustum/best5"].tolist()
     assert views[0] == int(np.argmax(got))
+
+
+def test_graphed_views_reproduce_the_eager_call(cuda):
+    """GraphedViews (lifting + point branch as one CUDA graph) returns what the eager forward_views returns, also after
+    new inputs are copied into its static buffers."""
+    from pn2_b200 import pointnet_util
+    from pn2_b200.models import GraphedViews, PointNet2Multiview2
+    B, N, V = 2, 2048, 3
+    prev = pointnet_util.set_mlp_precision("bf16")
+    try:
+        torch.manual_seed(1)
+        net = PointNet2Multiview2(21).eval().to(cuda)
+        args = (scenes.SCANNET_INTRINSIC, 0.1, 4.0, scenes.SCANNET_IMAGE_DIMS, 0.05)
+
+        def inputs(seed):
+            pts = scenes.scannet_batch(seed, B, N)[:, :, :3].astype(np.float32)
+            mv = [scenes.multiview_inputs(seed + b, pts[b], V, 128) for b in range(B)]
+            return (torch.from_numpy(pts).to(cuda).permute(0, 2, 1).contiguous(), torch.from_numpy(np.stack([m[0] for m in mv])).to(cuda),
+                    torch.from_numpy(np.stack([m[1] for m in mv])).to(cuda), torch.from_numpy(np.stack([m[2] for m in mv]).astype(np.float32)).to(cuda))
+
+        a, b = inputs(40), inputs(50)
+        g = GraphedViews(net, *a, *args)
+        with torch.no_grad():
+            for x in (a, b, a):
+                want = net.forward_views(*x, *args)
+                got = g.run(*x).clone()
+                assert torch.equal(got, want)
+    finally:
+        pointnet_util.set_mlp_precision(prev)
