@@ -575,20 +575,14 @@ class GraphedTrainStep:
     """
 
     def __init__(self, net, opt, loss_fn, example_xyz, example_feats, example_target, group=None, warmup=3):
-        import torch.distributed as dist
+        from .sharding import FlatGradients
         self.net, self.opt, self.loss_fn = net, opt, loss_fn
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        self.group = group
         for g in opt.param_groups:
             if not g.get("capturable", False):
                 raise ValueError("GraphedTrainStep needs an optimizer built with capturable=True (its step counter lives on the device)")
         self.xyz, self.feats, self.target = example_xyz.clone(), example_feats.clone(), example_target.clone()
-        params = [p for p in net.parameters() if p.requires_grad]
-        self.flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=example_xyz.device)
-        off = 0
-        for p in params:  # gradients accumulate in place into views of the flat buffer
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.grads = FlatGradients(net.parameters(), group)  # gradients accumulate in place into views of one flat buffer
+        self.world = self.grads.world
         dev = example_xyz.device
         # the warm-up steps below are real updates: model and optimizer are put back afterwards (in place, because the
         # graphs capture the addresses of the parameters and of the optimizer state)
@@ -622,16 +616,13 @@ class GraphedTrainStep:
                 opt.step()
 
     def _fwd_bwd(self):
-        self.flat.zero_()
+        self.grads.zero()
         loss = self.loss_fn(self.net(self.xyz, self.feats), self.target)
         loss.backward()
         return loss.detach()
 
     def _reduce(self):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat, group=self.group)
-            self.flat.div_(self.world)
+        self.grads.all_reduce_mean()
 
     def step(self, xyz, feats, target):
         self.xyz.copy_(xyz, non_blocking=True)

@@ -16,7 +16,7 @@ from pn2_b200.models import PointNet2SemSeg  # noqa: E402
 
 dev = torch.device("cuda:0")
 B = int(os.environ.get("B", "32"))
-ITERS = int(os.environ.get("ITERS", "30"))
+ITERS = int(os.environ.get("ITERS", "30" if os.environ.get("PRECISION", "bf16") == "bf16" else "8"))
 torch.manual_seed(0)
 model = PointNet2SemSeg(21).eval().to(dev)
 model.single_stream = True
@@ -29,7 +29,8 @@ if os.environ.get("TC_MAX_CTAS"):
     lib.pn2_debug_set_tc_max_ctas(int(os.environ["TC_MAX_CTAS"]))
 if os.environ.get("TC_WORKERS"):
     lib.pn2_debug_set_tc_workers(int(os.environ["TC_WORKERS"]))
-TC = ("pn2_sa_mlp_max_bf16", "pn2_fp_mlp_bf16")
+PREC = os.environ.get("PRECISION", "bf16")  # fp32: times the FFMA kernels of row_mlp.cu instead
+TC = ("pn2_sa_mlp_max_bf16", "pn2_fp_mlp_bf16") if PREC == "bf16" else ("pn2_sa_mlp_max", "pn2_fp_mlp")
 NAMES = ["sa1", "sa2", "sa3", "sa4", "fp4", "fp3", "fp2", "fp1+head"]
 orig_call = _lib.call
 rec = []
@@ -51,8 +52,8 @@ U._lib.call = hooked
 with torch.no_grad():
     U.set_mlp_precision("fp32")
     want = model(x6[:, :3], x6[:, 3:]).float()
-    U.set_mlp_precision("bf16")
-    for _ in range(25):  # clocks and caches settle (the first process on a fresh box reads ~10 % slow otherwise)
+    U.set_mlp_precision(PREC)
+    for _ in range(25 if PREC == "bf16" else 5):  # clocks and caches settle (the first process on a fresh box reads ~10 % slow otherwise)
         got = model(x6[:, :3], x6[:, 3:])
     torch.cuda.synchronize()
     rec.clear()

@@ -52,3 +52,51 @@ def test_sharding_single_process_is_identity():
     assert sharding.scene_ids_for_rank(5, 0, 1) == [0, 1, 2, 3, 4]
     t = torch.tensor([3.0])
     assert float(sharding.max_over_ranks(t)) == 3.0
+
+
+def _grad_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "multi-modal-learning-on-3d-point-clouds_b200"))
+    from pn2_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)  # replicated weights
+    net = torch.nn.Sequential(torch.nn.Conv1d(6, 8, 1), torch.nn.ReLU(), torch.nn.Conv1d(8, 3, 1))
+    grads = sharding.FlatGradients(net.parameters())
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(100 + rank)  # every rank its own shard of scenes
+    local, after = [], None
+    for step in range(2):
+        x = torch.randn(4, 6, 32, generator=g)
+        grads.zero()
+        net(x).square().mean().backward()  # accumulates in place into the views of the flat buffer
+        local.append(grads.flat.clone())
+        grads.all_reduce_mean()
+        if step == 0:
+            after = grads.flat.clone()
+        opt.step()
+    q.put((rank, [t.numpy() for t in local], after.numpy(), torch.cat([p.detach().reshape(-1) for p in net.parameters()]).numpy(),
+           [p.grad.data_ptr() == grads.flat[o:o + 1].data_ptr() for p, o in zip(grads.params, np.cumsum([0] + [p.numel() for p in grads.params])[:-1])]))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_all_reduce_two_ranks_gloo():
+    """Training exchange: the gradients of all parameters live in one flat buffer that is averaged by ONE
+    all-reduce per step; afterwards both ranks hold the mean of the per-rank gradients and identical weights."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, loc0, after0, w0, views0), (_, loc1, after1, w1, views1) = res
+    assert all(views0) and all(views1)                                  # .grad tensors are views into the flat buffer
+    assert not np.array_equal(loc0[0], loc1[0])                         # different shards, different local gradients
+    np.testing.assert_allclose(after0, (loc0[0] + loc1[0]) / 2, rtol=0, atol=1e-7)
+    np.testing.assert_array_equal(after0, after1)                       # both ranks hold the same averaged gradient
+    np.testing.assert_array_equal(w0, w1)                               # and stay in lock-step after two updates
