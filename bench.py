@@ -106,10 +106,10 @@ def build_model(device):
 
 def host_batches(rank, batch, count):
     """`count` distinct pinned host batches in the loader's layout (B, N, 6) [xyz | rgb]."""
-    from pn2_b200 import scenes
+    from pn2_b200 import scenes, sharding
     out = []
     for i in range(count):
-        a = torch.from_numpy(scenes.scannet_batch(100000 * rank + i * batch, batch, NPOINTS))
+        a = torch.from_numpy(scenes.scannet_batch(sharding.weak_scene_ids(rank, batch, i)[0], batch, NPOINTS))
         out.append(a.pin_memory() if torch.cuda.is_available() else a)
     return out
 
@@ -439,6 +439,7 @@ def run_ours(args):
     from pn2_b200 import _lib
     from pn2_b200 import pointnet_util as _pu
     from pn2_b200 import scenes as _scenes
+    from pn2_b200 import sharding
     from pn2_b200.models import GraphedForward, PipelinedForward
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -461,7 +462,7 @@ def run_ours(args):
     # rotating inputs: 24 distinct batches = 151 MB of input (+ the activations they produce) > the 126 MB L2
     n_rot = 24
     hosts = host_batches(rank, B, 8)
-    devs = [torch.from_numpy(_scenes.scannet_batch(100000 * rank + 1000 + i * B, B, NPOINTS)).to(device).permute(0, 2, 1).contiguous()
+    devs = [torch.from_numpy(_scenes.scannet_batch(sharding.weak_scene_ids(rank, B, i)[0] + 1000, B, NPOINTS)).to(device).permute(0, 2, 1).contiguous()
             for i in range(n_rot)]  # (B, 6, N) resident, as the train script feeds it
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
 
