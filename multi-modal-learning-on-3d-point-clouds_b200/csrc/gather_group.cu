@@ -37,11 +37,13 @@ gather_rows_kernel(int c, int n, long long J, const float *__restrict__ points, 
 }
 
 // Shared-memory variant for long index lists (grouping: J = npoints*nsample >> N).  A CTA stages CC whole source
-// rows (CC * N floats, coalesced float4 copies) and then streams the index list once: every random access is an
-// LDS, HBM sees only the compulsory bytes (source rows once, indices, coalesced output).
-constexpr int GS_THREADS = 512;
-
-__global__ void __launch_bounds__(GS_THREADS, 1)
+// rows (CC * N floats, 16-byte asynchronous copies, all in flight) and then streams the index list once: every random
+// access is an LDS, HBM sees only the compulsory bytes (source rows once, indices, coalesced output).
+// The index loads are the only long-latency step of the streaming loop, and with few staged rows (long rows: N >= 16 k
+// leaves room for one to three) there is little work per index to hide them behind: the loop keeps the NEXT iteration's
+// U index vectors in flight while the current ones are expanded, and CTAs that stage at most two rows run 1024 threads.
+template <int THREADS, int U>
+__global__ void __launch_bounds__(THREADS, 1)
 gather_rows_smem_kernel(int c, int n, long long J, int cc, const float *__restrict__ points, const int32_t *__restrict__ idx,
                         float *__restrict__ out) {
     extern __shared__ __align__(16) float rows[];  // [cc][n]
@@ -51,40 +53,53 @@ gather_rows_smem_kernel(int c, int n, long long J, int cc, const float *__restri
     const float *src = points + ((size_t)b * c + c0) * n;
     const long long total = (long long)nc * n;
     if (((uintptr_t)src & 15) == 0 && (total & 3) == 0) {
-        const float4 *s4 = reinterpret_cast<const float4 *>(src);
-        float4 *d4 = reinterpret_cast<float4 *>(rows);
-        for (long long e = threadIdx.x; e < total / 4; e += GS_THREADS) d4[e] = __ldcs(s4 + e);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(rows);
+        for (long long e = threadIdx.x; e < total / 4; e += THREADS)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)e * 16u), "l"(src + 4 * e) : "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
-        for (long long e = threadIdx.x; e < total; e += GS_THREADS) rows[e] = __ldcs(src + e);
+        for (long long e = threadIdx.x; e < total; e += THREADS) rows[e] = __ldcs(src + e);
     }
     __syncthreads();
     const int32_t *ib = idx + (size_t)b * J;
     float *ob = out + ((size_t)b * c + c0) * J;
     if ((J & 3) == 0 && ((uintptr_t)ib & 15) == 0 && ((uintptr_t)ob & 15) == 0) {
-        // four consecutive outputs per thread: one 128-bit index load, nc x (4 LDS + one 128-bit streaming store),
-        // two such groups in flight per iteration
+        // four consecutive outputs per thread and vector: one 128-bit index load, nc x (4 LDS + one 128-bit streaming
+        // store); U vectors per iteration, the next iteration's U index loads issued before the current ones are used
         const long long J4 = J / 4;
         const long long per = (J4 + gridDim.x - 1) / gridDim.x;
         const long long q0 = (long long)blockIdx.x * per, q1 = min(J4, q0 + per);
         const int4 *ib4 = reinterpret_cast<const int4 *>(ib);
-        for (long long q = q0 + threadIdx.x; q < q1; q += 2 * GS_THREADS) {
-            const long long qb = q + GS_THREADS;
-            const bool two = qb < q1;
-            const int4 ka = __ldcs(ib4 + q);
-            int4 kb = ka;
-            if (two) kb = __ldcs(ib4 + qb);
+        int4 k[U], kn[U];
+        long long q = q0 + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            k[u] = make_int4(0, 0, 0, 0);
+            if (q + (long long)u * THREADS < q1) k[u] = __ldcs(ib4 + q + (long long)u * THREADS);
+        }
+        for (; q < q1; q += (long long)U * THREADS) {
+            const long long qn = q + (long long)U * THREADS;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                kn[u] = make_int4(0, 0, 0, 0);
+                if (qn + (long long)u * THREADS < q1) kn[u] = __ldcs(ib4 + qn + (long long)u * THREADS);
+            }
             for (int i = 0; i < nc; ++i) {
                 const float *r = rows + (size_t)i * n;
                 float4 *dst = reinterpret_cast<float4 *>(ob + (size_t)i * J);
-                __stcs(dst + q, make_float4(r[ka.x], r[ka.y], r[ka.z], r[ka.w]));
-                if (two) __stcs(dst + qb, make_float4(r[kb.x], r[kb.y], r[kb.z], r[kb.w]));
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (q + (long long)u * THREADS < q1)
+                        __stcs(dst + q + (long long)u * THREADS, make_float4(r[k[u].x], r[k[u].y], r[k[u].z], r[k[u].w]));
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u) k[u] = kn[u];
         }
         return;
     }
     const long long per = (J + gridDim.x - 1) / gridDim.x;
     const long long j0 = (long long)blockIdx.x * per, j1 = min(J, j0 + per);
-    for (long long j = j0 + threadIdx.x; j < j1; j += GS_THREADS) {
+    for (long long j = j0 + threadIdx.x; j < j1; j += THREADS) {
         const int k = __ldcs(ib + j);
         for (int i = 0; i < nc; ++i) __stcs(ob + (size_t)i * J + j, rows[(size_t)i * n + k]);
     }
@@ -186,9 +201,16 @@ int gather_rows(const char *op, int b, int c, int n, long long J, const float *p
         int jsplit = 1;
         while ((long long)jsplit * chunks * b < 2ll * sm_count() && J / (jsplit * 2) >= 8 * n) jsplit *= 2;
         const size_t smem = (size_t)cc * n * sizeof(float);
-        PN2_CUDA(cudaFuncSetAttribute(gather_rows_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(jsplit, chunks, b);
-        gather_rows_smem_kernel<<<grid, GS_THREADS, smem, (cudaStream_t)stream>>>(c, n, J, cc, points, idx, out);
+        if (cc <= 2) {
+            auto kern = gather_rows_smem_kernel<1024, 2>;
+            PN2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, 1024, smem, (cudaStream_t)stream>>>(c, n, J, cc, points, idx, out);
+        } else {
+            auto kern = gather_rows_smem_kernel<512, 2>;
+            PN2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, 512, smem, (cudaStream_t)stream>>>(c, n, J, cc, points, idx, out);
+        }
         PN2_LAUNCH_OK(op);
         return PN2_OK;
     }

@@ -139,19 +139,21 @@ __global__ void __launch_bounds__(RM_THREADS, 1) row_mlp_kernel(const __grid_con
     constexpr int TRP = TR + 4;
     // shared memory layout: [ping: buf_a_floats][pong: buf_b_floats][weight tiles: 2*KC*WSP]
     extern __shared__ __align__(16) float smem[];
-    float *buf[2] = {smem, smem + p.buf_a_floats};
-    float *ws = buf[1] + p.buf_b_floats;
+    // (the ping / pong pointers are computed as offsets from `smem`, not picked from a pointer array: an indexed
+    // array of pointers lives in local memory and hides the address space, and every activation access of the layer
+    // tiles became a generic LD.E / ST.E instead of LDS / STS)
+    float *ws = smem + p.buf_a_floats + p.buf_b_floats;
     const long long tile = blockIdx.x;
 
     if (p.mode == MODE_SA)
-        gather_sa<TR>(p, buf[0], tile);
+        gather_sa<TR>(p, smem, tile);
     else
-        gather_fp<TR>(p, buf[0], tile);
+        gather_fp<TR>(p, smem, tile);
     __syncthreads();
 
     for (int l = 0; l < p.num_layers; ++l) {
-        const float *xin = buf[l & 1];
-        float *xout = buf[(l + 1) & 1];
+        const float *xin = smem + ((l & 1) ? p.buf_a_floats : 0);
+        float *xout = smem + ((l & 1) ? 0 : p.buf_a_floats);
         const bool last = (l == p.num_layers - 1);
         const int cin = p.cin[l], cout = p.cout[l];
         const int nt = pick_nt(cout, TR);

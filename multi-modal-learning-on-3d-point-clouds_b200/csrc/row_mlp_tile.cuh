@@ -31,9 +31,12 @@ __device__ __forceinline__ void layer_tile(const float *__restrict__ xin, float 
     const int tid = threadIdx.x;
     const int tx = tid % TXN, ty = tid / TXN;
 
-    // staging coordinates: smem position p <-> logical column (p / TN) + TXN * (p % TN)
+    // staging coordinates: smem position p <-> logical column.  A thread's TN columns are tx + TXN * j; they sit in
+    // groups of four so that the lanes of a quarter warp read CONSECUTIVE 16-byte slots (p = (j / 4) * 4 TXN + 4 tx + j % 4):
+    // with the eight columns of a thread contiguous, lanes 32 bytes apart met two to a bank group on every 128-bit load.
     const int sp = tid % NT, sg = tid / NT;
-    const int scol = n0 + (sp / TN) + TXN * (sp % TN);
+    constexpr int GW = TN >= 4 ? 4 : TN;  // columns of one thread that are contiguous in the tile
+    const int scol = n0 + ((sp % (TXN * GW)) / GW) + TXN * (GW * (sp / (TXN * GW)) + sp % GW);
     const float *wrow = W + (size_t)scol * cin;
     const bool col_ok = scol < cout;
 
@@ -46,11 +49,27 @@ __device__ __forceinline__ void layer_tile(const float *__restrict__ xin, float 
     float wreg[EPT];
     const int nchunks = (cin + KC - 1) / KC;
     // prologue: stage chunk 0
+    // a thread's EPT weights are consecutive k of one column: 128-bit loads when the rows allow it (a scalar load per
+    // element costs a 32-byte sector request per lane -- the columns of a warp are cin floats apart)
+    const bool wvec = (EPT % 4 == 0) && (cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    auto load_chunk = [&](int k0) {
+        if (wvec) {
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        const int k = sg * EPT + e;
-        wreg[e] = (col_ok && k < cin) ? __ldg(wrow + k) : 0.f;
-    }
+            for (int e = 0; e < EPT; e += 4) {
+                const int k = k0 + sg * EPT + e;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col_ok && k < cin) v = __ldg(reinterpret_cast<const float4 *>(wrow + k));
+                wreg[e] = v.x; wreg[e + 1] = v.y; wreg[e + 2] = v.z; wreg[e + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int k = k0 + sg * EPT + e;
+                wreg[e] = (col_ok && k < cin) ? __ldg(wrow + k) : 0.f;
+            }
+        }
+    };
+    load_chunk(0);
 #pragma unroll
     for (int e = 0; e < EPT; ++e) ws[(sg * EPT + e) * WSP + sp] = wreg[e];
     __syncthreads();
@@ -59,13 +78,7 @@ __device__ __forceinline__ void layer_tile(const float *__restrict__ xin, float 
         float *wcur = ws + (c & 1) * (KC * WSP);
         float *wnxt = ws + ((c + 1) & 1) * (KC * WSP);
         const bool more = (c + 1) < nchunks;
-        if (more) {
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) {
-                const int k = (c + 1) * KC + sg * EPT + e;
-                wreg[e] = (col_ok && k < cin) ? __ldg(wrow + k) : 0.f;
-            }
-        }
+        if (more) load_chunk((c + 1) * KC);
         const float *xa = xin + (size_t)(c * KC) * TRP + ty * TM;
         const int kk_end = min(KC, cin - c * KC);
 #pragma unroll 4
@@ -76,11 +89,11 @@ __device__ __forceinline__ void layer_tile(const float *__restrict__ xin, float 
                 const float4 v = *reinterpret_cast<const float4 *>(xa + kk * TRP + i);
                 a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
             }
-            const float *wb = wcur + kk * WSP + tx * TN;
+            const float *wb = wcur + kk * WSP + tx * GW;
             if constexpr (TN >= 4) {
 #pragma unroll
                 for (int j = 0; j < TN; j += 4) {
-                    const float4 v = *reinterpret_cast<const float4 *>(wb + j);
+                    const float4 v = *reinterpret_cast<const float4 *>(wb + j * TXN);
                     b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
                 }
             } else if constexpr (TN == 2) {
