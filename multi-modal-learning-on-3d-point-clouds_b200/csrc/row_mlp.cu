@@ -18,6 +18,8 @@
 // BatchNorm is folded into (W, bias) by the caller (eval mode), see pn2_b200/pointnet_util.py.
 //
 // fp32 FFMA throughout (the 1e-5 parity path).  The bf16 tcgen05 variant lives in row_mlp_tc.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "row_mlp_tile.cuh"
 
@@ -74,21 +76,29 @@ __device__ __forceinline__ void gather_sa(const RowMlpParams &p, float *x0, long
             x0[(size_t)c * TRP + r] = v;
         }
     } else {
-        // wide rows: one warp per row, lanes along the (contiguous, channel-last) feature row
+        // wide rows: one warp per row, lanes along the (contiguous, channel-last) feature row.  Lane i first loads the
+        // sample index of row warp + NW * i (one round trip for the warp's rows); the row loop gets it by shuffle
+        constexpr int NW = RM_THREADS / 32, RPW = TR / NW;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int r = warp; r < TR; r += RM_THREADS / 32) {
+        long long m_src = -1;
+        if (lane < RPW) {
+            const int r = warp + NW * lane;
             const long long g = tile * gpt + r / K;
-            const bool ok = g < p.groups;
-            int pt = 0, b = 0;
-            if (ok) {
-                b = (int)(g / p.m);
-                pt = __ldg(p.idx + g * K + (r % K));
-            }
-            const size_t src = (size_t)b * p.n + pt;
+            if (g < p.groups) m_src = (g / p.m) * p.n + __ldg(p.idx + g * K + (r % K));
+        }
+#pragma unroll 2
+        for (int i = 0; i < RPW; ++i) {
+            const int r = warp + NW * i;
+            const long long g = tile * gpt + r / K;
+            const long long src_or = __shfl_sync(0xffffffffu, m_src, i);
+            const bool ok = src_or >= 0;
+            const size_t src = ok ? (size_t)src_or : 0;
             if (lane < 3)
                 x0[(size_t)(xyz_off + lane) * TRP + r] =
                     ok ? __fsub_rn(__ldg(p.xyz + src * 3 + lane), __ldg(p.new_xyz + g * 3 + lane)) : 0.f;
-            for (int c = lane; c < D; c += 32) x0[(size_t)(feat_off + c) * TRP + r] = ok ? __ldg(p.feat + src * D + c) : 0.f;
+            const float *f = p.feat + src * D;
+#pragma unroll 4
+            for (int c = lane; c < D; c += 32) x0[(size_t)(feat_off + c) * TRP + r] = ok ? __ldg(f + c) : 0.f;
             for (int c = C0 + lane; c < cpad; c += 32) x0[(size_t)c * TRP + r] = 0.f;
         }
     }
@@ -97,33 +107,53 @@ __device__ __forceinline__ void gather_sa(const RowMlpParams &p, float *x0, long
 template <int TR>
 __device__ __forceinline__ void gather_fp(const RowMlpParams &p, float *x0, long long tile) {
     constexpr int TRP = TR + 4;
+    constexpr int NW = RM_THREADS / 32;
+    constexpr int RPW = TR / NW;  // rows per warp: r = warp + NW * i
+    static_assert(RPW >= 1 && RPW <= 32, "rows per warp");
     const int D1 = p.d1, D2 = p.d2, C0 = D1 + D2;
     const int cpad = round_up(C0, KC);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = p.n;
-    for (int r = warp; r < TR; r += RM_THREADS / 32) {
-        const long long row = tile * TR + r;
-        const bool ok = row < p.rows;
-        const int b = ok ? (int)(row / n) : 0;
-        if (D1 > 0) {
-            const float *f1 = p.feat1 + (size_t)row * D1;
-            for (int c = lane; c < D1; c += 32) x0[(size_t)c * TRP + r] = ok ? __ldg(f1 + c) : 0.f;
-        }
-        if (p.fp_m == 1) {
-            // S == 1: the single coarse feature row is repeated (model/pointnet_util.py:202-203)
-            const float *f2 = p.feat2 + (size_t)b * D2;
-            for (int c = lane; c < D2; c += 32) x0[(size_t)(D1 + c) * TRP + r] = ok ? __ldg(f2 + c) : 0.f;
-        } else {
-            int i0 = 0, i1 = 0, i2 = 0;
-            float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-            if (ok) {
+    const bool single = p.fp_m == 1;
+    // index phase: lane i loads what row warp + NW * i needs (its three coarse rows and weights), so the whole warp pays
+    // ONE round trip for its RPW rows; the row loop below gets them by shuffle and its feature loads depend on registers only
+    // (one dependent index -> feature chain per row kept 16 round trips per warp on the critical path of the tile)
+    long long m_row = -1;
+    long long m_s0 = 0, m_s1 = 0, m_s2 = 0;  // element offsets of the coarse rows in feat2
+    float m_w0 = 0.f, m_w1 = 0.f, m_w2 = 0.f;
+    if (lane < RPW) {
+        const long long row = tile * TR + warp + NW * lane;
+        if (row < p.rows) {
+            m_row = row;
+            const long long b = row / n;
+            if (single) {
+                m_s0 = b * D2;  // S == 1: the single coarse feature row is repeated (model/pointnet_util.py:202-203)
+            } else {
                 const int32_t *id = p.idx + (size_t)row * 3;
                 const float *w = p.weight + (size_t)row * 3;
-                i0 = __ldg(id); i1 = __ldg(id + 1); i2 = __ldg(id + 2);
-                w0 = __ldg(w); w1 = __ldg(w + 1); w2 = __ldg(w + 2);
+                const long long base = b * p.fp_m;
+                m_s0 = (base + __ldg(id)) * D2; m_s1 = (base + __ldg(id + 1)) * D2; m_s2 = (base + __ldg(id + 2)) * D2;
+                m_w0 = __ldg(w); m_w1 = __ldg(w + 1); m_w2 = __ldg(w + 2);
             }
-            const float *f2 = p.feat2 + (size_t)b * p.fp_m * D2;
-            const float *r0 = f2 + (size_t)i0 * D2, *r1 = f2 + (size_t)i1 * D2, *r2 = f2 + (size_t)i2 * D2;
+        }
+    }
+#pragma unroll 2
+    for (int i = 0; i < RPW; ++i) {
+        const int r = warp + NW * i;
+        const long long row = __shfl_sync(0xffffffffu, m_row, i);
+        const bool ok = row >= 0;
+        if (D1 > 0) {
+            const float *f1 = p.feat1 + (size_t)(ok ? row : 0) * D1;
+            for (int c = lane; c < D1; c += 32) x0[(size_t)c * TRP + r] = ok ? __ldg(f1 + c) : 0.f;
+        }
+        const float *r0 = p.feat2 + __shfl_sync(0xffffffffu, m_s0, i);
+        if (single) {
+            for (int c = lane; c < D2; c += 32) x0[(size_t)(D1 + c) * TRP + r] = ok ? __ldg(r0 + c) : 0.f;
+        } else {
+            const float *r1 = p.feat2 + __shfl_sync(0xffffffffu, m_s1, i), *r2 = p.feat2 + __shfl_sync(0xffffffffu, m_s2, i);
+            const float w0 = __shfl_sync(0xffffffffu, m_w0, i), w1 = __shfl_sync(0xffffffffu, m_w1, i), w2 = __shfl_sync(0xffffffffu, m_w2, i);
+            // rows past the end carry offset 0 and weight 0: they read a valid row and store zeros
+#pragma unroll 4
             for (int c = lane; c < D2; c += 32) {
                 // same rounding sequence as three_interpolate (interpolate.cu)
                 const float v = __fmaf_rn(w2, __ldg(r2 + c), __fmaf_rn(w0, __ldg(r0 + c), __fmul_rn(w1, __ldg(r1 + c))));
@@ -135,7 +165,10 @@ __device__ __forceinline__ void gather_fp(const RowMlpParams &p, float *x0, long
 }
 
 template <int TR>
-__global__ void __launch_bounds__(RM_THREADS, 1) row_mlp_kernel(const __grid_constant__ RowMlpParams p) {
+#ifndef PN2_RM_MINB
+#define PN2_RM_MINB 2
+#endif
+__global__ void __launch_bounds__(RM_THREADS, PN2_RM_MINB) row_mlp_kernel(const __grid_constant__ RowMlpParams p) {
     constexpr int TRP = TR + 4;
     // shared memory layout: [ping: buf_a_floats][pong: buf_b_floats][weight tiles: 2*KC*WSP]
     extern __shared__ __align__(16) float smem[];
@@ -151,12 +184,18 @@ __global__ void __launch_bounds__(RM_THREADS, 1) row_mlp_kernel(const __grid_con
         gather_fp<TR>(p, smem, tile);
     __syncthreads();
 
+    int cur = 0;  // which buffer holds the current layer's input
     for (int l = 0; l < p.num_layers; ++l) {
-        const float *xin = smem + ((l & 1) ? p.buf_a_floats : 0);
-        float *xout = smem + ((l & 1) ? 0 : p.buf_a_floats);
         const bool last = (l == p.num_layers - 1);
         const int cin = p.cin[l], cout = p.cout[l];
         const int nt = pick_nt(cout, TR);
+        // A layer of ONE n-tile writes its output over its input: every read of the input is behind the barrier that ends
+        // the tile's k loop, and the epilogue stores come after it.  Stacks of such layers (fp1 + head, sa1, sa2) need no
+        // pong buffer, which is what lets two CTAs share an SM.  Wider layers write to the other buffer (make_layout).
+        const bool in_place = cout <= nt;
+        const float *xin = smem + (cur ? p.buf_a_floats : 0);
+        float *xout = smem + ((cur != 0) == in_place ? p.buf_a_floats : 0);
+        if (!in_place) cur ^= 1;
         for (int n0 = 0; n0 < cout; n0 += nt) {
             const int ch0 = last ? 0 : n0;
             if (nt == 128)
@@ -202,21 +241,23 @@ struct Layout {
 };
 
 Layout make_layout(int tr, int c0, const pn2_mlp *mlp) {
+    // mirrors the buffer walk of row_mlp_kernel: single-n-tile layers run in place, wider ones flip buffers
     const int trp = tr + 4;
-    int a = round_up(c0, KC) * trp, b = 0;
+    int need[2] = {round_up(c0, KC) * trp, 0};
+    int cur = 0;
     for (int l = 0; l < mlp->num_layers; ++l) {
         const int nt = pick_nt(mlp->cout[l], tr);
+        const bool in_place = mlp->cout[l] <= nt;
+        // the last layer hands one n-tile at a time to the pool / store step
         const int ch = (l == mlp->num_layers - 1) ? nt : round_up(mlp->cout[l], nt);
-        if (((l + 1) & 1) == 1)
-            b = b > ch * trp ? b : ch * trp;
-        else
-            a = a > ch * trp ? a : ch * trp;
+        if (!in_place) cur ^= 1;
+        need[cur] = need[cur] > ch * trp ? need[cur] : ch * trp;
         // inputs are read up to round_up(cin, KC) channels only through kk_end, no extra space needed
     }
     Layout L;
-    L.buf_a = a;
-    L.buf_b = b;
-    L.bytes = (size_t)(a + b + 2 * KC * WSP) * sizeof(float);
+    L.buf_a = need[0];
+    L.buf_b = need[1];
+    L.bytes = (size_t)(need[0] + need[1] + 2 * KC * WSP) * sizeof(float);
     return L;
 }
 
@@ -249,10 +290,12 @@ int launch(const RowMlpParams &p, const Layout &L, long long tiles, cudaStream_t
 // would leave SMs idle.
 int dispatch(RowMlpParams &p, const pn2_mlp *mlp, int c0, long long total_rows, int min_tr, cudaStream_t s) {
     const int cands[4] = {128, 64, 32, 16};
+    static const int forced = getenv("PN2_DEV_ROW_TILE") ? atoi(getenv("PN2_DEV_ROW_TILE")) : 0;  // developer timing only
     int chosen = -1;
     for (int i = 0; i < 4; ++i) {
         const int tr = cands[i];
         if (tr < min_tr || tr % min_tr) continue;
+        if (forced && tr > forced && tr / 2 >= min_tr) continue;
         if (make_layout(tr, c0, mlp).bytes > SMEM_LIMIT) continue;
         chosen = tr;
         const long long tiles = (total_rows + tr - 1) / tr;

@@ -18,7 +18,7 @@ __host__ __device__ inline int round_up(int v, int a) { return (v + a - 1) / a *
 
 // One n-tile of one layer: acc = X_in[.,rows] * W[n0 + cols, .]^T, then bias/ReLU and a k-major store.
 template <int TR, int NT>
-__device__ __forceinline__ void layer_tile(const float *__restrict__ xin, float *__restrict__ xout, int out_ch0,
+__device__ __forceinline__ void layer_tile(const float *xin, float *xout, int out_ch0,
                                            const float *__restrict__ W, const float *__restrict__ bias, int cin,
                                            int cout, int n0, int relu, float *ws) {
     constexpr int TRP = TR + 4;
@@ -29,7 +29,14 @@ __device__ __forceinline__ void layer_tile(const float *__restrict__ xin, float 
     constexpr int EPT = KC * NT / RM_THREADS;  // weight elements staged per thread per chunk
     static_assert(TN >= 1 && EPT >= 1, "bad tile");
     const int tid = threadIdx.x;
-    const int tx = tid % TXN, ty = tid / TXN;
+    // thread -> (tx, ty).  A 128-bit shared load costs one wavefront per distinct 128-byte line and HALF warp (ncu: 2 for an
+    // A fragment shared by 16 lanes, 4 for 16 lanes x 16 B of B read by both halves), so a warp is laid out as 8 tx x 4 ty:
+    // each half warp reads one 128-byte line of B and two 16-byte pieces of one line of A.  Narrow thread tiles (TN < 4:
+    // 64- / 32-bit B loads) keep consecutive lanes along tx.
+    constexpr int LTX = (TN >= 4 && TXN >= 8) ? 8 : (TXN < 32 ? TXN : 32);
+    constexpr int WX = TXN / LTX;
+    const int lane_ = tid & 31, warp_ = tid >> 5;
+    const int tx = (warp_ % WX) * LTX + lane_ % LTX, ty = (warp_ / WX) * (32 / LTX) + lane_ / LTX;
 
     // staging coordinates: smem position p <-> logical column.  A thread's TN columns are tx + TXN * j; they sit in
     // groups of four so that the lanes of a quarter warp read CONSECUTIVE 16-byte slots (p = (j / 4) * 4 TXN + 4 tx + j % 4):
@@ -81,8 +88,7 @@ __device__ __forceinline__ void layer_tile(const float *__restrict__ xin, float 
         if (more) load_chunk((c + 1) * KC);
         const float *xa = xin + (size_t)(c * KC) * TRP + ty * TM;
         const int kk_end = min(KC, cin - c * KC);
-#pragma unroll 4
-        for (int kk = 0; kk < kk_end; ++kk) {
+        auto step = [&](int kk) {
             float a[TM], b[TN];
 #pragma unroll
             for (int i = 0; i < TM; i += 4) {
@@ -106,6 +112,12 @@ __device__ __forceinline__ void layer_tile(const float *__restrict__ xin, float 
             for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        };
+        if (kk_end == KC) {  // whole chunk: no per-step bound checks, loads scheduled across the 16 steps
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) step(kk);
+        } else {
+            for (int kk = 0; kk < kk_end; ++kk) step(kk);
         }
         if (more) {
 #pragma unroll

@@ -8,7 +8,7 @@ from pn2_b200 import pointnet2_utils as pu
 from pn2_b200.models import PointNet2SemSeg
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-U.set_mlp_precision("bf16")
+U.set_mlp_precision(os.environ.get("PRECISION", "bf16"))  # fp32: the FFMA kernels of row_mlp.cu
 torch.manual_seed(0)
 model = PointNet2SemSeg(21).eval().to(dev)
 pts = torch.from_numpy(scenes.scannet_batch(0, B, 8192)).to(dev)
