@@ -153,10 +153,15 @@ three_interpolate_kernel(int c, int m, int n, const float *__restrict__ points, 
 constexpr int TS_THREADS = 256;
 constexpr int LC_GRAN = 32;  // points per warp granule of the lane-along-channel kernel
 
-template <int CC, int PAD>
-__global__ void __launch_bounds__(TS_THREADS, 3)
+// T threads per CTA, MINB CTAs per SM (by the size of the staged tile).  With one or two CTAs per SM the index / weight
+// vectors of the NEXT four points are loaded while the current four are interpolated (they are the only long-latency loads
+// of the loop and 8-16 warps do not hide them; with three CTAs per SM the 85-register budget has no room for them).
+template <int CC, int PAD, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB)
 three_interpolate_smem_kernel(int c, int m, int n, const float *__restrict__ points, const int32_t *__restrict__ idx,
                               const float *__restrict__ weight, float *__restrict__ out) {
+    constexpr int TS_THREADS = T;
+    constexpr bool kPrefetch = MINB <= 2 && CC <= 8;  // wider tiles: enough work per index vector, and no registers to spare
     // row stride (floats): 16-byte aligned; PAD = 4 spreads the rows over the banks, PAD = 0 (CC = 4: 16 bytes per coarse
     // point) is the dense form that still fits when the coarse set is large (m <= 12800)
     constexpr int CCP = CC + PAD;
@@ -187,15 +192,34 @@ three_interpolate_smem_kernel(int c, int m, int n, const float *__restrict__ poi
         const int n4 = n / 4;
         const int per = (n4 + gridDim.x - 1) / gridDim.x;
         const int q0 = blockIdx.x * per, q1 = min(n4, q0 + per);
+        int4 kv[3], kn[3];
+        float4 wv[3], wn[3];
+        auto load_iw = [&](int q, int4 (&ki)[3], float4 (&wi)[3]) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                ki[u] = make_int4(0, 0, 0, 0);
+                wi[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < q1) {
+                    ki[u] = __ldcs(reinterpret_cast<const int4 *>(idb) + (size_t)q * 3 + u);
+                    wi[u] = __ldcs(reinterpret_cast<const float4 *>(wb) + (size_t)q * 3 + u);
+                }
+            }
+        };
+        if (kPrefetch) load_iw(q0 + threadIdx.x, kn, wn);
         for (int q = q0 + threadIdx.x; q < q1; q += TS_THREADS) {
+            if (kPrefetch) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) { kv[u] = kn[u]; wv[u] = wn[u]; }
+                load_iw(q + TS_THREADS, kn, wn);
+            } else {
+                load_iw(q, kv, wv);
+            }
             int k[12];
             float w[12];
 #pragma unroll
             for (int u = 0; u < 3; ++u) {
-                const int4 kv = __ldcs(reinterpret_cast<const int4 *>(idb) + (size_t)q * 3 + u);
-                const float4 wv = __ldcs(reinterpret_cast<const float4 *>(wb) + (size_t)q * 3 + u);
-                k[4 * u] = kv.x; k[4 * u + 1] = kv.y; k[4 * u + 2] = kv.z; k[4 * u + 3] = kv.w;
-                w[4 * u] = wv.x; w[4 * u + 1] = wv.y; w[4 * u + 2] = wv.z; w[4 * u + 3] = wv.w;
+                k[4 * u] = kv[u].x; k[4 * u + 1] = kv[u].y; k[4 * u + 2] = kv[u].z; k[4 * u + 3] = kv[u].w;
+                w[4 * u] = wv[u].x; w[4 * u + 1] = wv[u].y; w[4 * u + 2] = wv[u].z; w[4 * u + 3] = wv[u].w;
             }
 #pragma unroll
             for (int cq = 0; cq < CC / 4; ++cq) {
@@ -267,6 +291,16 @@ three_interpolate_row_kernel(int c, int m, int n, const float *__restrict__ poin
     }
 }
 
+template <int CC, int PAD, int T, int MINB>
+int launch_interp_smem_as(dim3 grid, size_t smem, int c, int m, int n, const float *points, const int32_t *idx, const float *weight,
+                          float *out, cudaStream_t s) {
+    auto kern = three_interpolate_smem_kernel<CC, PAD, T, MINB>;
+    PN2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, T, smem, s>>>(c, m, n, points, idx, weight, out);
+    PN2_LAUNCH_OK("three_interpolate");
+    return PN2_OK;
+}
+
 template <int CC, int PAD = 4>
 int launch_interp_smem(int b, int c, int m, int n, const float *points, const int32_t *idx, const float *weight, float *out,
                        cudaStream_t s) {
@@ -277,11 +311,11 @@ int launch_interp_smem(int b, int c, int m, int n, const float *points, const in
     // per CTA so the staging stays a small part of its work
     int nsplit = 1;
     while ((long long)nsplit * chunks * b < 2ll * per_sm * sm_count() && n / (nsplit + 1) >= 2 * m) ++nsplit;
-    PN2_CUDA(cudaFuncSetAttribute(three_interpolate_smem_kernel<CC, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nsplit, chunks, b);
-    three_interpolate_smem_kernel<CC, PAD><<<grid, TS_THREADS, smem, s>>>(c, m, n, points, idx, weight, out);
-    PN2_LAUNCH_OK("three_interpolate");
-    return PN2_OK;
+    // one CTA per SM (large coarse sets): 512 threads, so 16 warps stream the points
+    if (per_sm == 3) return launch_interp_smem_as<CC, PAD, 256, 3>(grid, smem, c, m, n, points, idx, weight, out, s);
+    if (per_sm == 2) return launch_interp_smem_as<CC, PAD, 256, 2>(grid, smem, c, m, n, points, idx, weight, out, s);
+    return launch_interp_smem_as<CC, PAD, 512, 1>(grid, smem, c, m, n, points, idx, weight, out, s);
 }
 
 // Lane-along-channel kernel (32 channels per tile, coarse sets up to ~1400 points).

@@ -5,6 +5,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "multi-modal-learning-on-3d-point-clouds_b200"))
 import numpy as np, torch
 from pn2_b200 import _lib as L
+if os.environ.get("PN2_LIB_PATH"):  # A/B runs against a second build of the library
+    L.LIB_PATH = os.environ["PN2_LIB_PATH"]
 from pn2_b200 import pointnet2_utils as pu
 dev = torch.device("cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -25,7 +27,8 @@ def t_ms(fn, iters=9):
 g = torch.Generator(device=dev).manual_seed(0)
 SHAPES = [(32, 128, 1024, 8192)] if len(sys.argv) > 1 else [(32, 128, 1024, 8192), (64, 128, 2048, 8192), (64, 128, 4096, 16384), (16, 256, 256, 1024), (64, 128, 1024, 4096),
           (32, 256, 64, 256), (32, 128, 256, 1024), (8, 128, 1024, 8192), (2, 128, 1024, 8192),
-          (3, 100, 1023, 8188), (5, 37, 700, 4100), (2, 128, 1, 512), (4, 64, 1500, 30000)]
+          (3, 100, 1023, 8188), (5, 37, 700, 4100), (2, 128, 1, 512), (4, 64, 1500, 30000),
+          (32, 128, 8192, 32768), (16, 64, 12000, 48000), (16, 128, 2048, 34720)]
 MODES = [32, 32 | 256, 32 | 1024, 32 | 2048]  # + 1024 / 2048: bisect probes (no stores / no row reads; results differ)
 for (B, C, m, n) in SHAPES:
     f = torch.randn(B, C, m, device=dev)
