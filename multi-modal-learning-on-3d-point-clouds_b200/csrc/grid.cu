@@ -13,6 +13,9 @@
 // The sorted order doubles as a spatially coherent row order for the feature-propagation gather (row_mlp_tc.cu).
 #include "common.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace pn2 {
 namespace {
 
@@ -363,33 +366,37 @@ ball_query_grid_kernel(int n, int m, float radius, int nsample, const float *__r
 }
 
 // ---- three nearest neighbours (+ the reference's interpolation weights) --------------------------------------
-struct Best3 {
-    float d1, d2, d3;
-    int i1, i2, i3;
+// The running best three are 64-bit keys (float bits of the squared distance << 32 | index): distances are >= 0, so the
+// unsigned order of the keys is the lexicographic (d, index) order, and keeping the three smallest keys gives the same
+// final state as the reference's ascending strict-'<' scan whatever order the candidates arrive in.  The insertion is a
+// branch-free min / max network: with 32 queries per warp nearly every candidate is inserted by SOME lane, so a branchy
+// insertion runs all of its nested paths for almost every candidate (ncu: 18 of 32 lanes active on average, 2700 warp
+// instructions per 32 queries at the fp1 shape).
+struct Key3 {
+    unsigned long long k1, k2, k3;
 };
 
-__device__ __forceinline__ bool before(float d, int i, float bd, int bi) { return d < bd || (d == bd && i < bi); }
+constexpr unsigned long long KEY_EMPTY = (0x7f800000ull << 32) | 0x7fffffffull;  // (+inf, no index)
 
-// (d, index) lexicographic insertion: the same final state as the reference's ascending strict-'<' scan
-__device__ __forceinline__ void best3_insert(Best3 &t, float d, int k) {
-    if (before(d, k, t.d3, t.i3)) {
-        if (before(d, k, t.d1, t.i1)) {
-            t.d3 = t.d2; t.i3 = t.i2;
-            t.d2 = t.d1; t.i2 = t.i1;
-            t.d1 = d;    t.i1 = k;
-        } else if (before(d, k, t.d2, t.i2)) {
-            t.d3 = t.d2; t.i3 = t.i2;
-            t.d2 = d;    t.i2 = k;
-        } else {
-            t.d3 = d;    t.i3 = k;
-        }
-    }
+__device__ __forceinline__ void key3_insert(Key3 &t, float d, int k) {
+    const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)k;
+    const unsigned long long a = min(t.k1, key), r1 = max(t.k1, key);
+    const unsigned long long b = min(t.k2, r1), r2 = max(t.k2, r1);
+    t.k1 = a;
+    t.k2 = b;
+    t.k3 = min(t.k3, r2);
 }
 
 // One query of the 3-NN search; `sorted` / `cell_start` point to the cloud's cell list in global OR shared memory
-// (three_nn_grid_staged_kernel copies small coarse clouds there first).
-__device__ __forceinline__ void three_nn_grid_query(int n, int m, int b, int slot, const GridMeta &g, const float *__restrict__ unknown_all,
-                                                    const float *__restrict__ known_all, const float4 *sorted, const int32_t *cell_start,
+// (three_nn_grid_staged_kernel copies small coarse clouds there first).  Lanes past the end repeat the last query and
+// store nothing.
+// (Measured and not kept: a first pass in which all lanes of a warp scan the ONE block that holds every lane's ring-1
+// neighbourhood -- uniform trip counts, broadcast loads.  With the queries in the row-major cell order of the fine grid a
+// warp's 32 queries span ~6 coarse cells, the common block holds 2-3 x the candidates and the pass is slower at every
+// size: fp1 shape 43 us without it, 45-50 us with block limits of 27-80 cells.)
+__device__ __forceinline__ void three_nn_grid_query(int n, int m, int b, int slot, bool valid, const GridMeta &g,
+                                                    const float *__restrict__ unknown_all, const float *__restrict__ known_all,
+                                                    const float4 *sorted, const int32_t *cell_start,
                                                     const int32_t *__restrict__ query_order, float *__restrict__ dist2_out,
                                                     int32_t *__restrict__ idx_out, float *__restrict__ weight_out) {
     // optional spatially coherent processing order (neighbouring threads then walk the same cells)
@@ -398,7 +405,7 @@ __device__ __forceinline__ void three_nn_grid_query(int n, int m, int b, int slo
     const float ux = u[0], uy = u[1], uz = u[2];
     const float h = 1.0f / g.inv_h;
     const float INF = __int_as_float(0x7f800000);
-    Best3 t;
+    Key3 t;
     const int cx = cell_coord(ux, g.ox, g.inv_h, g.dx), cy = cell_coord(uy, g.oy, g.inv_h, g.dy),
               cz = cell_coord(uz, g.oz, g.inv_h, g.dz);
     bool done = false;
@@ -408,8 +415,7 @@ __device__ __forceinline__ void three_nn_grid_query(int n, int m, int b, int slo
     for (int ring = 1; !done; ring = ring < 2 ? 2 : 2 * ring) {
         const long long rows = (long long)min(2 * ring + 1, g.dy) * min(2 * ring + 1, g.dz);
         if (ring > 2 && (rows * 8 > m || ring > 64)) break;
-        t.d1 = t.d2 = t.d3 = INF;
-        t.i1 = t.i2 = t.i3 = 0x7fffffff;
+        t.k1 = t.k2 = t.k3 = KEY_EMPTY;
         const int x0 = max(cx - ring, 0), x1 = min(cx + ring, g.dx - 1);
         const int y0 = max(cy - ring, 0), y1 = min(cy + ring, g.dy - 1);
         const int z0 = max(cz - ring, 0), z1 = min(cz + ring, g.dz - 1);
@@ -419,7 +425,7 @@ __device__ __forceinline__ void three_nn_grid_query(int n, int m, int b, int slo
                 const int s = cell_start[base + x0], e = cell_start[base + x1 + 1];
                 for (int p = s; p < e; ++p) {
                     const float4 v = sorted[p];
-                    best3_insert(t, dist_ref(ux, uy, uz, v.x, v.y, v.z), __float_as_int(v.w));
+                    key3_insert(t, dist_ref(ux, uy, uz, v.x, v.y, v.z), __float_as_int(v.w));
                 }
             }
         // Every known point outside the scanned block is at least `rho` away: the distance from the query to the
@@ -436,28 +442,29 @@ __device__ __forceinline__ void three_nn_grid_query(int n, int m, int b, int slo
             done = true;  // the block covers the whole grid
         } else if (rho > 0.f) {
             const float safe = rho * 0.999f;  // margin >> fp32 rounding of cell edges and distances
-            done = t.d3 < safe * safe;
+            done = __uint_as_float((unsigned)(t.k3 >> 32)) < safe * safe;
         }
     }
     if (!done) {
-        // sparse neighbourhood: exact scan of the whole known set (original order, strict '<' as the reference)
+        // sparse neighbourhood: exact scan of the whole known set
         const float *known = known_all + (size_t)b * m * 3;
-        t.d1 = t.d2 = t.d3 = INF;
-        t.i1 = t.i2 = t.i3 = 0x7fffffff;
+        t.k1 = t.k2 = t.k3 = KEY_EMPTY;
         for (int k = 0; k < m; ++k)
-            best3_insert(t, dist_ref(ux, uy, uz, __ldg(known + 3 * k), __ldg(known + 3 * k + 1), __ldg(known + 3 * k + 2)), k);
+            key3_insert(t, dist_ref(ux, uy, uz, __ldg(known + 3 * k), __ldg(known + 3 * k + 1), __ldg(known + 3 * k + 2)), k);
     }
-    if (t.d1 == INF) t.i1 = 0;  // fewer than three known points: index 0 / +inf as the reference leaves them
-    if (t.d2 == INF) t.i2 = 0;
-    if (t.d3 == INF) t.i3 = 0;
+    if (!valid) return;
+    const float d1 = __uint_as_float((unsigned)(t.k1 >> 32)), d2 = __uint_as_float((unsigned)(t.k2 >> 32)),
+                d3 = __uint_as_float((unsigned)(t.k3 >> 32));
+    // fewer than three known points: index 0 / +inf as the reference leaves them
+    const int i1 = d1 == INF ? 0 : (int)(unsigned)t.k1, i2 = d2 == INF ? 0 : (int)(unsigned)t.k2, i3 = d3 == INF ? 0 : (int)(unsigned)t.k3;
     const size_t o = ((size_t)b * n + i) * 3;
-    idx_out[o] = t.i1; idx_out[o + 1] = t.i2; idx_out[o + 2] = t.i3;
+    idx_out[o] = i1; idx_out[o + 1] = i2; idx_out[o + 2] = i3;
     if (dist2_out) {
-        dist2_out[o] = t.d1; dist2_out[o + 1] = t.d2; dist2_out[o + 2] = t.d3;
+        dist2_out[o] = d1; dist2_out[o + 1] = d2; dist2_out[o + 2] = d3;
     }
     if (weight_out) {
         // model/pointnet2_utils.py:97 + model/pointnet_util.py:206-208
-        float e1 = __fsqrt_rn(t.d1), e2 = __fsqrt_rn(t.d2), e3 = __fsqrt_rn(t.d3);
+        float e1 = __fsqrt_rn(d1), e2 = __fsqrt_rn(d2), e3 = __fsqrt_rn(d3);
         e1 = e1 < 1e-10f ? 1e-10f : e1;
         e2 = e2 < 1e-10f ? 1e-10f : e2;
         e3 = e3 < 1e-10f ? 1e-10f : e3;
@@ -475,20 +482,19 @@ three_nn_grid_kernel(int n, int m, const float *__restrict__ unknown_all, const 
                      float *__restrict__ dist2_out, int32_t *__restrict__ idx_out, float *__restrict__ weight_out) {
     const int b = blockIdx.y;
     const int slot = blockIdx.x * 128 + threadIdx.x;
-    if (slot >= n) return;
     const GridMeta g = meta_all[b];
-    three_nn_grid_query(n, m, b, slot, g, unknown_all, known_all, sorted_all + (size_t)b * m,
+    three_nn_grid_query(n, m, b, min(slot, n - 1), slot < n, g, unknown_all, known_all, sorted_all + (size_t)b * m,
                         cell_start_all + (size_t)b * (GRID_MAX_CELLS + 1), query_order, dist2_out, idx_out, weight_out);
 }
 
 // Small coarse clouds (m <= TNS_MAX_M: the 1024 / 256 / 64-point levels of the semseg stacks): the CTA copies the cloud's
 // sorted points and -- when the grid has at most TNS_MAX_CELLS cells -- its cell-start table into shared memory once
-// and its 512 queries search there; every cell-table and candidate read is then a shared-memory load instead of a
+// and its 256 queries search there; every cell-table and candidate read is then a shared-memory load instead of a
 // dependent L1 / L2 access (a query makes ~18 table reads and ~30 candidate reads in a chain).
-constexpr int TNS_THREADS = 512, TNS_MAX_M = 2048, TNS_MAX_CELLS = 8192;
+constexpr int TNS_THREADS = 256, TNS_MAX_M = 2048, TNS_MAX_CELLS = 8192;
 
 __global__ void __launch_bounds__(TNS_THREADS)
-three_nn_grid_staged_kernel(int n, int m, const float *__restrict__ unknown_all, const float *__restrict__ known_all,
+three_nn_grid_staged_kernel(int n, int m, int cell_cap, const float *__restrict__ unknown_all, const float *__restrict__ known_all,
                             const float4 *__restrict__ sorted_all, const int32_t *__restrict__ cell_start_all,
                             const GridMeta *__restrict__ meta_all, const int32_t *__restrict__ query_order,
                             float *__restrict__ dist2_out, int32_t *__restrict__ idx_out, float *__restrict__ weight_out) {
@@ -500,13 +506,12 @@ three_nn_grid_staged_kernel(int n, int m, const float *__restrict__ unknown_all,
     const float4 *sorted = sorted_all + (size_t)b * m;
     const int32_t *cell_start = cell_start_all + (size_t)b * (GRID_MAX_CELLS + 1);
     for (int e = threadIdx.x; e < m; e += TNS_THREADS) s_sorted[e] = __ldg(sorted + e);
-    const bool cells_fit = g.ncells <= TNS_MAX_CELLS;  // uniform over the CTA
+    const bool cells_fit = g.ncells <= cell_cap;  // uniform over the CTA (cell_cap: what the launch reserved, <= TNS_MAX_CELLS)
     if (cells_fit)
         for (int e = threadIdx.x; e <= g.ncells; e += TNS_THREADS) s_cells[e] = __ldg(cell_start + e);
     __syncthreads();
     const int slot = blockIdx.x * TNS_THREADS + threadIdx.x;
-    if (slot >= n) return;
-    three_nn_grid_query(n, m, b, slot, g, unknown_all, known_all, s_sorted, cells_fit ? s_cells : cell_start, query_order, dist2_out,
+    three_nn_grid_query(n, m, b, min(slot, n - 1), slot < n, g, unknown_all, known_all, s_sorted, cells_fit ? s_cells : cell_start, query_order, dist2_out,
                         idx_out, weight_out);
 }
 
@@ -583,10 +588,13 @@ extern "C" int pn2_three_nn_grid(int b, int n, int m, const float *unknown, cons
     PN2_REQUIRE(unknown && known && sorted && cell_start && meta && idx, "three_nn_grid: null pointer");
     PN2_REQUIRE(b <= 65535, "three_nn_grid: b exceeds the grid limit");
     if (m <= TNS_MAX_M && n >= 2 * TNS_THREADS) {
-        const size_t smem = (size_t)m * sizeof(float4) + (size_t)(TNS_MAX_CELLS + 1) * sizeof(int32_t);
+        // room for a table of up to 4 cells per coarse point (the automatic cell size gives about one); larger tables
+        // are read from global memory
+        const int cell_cap = std::min(TNS_MAX_CELLS, 4 * m < 512 ? 512 : 4 * m);
+        const size_t smem = (size_t)m * sizeof(float4) + (size_t)(cell_cap + 1) * sizeof(int32_t);
         PN2_CUDA(cudaFuncSetAttribute(three_nn_grid_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         three_nn_grid_staged_kernel<<<dim3(ceil_div(n, TNS_THREADS), b), TNS_THREADS, smem, (cudaStream_t)stream>>>(
-            n, m, unknown, known, reinterpret_cast<const float4 *>(sorted), cell_start, reinterpret_cast<const GridMeta *>(meta), query_order,
+            n, m, cell_cap, unknown, known, reinterpret_cast<const float4 *>(sorted), cell_start, reinterpret_cast<const GridMeta *>(meta), query_order,
             dist2, idx, weight);
         PN2_LAUNCH_OK("three_nn_grid_staged");
         return PN2_OK;
