@@ -228,8 +228,22 @@ def test_group_bit_exact_and_grad(cuda, B, C, N, P, S):
         np.testing.assert_array_equal(out.detach().cpu().numpy(), ref_cuda.grouping_operation(dev(f, cuda), dev(idx, cuda)).cpu().numpy())
 
 
+# the staged-row kernel of group_points where few rows fit in shared memory (long source rows): one staged row per
+# 1024-thread CTA with the index vectors of the next iteration in flight (N = 32768), two rows and an index list that is
+# not a multiple of four (scalar loop), four rows per 512-thread CTA
+@pytest.mark.parametrize("B,C,N,P,S", [(2, 16, 32768, 2048, 32), (1, 33, 20000, 1667, 25), (2, 17, 12000, 3000, 8)])
+def test_group_long_rows_bit_exact(cuda, B, C, N, P, S):
+    rng = np.random.default_rng(C * N + S)
+    f = rng.standard_normal((B, C, N)).astype(np.float32)
+    idx = rng.integers(0, N, (B, P, S)).astype(np.int32)
+    idx[:, 0, :] = N - 1  # last element of every row
+    out = pu.grouping_operation(dev(f, cuda), dev(idx, cuda))
+    np.testing.assert_array_equal(out.cpu().numpy(), orc.grouping_operation(f, idx))
+
+
 @pytest.mark.parametrize("B,C,m,n", [(2, 128, 1024, 8192), (2, 256, 64, 256), (1, 7, 50, 33), (2, 512, 16, 64),
-                                     (1, 70, 8192, 32768), (1, 66, 15000, 30002), (2, 33, 6000, 12001)])  # large coarse sets
+                                     (1, 70, 8192, 32768), (1, 66, 15000, 30002), (2, 33, 6000, 12001),  # large coarse sets
+                                     (1, 70, 4096, 16384), (2, 40, 2048, 8192)])  # tiled kernel, one / two CTAs per SM (index prefetch)
 def test_three_interpolate_and_grad(cuda, B, C, m, n):
     rng = np.random.default_rng(C + m + n)
     f = rng.standard_normal((B, C, m)).astype(np.float32)
