@@ -77,17 +77,29 @@ struct ActIn {  // x with the previous layer's BatchNorm + ReLU folded in (scale
         if (scale) v = fmaxf(fmaf(v, __ldg(scale + k), __ldg(shift + k)), 0.f);
         return v;
     }
-    __device__ __forceinline__ float4 four(long long r, int k) const {  // k % 4 == 0
-        if (r < rows && k + 3 < c && (c & 3) == 0) {
-            float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * c + k));
-            if (scale) {
-                const float4 s = __ldg(reinterpret_cast<const float4 *>(scale + k)), t = __ldg(reinterpret_cast<const float4 *>(shift + k));
-                v.x = fmaxf(fmaf(v.x, s.x, t.x), 0.f); v.y = fmaxf(fmaf(v.y, s.y, t.y), 0.f);
-                v.z = fmaxf(fmaf(v.z, s.z, t.z), 0.f); v.w = fmaxf(fmaf(v.w, s.w, t.w), 0.f);
-            }
-            return v;
+    // The load of an operand chunk is split in two: raw() issues the long-latency loads of the row data and nothing that
+    // depends on them, finish() applies the per-channel transform.  The GEMM loops call raw() for chunk c + 1, multiply chunk
+    // c, and only then finish() + store: with the transform inside the load the first dependent FFMA stalled the warp on the
+    // loads (in-order issue) BEFORE the multiplies of the current chunk, so no load latency was ever hidden (ncu: the
+    // transform's FFMA / FSEL carry the long-scoreboard samples, FMA pipe 10-13 % busy).
+    struct Raw {
+        float4 v;
+    };
+    __device__ __forceinline__ bool fast(long long r, int k) const { return r < rows && k + 3 < c && (c & 3) == 0; }
+    __device__ __forceinline__ Raw raw(long long r, int k) const {  // k % 4 == 0
+        Raw q;
+        if (fast(r, k)) q.v = __ldg(reinterpret_cast<const float4 *>(x + r * c + k));
+        else q.v = make_float4(one(r, k), one(r, k + 1), one(r, k + 2), one(r, k + 3));  // ragged edge: final values at once
+        return q;
+    }
+    __device__ __forceinline__ float4 finish(const Raw &q, long long r, int k) const {
+        float4 v = q.v;
+        if (scale && fast(r, k)) {
+            const float4 s = __ldg(reinterpret_cast<const float4 *>(scale + k)), t = __ldg(reinterpret_cast<const float4 *>(shift + k));
+            v.x = fmaxf(fmaf(v.x, s.x, t.x), 0.f); v.y = fmaxf(fmaf(v.y, s.y, t.y), 0.f);
+            v.z = fmaxf(fmaf(v.z, s.z, t.z), 0.f); v.w = fmaxf(fmaf(v.w, s.w, t.w), 0.f);
         }
-        return make_float4(one(r, k), one(r, k + 1), one(r, k + 2), one(r, k + 3));
+        return v;
     }
 };
 
@@ -101,20 +113,33 @@ struct DzIn {  // dz = ca * g * [scale z + shift > 0] + cb + cc * z, built from 
         const float dy = fmaf(zz, __ldg(scale + k), __ldg(shift + k)) > 0.f ? gg : 0.f;
         return fmaf(__ldg(cc + k), zz, fmaf(__ldg(ca + k), dy, __ldg(cb + k)));
     }
-    __device__ __forceinline__ float4 four(long long r, int k) const {
-        if (r < rows && k + 3 < c && (c & 3) == 0) {
-            const float4 zz = __ldg(reinterpret_cast<const float4 *>(z + r * c + k)), gg = __ldg(reinterpret_cast<const float4 *>(g + r * c + k));
-            const float4 s = __ldg(reinterpret_cast<const float4 *>(scale + k)), t = __ldg(reinterpret_cast<const float4 *>(shift + k));
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(ca + k)), b = __ldg(reinterpret_cast<const float4 *>(cb + k));
-            const float4 cq = __ldg(reinterpret_cast<const float4 *>(cc + k));
-            float4 o;
-            o.x = fmaf(cq.x, zz.x, fmaf(a.x, fmaf(zz.x, s.x, t.x) > 0.f ? gg.x : 0.f, b.x));
-            o.y = fmaf(cq.y, zz.y, fmaf(a.y, fmaf(zz.y, s.y, t.y) > 0.f ? gg.y : 0.f, b.y));
-            o.z = fmaf(cq.z, zz.z, fmaf(a.z, fmaf(zz.z, s.z, t.z) > 0.f ? gg.z : 0.f, b.z));
-            o.w = fmaf(cq.w, zz.w, fmaf(a.w, fmaf(zz.w, s.w, t.w) > 0.f ? gg.w : 0.f, b.w));
-            return o;
+    struct Raw {
+        float4 z, g;  // ragged edge: z holds the final values
+    };
+    __device__ __forceinline__ bool fast(long long r, int k) const { return r < rows && k + 3 < c && (c & 3) == 0; }
+    __device__ __forceinline__ Raw raw(long long r, int k) const {
+        Raw q;
+        if (fast(r, k)) {
+            q.z = __ldg(reinterpret_cast<const float4 *>(z + r * c + k));
+            q.g = __ldg(reinterpret_cast<const float4 *>(g + r * c + k));
+        } else {
+            q.z = make_float4(one(r, k), one(r, k + 1), one(r, k + 2), one(r, k + 3));
+            q.g = q.z;
         }
-        return make_float4(one(r, k), one(r, k + 1), one(r, k + 2), one(r, k + 3));
+        return q;
+    }
+    __device__ __forceinline__ float4 finish(const Raw &q, long long r, int k) const {
+        if (!fast(r, k)) return q.z;
+        const float4 zz = q.z, gg = q.g;
+        const float4 s = __ldg(reinterpret_cast<const float4 *>(scale + k)), t = __ldg(reinterpret_cast<const float4 *>(shift + k));
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(ca + k)), b = __ldg(reinterpret_cast<const float4 *>(cb + k));
+        const float4 cq = __ldg(reinterpret_cast<const float4 *>(cc + k));
+        float4 o;
+        o.x = fmaf(cq.x, zz.x, fmaf(a.x, fmaf(zz.x, s.x, t.x) > 0.f ? gg.x : 0.f, b.x));
+        o.y = fmaf(cq.y, zz.y, fmaf(a.y, fmaf(zz.y, s.y, t.y) > 0.f ? gg.y : 0.f, b.y));
+        o.z = fmaf(cq.z, zz.z, fmaf(a.z, fmaf(zz.z, s.z, t.z) > 0.f ? gg.z : 0.f, b.z));
+        o.w = fmaf(cq.w, zz.w, fmaf(a.w, fmaf(zz.w, s.w, t.w) > 0.f ? gg.w : 0.f, b.w));
+        return o;
     }
 };
 
@@ -140,12 +165,13 @@ __device__ __forceinline__ void gemm_rows(const LA &la, const WeightIn &lb, long
     // A: 128 rows x 16 k = 512 float4; thread -> (row = q / 4, kq = q % 4) for q = tid, tid + 256
     // B: NT columns x 16 k = NT * 4 float4
     constexpr int BQ = (NT * 4 + TG_THREADS - 1) / TG_THREADS;
-    float4 ra[2], rb[BQ];
-    auto load = [&](int k0) {
+    typename LA::Raw ra[2];
+    float4 rb[BQ];
+    auto load = [&](int k0) {  // long-latency loads only (see ActIn::raw)
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int q = tid + u * TG_THREADS;
-            ra[u] = la.four(m0 + (q >> 2), k0 + 4 * (q & 3));
+            ra[u] = la.raw(m0 + (q >> 2), k0 + 4 * (q & 3));
         }
 #pragma unroll
         for (int u = 0; u < BQ; ++u) {
@@ -153,13 +179,14 @@ __device__ __forceinline__ void gemm_rows(const LA &la, const WeightIn &lb, long
             rb[u] = q < NT * 4 ? lb.four(n0 + (q >> 2), k0 + 4 * (q & 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    auto store = [&](int buf) {
+    auto store = [&](int buf, int k0) {
         float *a = As + buf * TG_KC * S::AS, *b = Bs + buf * TG_KC * S::BS;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int q = tid + u * TG_THREADS, r = q >> 2, kq = 4 * (q & 3);
-            a[(kq + 0) * S::AS + r] = ra[u].x; a[(kq + 1) * S::AS + r] = ra[u].y;
-            a[(kq + 2) * S::AS + r] = ra[u].z; a[(kq + 3) * S::AS + r] = ra[u].w;
+            const float4 v = la.finish(ra[u], m0 + r, k0 + kq);
+            a[(kq + 0) * S::AS + r] = v.x; a[(kq + 1) * S::AS + r] = v.y;
+            a[(kq + 2) * S::AS + r] = v.z; a[(kq + 3) * S::AS + r] = v.w;
         }
 #pragma unroll
         for (int u = 0; u < BQ; ++u) {
@@ -177,12 +204,12 @@ __device__ __forceinline__ void gemm_rows(const LA &la, const WeightIn &lb, long
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const int nchunks = (K + TG_KC - 1) / TG_KC;
     load(0);
-    store(0);
+    store(0, 0);
     __syncthreads();
     for (int c = 0; c < nchunks; ++c) {
         if (c + 1 < nchunks) load((c + 1) * TG_KC);
         mma_chunk<NT>(As + (c & 1) * TG_KC * S::AS, Bs + (c & 1) * TG_KC * S::BS, acc, ty, tx);
-        if (c + 1 < nchunks) store((c + 1) & 1);
+        if (c + 1 < nchunks) store((c + 1) & 1, (c + 1) * TG_KC);
         __syncthreads();
     }
 }
@@ -194,7 +221,7 @@ train_linear_fwd_kernel(ActIn xin, WeightIn w, const float *__restrict__ bias, f
                         long long tiles) {
     using S = TileShape<NT>;
     extern __shared__ __align__(16) float smem[];
-    __shared__ float csum[2][NT];
+    __shared__ float cpart[2][TG_THREADS / 32][NT];  // per-warp partial sums of the tile's columns (sum, sum of squares)
     const int cout = w.n_total, cin = w.k_total;
     const int tid = threadIdx.x, tx = tid % S::TX, ty = tid / S::TX;
     const int ntn = (cout + NT - 1) / NT;
@@ -204,8 +231,6 @@ train_linear_fwd_kernel(ActIn xin, WeightIn w, const float *__restrict__ bias, f
         const long long m0 = mt * TG_M;
         float acc[S::TM][4];
         gemm_rows<NT>(xin, w, m0, n0, cin, smem, acc);
-        if (tid < 2 * NT) csum[tid / NT][tid % NT] = 0.f;
-        __syncthreads();
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
         const int col = n0 + tx * 4;
         float bv[4];
@@ -232,13 +257,31 @@ train_linear_fwd_kernel(ActIn xin, WeightIn w, const float *__restrict__ bias, f
                     if (col + j < cout) z[r * cout + col + j] = v[j];
             }
         }
+        // column sums: lanes of a warp that share tx (32 / TX rows of threads) by shuffles, the 8 warps through shared
+        // memory (shared-memory float atomics compile to compare-and-swap loops: 8-way contended, they were 7 % of the
+        // kernel's instructions and a quarter of its stall samples)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            atomicAdd(&csum[0][tx * 4 + j], s1[j]);
-            atomicAdd(&csum[1][tx * 4 + j], s2[j]);
+#pragma unroll
+            for (int o = S::TX; o < 32; o <<= 1) {
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+            }
+        }
+        if ((tid & 31) < S::TX) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                cpart[0][tid >> 5][tx * 4 + j] = s1[j];
+                cpart[1][tid >> 5][tx * 4 + j] = s2[j];
+            }
         }
         __syncthreads();
-        if (tid < 2 * NT && n0 + (tid % NT) < cout) atomicAdd(stats + (size_t)(tid / NT) * cout + n0 + (tid % NT), (double)csum[tid / NT][tid % NT]);
+        if (tid < 2 * NT && n0 + (tid % NT) < cout) {
+            float t = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < TG_THREADS / 32; ++w8) t += cpart[tid / NT][w8][tid % NT];
+            atomicAdd(stats + (size_t)(tid / NT) * cout + n0 + (tid % NT), (double)t);
+        }
         __syncthreads();
     }
 }
@@ -332,43 +375,51 @@ train_linear_bwd_weight_kernel(DzIn dz, ActIn xin, float *__restrict__ dw, long 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
             constexpr int AQ = (MT * 4 + TG_THREADS - 1) / TG_THREADS;
-            float4 ra[AQ], rb[BQ];
+            DzIn::Raw ra[AQ];
+            ActIn::Raw rb[BQ];
             // A chunk: 16 rows x MT co = MT * 4 float4: q -> (k = q / (MT / 4), co4 = q % (MT / 4));  B chunk: 16 rows x NT ci
-            auto load = [&](long long r0) {
+            // rows past the CTA's range are read as rows past the end of the matrix (zeros)
+            auto load = [&](long long r0) {  // long-latency loads only (see ActIn::raw)
 #pragma unroll
                 for (int u = 0; u < AQ; ++u) {
                     const int q = tid + u * TG_THREADS;
                     const long long r = r0 + q / (MT / 4);
-                    ra[u] = (q < MT * 4 && r < r_end) ? dz.four(r, m0 + 4 * (q % (MT / 4))) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q < MT * 4) ra[u] = dz.raw(r < r_end ? r : dz.rows, m0 + 4 * (q % (MT / 4)));
                 }
 #pragma unroll
                 for (int u = 0; u < BQ; ++u) {
                     const int q = tid + u * TG_THREADS;
                     const long long r = r0 + q / (NT / 4);
-                    rb[u] = (q < NT * 4 && r < r_end) ? xin.four(r, n0 + 4 * (q % (NT / 4))) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q < NT * 4) rb[u] = xin.raw(r < r_end ? r : xin.rows, n0 + 4 * (q % (NT / 4)));
                 }
             };
-            auto store = [&](int buf) {
+            auto store = [&](int buf, long long r0) {
                 float *a = As + buf * TG_KC * S::AS, *b = Bs + buf * TG_KC * S::BS;
 #pragma unroll
                 for (int u = 0; u < AQ; ++u) {
                     const int q = tid + u * TG_THREADS;
-                    if (q < MT * 4) *reinterpret_cast<float4 *>(a + (q / (MT / 4)) * S::AS + 4 * (q % (MT / 4))) = ra[u];
+                    const long long r = r0 + q / (MT / 4);
+                    if (q < MT * 4)
+                        *reinterpret_cast<float4 *>(a + (q / (MT / 4)) * S::AS + 4 * (q % (MT / 4))) =
+                            dz.finish(ra[u], r < r_end ? r : dz.rows, m0 + 4 * (q % (MT / 4)));
                 }
 #pragma unroll
                 for (int u = 0; u < BQ; ++u) {
                     const int q = tid + u * TG_THREADS;
-                    if (q < NT * 4) *reinterpret_cast<float4 *>(b + (q / (NT / 4)) * S::BS + 4 * (q % (NT / 4))) = rb[u];
+                    const long long r = r0 + q / (NT / 4);
+                    if (q < NT * 4)
+                        *reinterpret_cast<float4 *>(b + (q / (NT / 4)) * S::BS + 4 * (q % (NT / 4))) =
+                            xin.finish(rb[u], r < r_end ? r : xin.rows, n0 + 4 * (q % (NT / 4)));
                 }
             };
             __syncthreads();  // the previous output tile's last chunk has been consumed
             load(r_begin);
-            store(0);
+            store(0, r_begin);
             __syncthreads();
             for (int c = 0; c < nchunks; ++c) {
                 if (c + 1 < nchunks) load(r_begin + (long long)(c + 1) * TG_KC);
                 mma_chunk<NT, MT>(As + (c & 1) * TG_KC * S::AS, Bs + (c & 1) * TG_KC * S::BS, acc, ty, tx);
-                if (c + 1 < nchunks) store((c + 1) & 1);
+                if (c + 1 < nchunks) store((c + 1) & 1, r_begin + (long long)(c + 1) * TG_KC);
                 __syncthreads();
             }
 #pragma unroll
