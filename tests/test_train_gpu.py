@@ -112,3 +112,58 @@ def test_graphed_train_step_reproduces_the_eager_loop(cuda):
     assert graphed == eager, (graphed, eager)
     for (k, a), (_, b) in zip(net_e.state_dict().items(), net_g.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+def test_multiview_msg_parallel_branches_match_the_sequential_chains(cuda):
+    """PointNet2Multiview2Msg in training mode: geometry and image-feature chains on two streams with ONE sampling for both
+    (models._MultiviewStackBase._two_branches) and the scales of every multi-scale module on streams of their own, against
+    the reference's order (one chain after the other, each sampling on
+    its own), eager and replayed as CUDA graphs; fixed-order backwards: identical losses and weights."""
+    import torch.nn.functional as F
+    from pn2_b200 import pointnet2_utils as pu
+    from pn2_b200.models import GraphedTrainStep, PointNet2Multiview2Msg
+    B, N = 2, 2048
+    pts = torch.from_numpy(scenes.scannet_batch(41, B, N)).to(cuda)
+    xyz = pts[:, :, :3].permute(0, 2, 1).contiguous()
+    img = torch.randn(B, 128, N, device=cuda, generator=torch.Generator(device=cuda).manual_seed(1))
+    target = (pts[:, :, 2].clamp(0, 2.69) / 2.7 * 20).long() + 1
+
+    def loss_fn(logits, tgt):
+        return F.cross_entropy(logits.reshape(-1, 21), tgt.reshape(-1), ignore_index=0)
+
+    def run(parallel, graphed):
+        torch.manual_seed(5)
+        net = PointNet2Multiview2Msg(21).to(cuda).train()
+        net.parallel_branches = parallel
+        for m in net.modules():
+            if hasattr(m, "parallel_scales"):
+                m.parallel_scales = parallel  # the scales of every multi-scale module on streams of their own as well
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4, capturable=True)
+        losses = []
+        if graphed:
+            stepper = GraphedTrainStep(net, opt, loss_fn, xyz, img, target)
+            losses = [float(stepper.step(xyz, img, target)) for _ in range(2)]
+        else:
+            for _ in range(2):
+                opt.zero_grad(set_to_none=True)
+                loss = loss_fn(net(xyz, img), target)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss.detach()))
+        torch.cuda.synchronize()
+        return losses, {k: v.clone() for k, v in net.state_dict().items()}
+
+    prev = pu.set_deterministic(True)
+    try:
+        seq = run(False, False)
+        par = run(True, False)
+        par_graph = run(True, True)
+    finally:
+        pu.set_deterministic(prev)
+    for name, other in (("two streams, eager", par), ("two streams, graphed", par_graph)):
+        assert other[0] == seq[0], (name, other[0], seq[0])
+        for k in seq[1]:
+            assert torch.equal(seq[1][k], other[1][k]), (name, k)
