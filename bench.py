@@ -672,11 +672,13 @@ def run_ours(args):
                     _pu.set_mlp_precision(prev)
             b2 = [d[:2].contiguous() for d in devs]   # BASELINE configs[0]: batch 2
             lat = one_at_a_time_ms(model, b2, 20)
-            thr = pipelined_value(model, b2, max(20, min(args.steps, 100)), depth)
+            # a batch of 2 keeps two SMs busy in its sampling phase: four times as many graph instances in flight as for batch 32
+            depth_b2 = 4 * depth
+            thr = pipelined_value(model, b2, max(4 * depth_b2, min(args.steps, 200)), depth_b2)
             legs["batch2"] = {"latency_ms": lat, "value_one_at_a_time": world * 2 / lat * 1e3, "value": world * 2 / thr * 1e3, "unit": "scenes/s",
                               "ms_per_step": thr,
                               "what": "BASELINE configs[0] shape: batch 2 x 8192 points per GPU.  latency_ms = one CUDA-graph forward at a "
-                                      "time, L2 flushed in between; value = %d graphs of batch 2 in flight" % depth}
+                                      "time, L2 flushed in between; value = %d graphs of batch 2 in flight" % depth_b2}
 
     # ---- BASELINE config[1]: the MSG train step, scenes sharded over the ranks, one gradient all-reduce -----------------
     train_ms, train_eager_ms = 0.0, 0.0
