@@ -87,6 +87,13 @@ def test_fused_path_only_for_eval_fp32_cuda_and_supported_shapes():
     assert not pu._fp32_supported(folded, 7, 8)           # channel mismatch
     deep = pu.PointNetSetAbstraction(16, 0.3, 8, 6, [8] * 7, False).eval()
     assert len(deep.mlp_convs) > _lib.PN2_MAX_LAYERS and not deep._fused_ok(x, f)
+    # shared-memory plan of the fp32 kernel (row_mlp.cu make_layout): layers of one n-tile run in place, so a stack of
+    # <= 128-wide layers needs ONE activation buffer (2512 x 20 floats at the 16-row tile: fits); a 256-wide layer has two
+    # n-tiles and needs the second buffer as well (does not fit), as does a wider input
+    wide_in = lambda widths, c0=2500: pu.PointNetFeaturePropagation(c0, widths).eval().folded()
+    assert pu._fp32_supported(wide_in([128, 128]), 2500, 0)
+    assert not pu._fp32_supported(wide_in([256, 128]), 2500, 0)
+    assert not pu._fp32_supported(wide_in([128, 128], 3000), 3000, 0)
 
 
 def test_dtype_checks_refuse_reinterpretation():
