@@ -97,7 +97,8 @@ def test_sa_msg_fused_matches_reference_modules(cuda, precision):
 
 
 FP_CASES = [(768, [256, 256], 64, 16, 256, 512), (131, [128, 128, 128], 4096, 512, 3, 128), (128, [128, 64], 500, 100, 0, 128),
-            (20, [32], 300, 1, 4, 16)]
+            (20, [32], 300, 1, 4, 16),
+            (2500, [128, 128], 80, 16, 452, 2048)]  # fp32 kernel: 16-row tiles, ONE 200 KB activation buffer (in-place layers)
 
 
 @pytest.mark.parametrize("cin,mlp,N,S,D1,D2", FP_CASES)
